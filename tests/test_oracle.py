@@ -1,0 +1,196 @@
+"""Pins the CPU oracle (no GPU needed).
+
+The reference tree holds no tests or golden vectors, so the oracle
+is pinned by: the recollected upstream known-answer literals on the 5-point "simple1"
+mesh, Qhull as an independent topology oracle, scipy's direct solver, and invariants.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import scipy.spatial
+
+import oracle
+from oracle.meshtri import MeshTri, canonical_cells, DegenerateCellsError
+from optimesh_b200 import generators as G
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def norms(p):
+    return np.abs(p).sum(), np.sqrt((p * p).sum()), np.abs(p).max()
+
+
+def test_simple1_lloyd_known_answer():
+    X, cells = G.SIMPLE1
+    p, c = oracle.optimize_points_cells(X, cells, "lloyd", 1.0e-2, 100)
+    n1, n2, ninf = norms(p)
+    # upstream literal, rel. tol 1e-12 as upstream
+    assert abs(n1 - 4.986335452622451) <= 1e-12 * n1
+    assert abs(n2 - 2.1181412069258942) <= 1e-12 * n2
+    assert ninf == 1.0
+
+
+def test_simple1_lloyd_iterates():
+    X, cells = G.SIMPLE1
+    expect = [0.43194444, 0.45420143, 0.46933845, 0.47952039, 0.48633545]
+    mesh = MeshTri(X, cells)
+    for k in range(5):
+        oracle.driver.step(mesh, "lloyd")
+        assert abs(mesh.points[4, 0] - expect[k]) < 5e-9
+        assert abs(mesh.points[4, 1] - 0.5) < 1e-15
+
+
+@pytest.mark.parametrize("method", ["cpt-fixed-point", "cpt-linear-solve", "odt-fixed-point"])
+def test_simple1_cpt_odt_known_answer(method):
+    X, cells = G.SIMPLE1
+    p, c = oracle.optimize_points_cells(X, cells, method, 1.0e-2, 100)
+    n1, n2, ninf = norms(p)
+    assert abs(n1 - 5.0) < 1e-12
+    assert abs(n2 - 2.1213203435596424) < 1e-12
+    assert ninf == 1.0
+
+
+def test_simple1_block_diagonal_converges_faster():
+    X, cells = G.SIMPLE1
+    steps = {}
+    for m in ("lloyd", "cvt-block-diagonal"):
+        mesh = MeshTri(X, cells)
+        steps[m] = [oracle.optimize(MeshTri(X, cells), m, tol, 100) for tol in (1e-2, 1e-3, 1e-5)]
+    assert steps["lloyd"] == [5, 10, 22]
+    assert steps["cvt-block-diagonal"] == [3, 5, 10]
+
+
+def test_method_name_normaliser():
+    assert oracle.normalize_method_name("CVT (block-diagonal)") == "cvt-block-diagonal"
+    assert oracle.normalize_method_name("Lloyd") == "lloyd"
+    assert oracle.normalize_method_name("CVT (full)") == "cvt-full"
+    with pytest.raises(NotImplementedError):
+        oracle.get_new_points(MeshTri(*G.SIMPLE1), "CVT (full)")
+    with pytest.raises(KeyError):
+        oracle.get_new_points(MeshTri(*G.SIMPLE1), "nope")
+
+
+def test_control_volumes_sum_to_area():
+    pts, cells = G.disk(60, 1)
+    m = MeshTri(pts, cells)
+    assert abs(m.control_volumes.sum() - m.cell_volumes.sum()) < 1e-12
+    assert np.allclose(2 * m.cell_partitions.sum(axis=0), m.cell_volumes, rtol=1e-12)
+
+
+def test_circumcenter_equidistant_and_quality():
+    pts, cells = G.disk(40, 2)
+    m = MeshTri(pts, cells)
+    cc = m.cell_circumcenters
+    d = np.stack([np.linalg.norm(pts[cells[:, k]] - cc, axis=1) for k in range(3)])
+    assert np.allclose(d[0], d[1], rtol=1e-9) and np.allclose(d[0], d[2], rtol=1e-9)
+    assert np.allclose(d[0], m.cell_circumradius, rtol=1e-9)
+    assert np.allclose(m.q_radius_ratio, 2 * m.cell_inradius / m.cell_circumradius, rtol=1e-10)
+    eq = MeshTri(np.array([[0, 0], [1, 0], [0.5, np.sqrt(3) / 2]]), np.array([[0, 1, 2]]))
+    assert abs(eq.q_radius_ratio[0] - 1.0) < 1e-14
+    assert np.allclose(eq.angles, np.pi / 3)
+
+
+def test_hex_patch_is_fixed_point():
+    # regular hexagonal patch: the centre vertex is a fixed point of every method
+    t = np.arange(6) * np.pi / 3
+    pts = np.concatenate([[[0.0, 0.0]], np.stack([np.cos(t), np.sin(t)], axis=1)])
+    cells = np.array([[0, 1 + k, 1 + (k + 1) % 6] for k in range(6)])
+    for meth in oracle.METHODS:
+        new = oracle.get_new_points(MeshTri(pts, cells), meth)
+        assert np.allclose(new[0], 0.0, atol=1e-14), meth
+
+
+def test_degenerate_cell_raises():
+    pts = np.array([[0.0, 0.0], [1.0, 0.0], [2.0, 0.0]])
+    with pytest.raises(DegenerateCellsError):
+        MeshTri(pts, np.array([[0, 1, 2]])).cell_volumes
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_flips_reach_qhull_delaunay(seed):
+    # Delaunay mesh, interior points jittered -> flips must restore Qhull's triangulation
+    pts, cells = G.disk(60, seed)
+    pts, cells = oracle.optimize_points_cells(pts, cells, "cpt-fixed-point", 0.0, 5)
+    rs = np.random.RandomState(seed)
+    mesh = MeshTri(pts, cells)
+    bnd = mesh.is_boundary_point
+    pts2 = pts.copy()
+    rmin = np.full(len(pts), np.inf)
+    np.minimum.at(rmin, cells.reshape(-1), np.repeat(mesh.cell_inradius, 3))
+    step = rs.uniform(-1, 1, size=pts.shape) * (0.45 * rmin / np.sqrt(2))[:, None]
+    pts2[~bnd] += step[~bnd]
+    mesh = MeshTri(pts2, cells)
+    assert np.all(_signed_areas(pts2, cells) * np.sign(_signed_areas(pts, cells)) > 0)
+    nflips, nrounds = mesh.flip_until_delaunay()
+    assert nflips > 0
+    assert mesh.num_delaunay_violations() == 0
+    ref = scipy.spatial.Delaunay(pts2).simplices
+    assert np.array_equal(canonical_cells(mesh.cells("points")), canonical_cells(ref))
+
+
+def _signed_areas(p, c):
+    a, b, cc = p[c[:, 0]], p[c[:, 1]], p[c[:, 2]]
+    return 0.5 * ((b[:, 0] - a[:, 0]) * (cc[:, 1] - a[:, 1]) - (b[:, 1] - a[:, 1]) * (cc[:, 0] - a[:, 0]))
+
+
+def test_sphere_flips_match_convex_hull():
+    pts, cells = G.tetra_sphere(8)
+    assert pts.shape[0] == 2 * 64 + 2 and cells.shape[0] == 4 * 64
+    rs = np.random.RandomState(0)
+    p2 = pts + rs.normal(scale=0.03, size=pts.shape)
+    p2 /= np.linalg.norm(p2, axis=1)[:, None]
+    mesh = MeshTri(p2, cells)
+    mesh.flip_until_delaunay()
+    hull = scipy.spatial.ConvexHull(p2).simplices
+    assert np.array_equal(canonical_cells(mesh.cells("points")), canonical_cells(hull))
+
+
+def test_cpt_linear_solve_is_harmonic():
+    pts, cells = G.square(12, 0.25, 0)
+    mesh = MeshTri(pts, cells)
+    new = oracle.get_new_points(mesh, "cpt-linear-solve")
+    bnd = mesh.is_boundary_point
+    assert np.allclose(new[bnd], pts[bnd], atol=1e-14)
+    # interior vertices are the mean of their neighbours
+    nbrs = [set() for _ in range(len(pts))]
+    for a, b, c in cells:
+        nbrs[a] |= {b, c}
+        nbrs[b] |= {a, c}
+        nbrs[c] |= {a, b}
+    for i in np.nonzero(~bnd)[0]:
+        assert np.allclose(new[i], new[list(nbrs[i])].mean(axis=0), atol=1e-12)
+
+
+def test_generators_sizes():
+    pts, cells = G.disk(120, 0)
+    assert pts.shape == (1383, 2) and cells.shape == (2643, 3)
+    pts, cells = G.square(10)
+    assert pts.shape == (100, 2) and cells.shape == (162, 3)
+    assert np.all(_signed_areas(pts, cells) > 0)
+    pts, cells = G.disk_mapped_grid(40)
+    assert np.all(_signed_areas(pts, cells) > 0)
+    m = MeshTri(pts, cells)
+    assert m.is_boundary_point.sum() == 4 * 39
+    assert np.allclose(np.linalg.norm(pts[m.is_boundary_point], axis=1), 1.0)
+    pts, cells = G.tetra_sphere(5)
+    m = MeshTri(pts, cells)
+    assert not m.is_boundary_point.any()
+    assert abs(m.cell_volumes.sum() - 4 * np.pi) < 0.15 * 4 * np.pi
+
+
+def test_config1_trajectory_golden():
+    """Config 1 (BASELINE.json configs[0]): Lloyd omega=1, disk(120), 50 steps, tol 1e-5.
+    Golden produced by tests/golden/make_golden.py from this oracle."""
+    with open(os.path.join(GOLDEN, "config1_lloyd.json")) as f:
+        gold = json.load(f)
+    pts, cells = G.disk(120, 0)
+    log = []
+    p, c = oracle.optimize_points_cells(pts, cells, "lloyd", 1.0e-5, 50, log=log)
+    assert len(log) == gold["steps"] == 50
+    assert [l["n_flips"] for l in log] == gold["n_flips"]
+    assert [l["n_limited"] for l in log] == gold["n_limited"]
+    assert np.allclose(norms(p), gold["norms"], rtol=1e-12)
+    ah, qh, s = oracle.stats(MeshTri(p, c))
+    assert ah.tolist() == gold["angle_hist"] and qh.tolist() == gold["q_hist"]
