@@ -1,0 +1,157 @@
+/* optimesh_b200 -- C-ABI of the B200-native smoothing step.
+ *
+ * Drop-in boundary for ONE hot path of meshpro/optimesh: the per-step smoothing update
+ * (relaxed Lloyd, CVT block-diagonal, CPT fixed-point / linear-solve, ODT fixed-point)
+ * plus the flip-until-Delaunay pass that follows every step.  The reference is pure
+ * Python (no FFI of its own); the entry points below are what a ctypes binding under
+ * the reference's Python API would call.  Reference interface replaced by each entry
+ * point is cited as /root/reference/README.md:line (the mounted tree holds only the
+ * README; the arithmetic follows SURVEY.md Appendix A).
+ *
+ * Conventions: every function returns 0 on success, non-zero on error; the message is
+ * available from om_last_error() (thread-local).  No C++ exception crosses the
+ * boundary.  The caller owns all host buffers; the library owns all device memory
+ * inside the handle.  One handle = one mesh on one GPU, one CUDA stream; a handle must
+ * not be used from two threads at once.  There is no CPU fallback: without a CUDA
+ * device om_create fails.
+ */
+#ifndef OPTIMESH_B200_H
+#define OPTIMESH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct om_handle om_handle;
+
+/* method ids (names: README.md:80, :90, :104) */
+enum {
+  OM_LLOYD = 0,              /* --method lloyd                 README.md:80  */
+  OM_CVT_BLOCK_DIAGONAL = 1, /* --method cvt-block-diagonal    README.md:80  */
+  OM_CPT_FIXED_POINT = 2,    /* --method cpt-fixed-point       README.md:90  */
+  OM_ODT_FIXED_POINT = 3,    /* --method odt-fixed-point       README.md:104 */
+  OM_CPT_LINEAR_SOLVE = 4    /* --method cpt-linear-solve      README.md:90  */
+};
+
+/* error codes */
+enum {
+  OM_OK = 0,
+  OM_ERR_CUDA = 1,
+  OM_ERR_ARG = 2,
+  OM_ERR_DEGENERATE = 3,   /* zero-area cell (upstream: "Degenerate cells.") */
+  OM_ERR_NONMANIFOLD = 4,  /* an edge with more than two adjacent cells, or bad topology */
+  OM_ERR_INDEX = 5,        /* cell refers to a vertex outside [0, N) */
+  OM_ERR_NOT_CONVERGED = 6
+};
+
+/* creation flags */
+enum {
+  OM_RENUMBER = 1 /* spatially (Morton) renumber vertices and cells internally; the
+                     numbering seen through the API is always the caller's */
+};
+
+typedef struct om_step_stats {
+  double max_diff2;      /* max_i |omega (new_i - x_i)|^2, before the step limiter   */
+  int64_t n_limited;     /* vertices whose step was shortened by the limiter          */
+  int64_t n_flips;       /* edge flips in the flip-until-Delaunay pass after the step */
+  int32_t n_flip_rounds; /* rounds that flipped at least one edge                     */
+  int32_t flip_cap_hit;  /* 1 if max rounds were exhausted with violations left       */
+  int32_t is_final;      /* max_diff2 < tol^2 (the caller adds "k >= max_num_steps")  */
+  int32_t solver_iters;  /* PCG iterations (cpt-linear-solve), else 0                 */
+  int32_t surface_sweeps;/* Newton sweeps of the implicit-surface projection          */
+  int32_t reserved;
+} om_step_stats;
+
+const char* om_last_error(void);
+
+/* number of visible CUDA devices */
+int om_device_count(int* n);
+
+/* Builds the device mesh from host arrays -- replaces meshplex.MeshTri(points, cells)
+ * (README.md:131) under optimize_points_cells (README.md:124-126).
+ *   points_host: N x dim float64, C-contiguous (dim 2 or 3)
+ *   cells_host : C x 3 integers of cells_itemsize bytes (4 or 8)
+ *   stream     : a cudaStream_t to run on, or NULL for a private stream
+ * Does: upload, optional renumbering, half-edge twin table, boundary flags.      */
+int om_create(om_handle** h, int device, void* stream, int64_t N, int dim, int64_t C,
+              const double* points_host, const void* cells_host, int cells_itemsize,
+              int flags);
+/* Same, inputs already resident in device memory (same layouts). */
+int om_create_device(om_handle** h, int device, void* stream, int64_t N, int dim, int64_t C,
+                     const double* points_dev, const void* cells_dev, int cells_itemsize,
+                     int flags);
+int om_destroy(om_handle* h);
+
+/* method + omega relaxation: optimize(..., method, omega=...) README.md:80, :124-126 */
+int om_set_method(om_handle* h, int method, double omega);
+/* step limiter of the driver loop on/off (default on) */
+int om_set_limiter(om_handle* h, int on);
+/* implicit surface, README.md:146-176.  kind 0: none; kind 1: sphere
+ * f(x) = R^2 - |x - c|^2, params = {cx, cy, cz, R} (the README's Sphere is {0,0,0,1}) */
+int om_set_surface(om_handle* h, int kind, double tol, const double* params, int max_sweeps);
+/* PCG controls for cpt-linear-solve */
+int om_set_solver(om_handle* h, double rtol, int max_iter);
+
+/* mesh.flip_until_delaunay() of the driver loop (meshplex) */
+int om_flip_until_delaunay(om_handle* h, double tol, int max_rounds, int64_t* n_flips,
+                           int32_t* n_rounds, int32_t* cap_hit);
+
+/* One iteration of the optimize() loop (README.md:131-132): new points, pin boundary,
+ * omega, limiter, surface projection, then flip-until-Delaunay. */
+int om_step(om_handle* h, double tol, om_step_stats* out);
+/* Only the point update (no surface projection, no flips): for callers that project
+ * on the host (generic implicit_surface objects) and for single-step parity tests. */
+int om_update_points(om_handle* h, double tol, om_step_stats* out);
+/* Projection alone (built-in surfaces). */
+int om_project(om_handle* h, int32_t* sweeps);
+/* The whole loop of optimize(mesh, method, tol, max_num_steps) on the device. */
+int om_run(om_handle* h, double tol, int64_t max_num_steps, int64_t* steps_done,
+           om_step_stats* last);
+
+/* optimesh.get_new_points(mesh, method) (README.md:141): un-relaxed, un-limited target
+ * positions, N x dim, caller numbering. */
+int om_new_points(om_handle* h, double* out_host);
+
+/* cpt-linear-solve alone: solve the Dirichlet graph Laplacian for all coordinates and
+ * overwrite the interior points with the solution. */
+int om_solve_graph_laplacian(om_handle* h, double rtol, int max_iter, int32_t* iters,
+                             double* rel_residual);
+
+/* print_stats (README.md:55-60): 72 angle bins of 2.5 deg, 40 quality bins of 0.025,
+ * summary8 = {angle min, max, avg, std, q min, avg, max, std}. */
+int om_stats(om_handle* h, int64_t* angle_hist72, int64_t* q_hist40, double* summary8);
+
+/* mesh.points / mesh.cells (README.md:133), caller numbering and cell row order */
+int om_get_points(om_handle* h, double* out_host);
+int om_set_points(om_handle* h, const double* in_host);
+int om_get_cells(om_handle* h, void* out_host, int itemsize);
+int om_get_boundary_flags(om_handle* h, uint8_t* out_host);
+
+/* Raw device pointers (internal numbering/layout), for zero-copy interop:
+ *   points: N x pd float64 (pd = 2 for dim 2, 4 for dim 3), cells: C x int4 (.w = caller
+ *   cell row), perm: internal -> caller vertex id (NULL if identity). */
+int om_device_ptrs(om_handle* h, double** points, int32_t** cells4, int32_t** perm,
+                   int32_t* point_stride);
+
+/* Halo support for meshes partitioned across GPUs (one process per GPU; the exchange
+ * itself is done by the caller with NCCL):
+ *   om_pack_points  : buf[i] = x[idx[i]] for i < n   (device buffers, caller ids)
+ *   om_unpack_points: x[idx[i]] = buf[i]
+ *   idx_dev are caller vertex ids resident on the device. */
+int om_pack_points(om_handle* h, const int32_t* idx_dev, int64_t n, double* buf_dev);
+int om_unpack_points(om_handle* h, const int32_t* idx_dev, int64_t n, const double* buf_dev);
+/* Vertices listed here are treated as pinned (ghost vertices of a partition). */
+int om_pin_vertices(om_handle* h, const int32_t* idx_host, int64_t n);
+
+/* kernels launched by this handle so far (bench.py's gpu_launches) */
+int om_launch_count(om_handle* h, int64_t* n);
+int om_synchronize(om_handle* h);
+/* stream the handle launches on (cudaStream_t) */
+int om_stream(om_handle* h, void** stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

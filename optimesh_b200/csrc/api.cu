@@ -1,0 +1,538 @@
+// C-ABI of liboptimesh_b200.so (see include/optimesh_b200.h).
+#include <stdarg.h>
+
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+#include "geom.cuh"
+
+static thread_local std::string g_err;
+
+void om_set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+}
+
+int om_fetch_scalars(om_handle* h) {
+  CUDA_TRY(cudaMemcpyAsync(h->hs, h->ds, sizeof(DevScalars), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return OM_OK;
+}
+
+int om_check_dev_err(om_handle* h) {
+  OM_TRY(om_fetch_scalars(h));
+  const int e = h->hs->err;
+  if (!e) return OM_OK;
+  CUDA_TRY(cudaMemsetAsync(&h->ds->err, 0, sizeof(int), h->stream));
+  if (e & OM_DEV_INDEX) {
+    om_set_error("cells refer to vertices outside [0, N)");
+    return OM_ERR_INDEX;
+  }
+  if (e & OM_DEV_DEGENERATE) {
+    om_set_error("Degenerate cells.");
+    return OM_ERR_DEGENERATE;
+  }
+  om_set_error("inconsistent mesh topology (non-manifold edge or broken vertex star)");
+  return OM_ERR_NONMANIFOLD;
+}
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+#define OM_ENTER(h)                              \
+  if (!(h)) {                                    \
+    om_set_error("null handle");                 \
+    return OM_ERR_ARG;                           \
+  }                                              \
+  DeviceGuard _guard((h)->device)
+
+template <int D>
+__global__ void k_export_points(const double* __restrict__ x, const int* __restrict__ perm, int N,
+                                double* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  Vec<D> p = ld_point<D>(x, i);
+  size_t dst = perm ? perm[i] : i;
+#pragma unroll
+  for (int k = 0; k < D; k++) out[dst * D + k] = p.v[k];
+}
+
+template <int D>
+__global__ void k_import_points(const double* __restrict__ in, const int* __restrict__ perm, int N,
+                                double* __restrict__ x) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  size_t src = perm ? perm[i] : i;
+  Vec<D> p;
+#pragma unroll
+  for (int k = 0; k < D; k++) p.v[k] = in[src * D + k];
+  st_point<D>(x, i, p);
+}
+
+template <typename T>
+__global__ void k_export_cells(const int4* __restrict__ cells, const int* __restrict__ perm, int C,
+                               T* __restrict__ out) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  int4 cl = cells[c];
+  size_t row = (size_t)cl.w;
+  out[3 * row] = (T)(perm ? perm[cl.x] : cl.x);
+  out[3 * row + 1] = (T)(perm ? perm[cl.y] : cl.y);
+  out[3 * row + 2] = (T)(perm ? perm[cl.z] : cl.z);
+}
+
+__global__ void k_export_flags(const uint8_t* __restrict__ f, const int* __restrict__ perm, int N,
+                               uint8_t* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) out[perm ? perm[i] : i] = f[i];
+}
+
+template <int D>
+__global__ void k_pack(const double* __restrict__ x, const int* __restrict__ inv,
+                       const int* __restrict__ idx, int64_t n, double* __restrict__ buf) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int v = idx[i];
+  if (inv) v = inv[v];
+  Vec<D> p = ld_point<D>(x, v);
+#pragma unroll
+  for (int k = 0; k < D; k++) buf[i * D + k] = p.v[k];
+}
+
+template <int D>
+__global__ void k_unpack(double* __restrict__ x, const int* __restrict__ inv,
+                         const int* __restrict__ idx, int64_t n, const double* __restrict__ buf) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int v = idx[i];
+  if (inv) v = inv[v];
+  Vec<D> p;
+#pragma unroll
+  for (int k = 0; k < D; k++) p.v[k] = buf[i * D + k];
+  st_point<D>(x, v, p);
+}
+
+__global__ void k_pin(uint8_t* __restrict__ f, const int* __restrict__ inv,
+                      const int* __restrict__ idx, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int v = idx[i];
+  f[inv ? inv[v] : v] = 1;
+}
+
+int create_common(om_handle** out, int device, void* stream, int64_t N, int dim, int64_t C,
+                  const double* points, const void* cells, int itemsize, int flags,
+                  bool inputs_on_device) {
+  if (!out) {
+    om_set_error("null output handle");
+    return OM_ERR_ARG;
+  }
+  *out = nullptr;
+  if (dim != 2 && dim != 3) {
+    om_set_error("points must have 2 or 3 columns, got %d", dim);
+    return OM_ERR_ARG;
+  }
+  if (itemsize != 4 && itemsize != 8) {
+    om_set_error("cells itemsize must be 4 or 8, got %d", itemsize);
+    return OM_ERR_ARG;
+  }
+  if (N < 0 || C < 0 || N >= (1ll << 31) - 1 || C >= (1ll << 29)) {
+    om_set_error("mesh size out of range (N=%lld, C=%lld)", (long long)N, (long long)C);
+    return OM_ERR_ARG;
+  }
+  if ((N > 0 && !points) || (C > 0 && !cells)) {
+    om_set_error("null input array");
+    return OM_ERR_ARG;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    om_set_error("no CUDA device available (%s); optimesh_b200 has no CPU fallback",
+                 cudaGetErrorString(e));
+    return OM_ERR_CUDA;
+  }
+  if (device < 0 || device >= ndev) {
+    om_set_error("device %d out of range (have %d)", device, ndev);
+    return OM_ERR_ARG;
+  }
+  DeviceGuard guard(device);
+  om_handle* h = new om_handle();
+  h->device = device;
+  h->N = N;
+  h->C = C;
+  h->D = dim;
+  h->PD = dim == 2 ? 2 : 4;
+  h->cells_itemsize = itemsize;
+  int rc = OM_OK;
+  auto fail = [&](int code) {
+    om_destroy(h);
+    return code;
+  };
+  if (stream) {
+    h->stream = (cudaStream_t)stream;
+  } else {
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+      om_set_error("cudaStreamCreate failed");
+      return fail(OM_ERR_CUDA);
+    }
+    h->own_stream = true;
+  }
+  const double* pdev = points;
+  const void* cdev = cells;
+  double* pup = nullptr;
+  void* cup = nullptr;
+  if (!inputs_on_device) {
+    const size_t pb = sizeof(double) * (size_t)N * dim, cb = (size_t)itemsize * 3 * (size_t)C;
+    if (cudaMalloc(&pup, std::max<size_t>(pb, 8)) != cudaSuccess ||
+        cudaMalloc(&cup, std::max<size_t>(cb, 8)) != cudaSuccess) {
+      om_set_error("device allocation failed");
+      cudaFree(pup);
+      return fail(OM_ERR_CUDA);
+    }
+    cudaMemcpyAsync(pup, points, pb, cudaMemcpyHostToDevice, h->stream);
+    cudaMemcpyAsync(cup, cells, cb, cudaMemcpyHostToDevice, h->stream);
+    pdev = pup;
+    cdev = cup;
+  }
+  rc = om_setup_mesh(h, pdev, cdev, flags);
+  cudaStreamSynchronize(h->stream);
+  cudaFree(pup);
+  cudaFree(cup);
+  if (rc != OM_OK) return fail(rc);
+  *out = h;
+  return OM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* om_last_error(void) { return g_err.c_str(); }
+
+int om_device_count(int* n) {
+  int c = 0;
+  cudaError_t e = cudaGetDeviceCount(&c);
+  if (n) *n = (e == cudaSuccess) ? c : 0;
+  return OM_OK;
+}
+
+int om_create(om_handle** h, int device, void* stream, int64_t N, int dim, int64_t C,
+              const double* points_host, const void* cells_host, int cells_itemsize, int flags) {
+  return create_common(h, device, stream, N, dim, C, points_host, cells_host, cells_itemsize,
+                       flags, false);
+}
+
+int om_create_device(om_handle** h, int device, void* stream, int64_t N, int dim, int64_t C,
+                     const double* points_dev, const void* cells_dev, int cells_itemsize,
+                     int flags) {
+  return create_common(h, device, stream, N, dim, C, points_dev, cells_dev, cells_itemsize, flags,
+                       true);
+}
+
+int om_destroy(om_handle* h) {
+  if (!h) return OM_OK;
+  DeviceGuard guard(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  cudaFree(h->x);
+  cudaFree(h->xnew);
+  cudaFree(h->cells);
+  cudaFree(h->adj);
+  cudaFree(h->adj_tmp);
+  cudaFree(h->v2c);
+  cudaFree(h->bflag);
+  cudaFree(h->perm);
+  cudaFree(h->inv_perm);
+  cudaFree(h->ce);
+  cudaFree(h->best);
+  cudaFree(h->flip_epoch);
+  cudaFree(h->reloc);
+  cudaFree(h->nbr_ptr);
+  cudaFree(h->nbr_idx);
+  cudaFree(h->nbr_w);
+  cudaFree(h->pcg_buf);
+  cudaFree(h->ds);
+  cudaFree(h->partials);
+  if (h->hs) cudaFreeHost(h->hs);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return OM_OK;
+}
+
+int om_set_method(om_handle* h, int method, double omega) {
+  OM_ENTER(h);
+  if (method < OM_LLOYD || method > OM_CPT_LINEAR_SOLVE) {
+    om_set_error("unknown method id %d", method);
+    return OM_ERR_ARG;
+  }
+  h->method = method;
+  h->omega = omega;
+  return OM_OK;
+}
+
+int om_set_limiter(om_handle* h, int on) {
+  OM_ENTER(h);
+  h->limiter = on ? 1 : 0;
+  return OM_OK;
+}
+
+int om_set_surface(om_handle* h, int kind, double tol, const double* params, int max_sweeps) {
+  OM_ENTER(h);
+  if (kind != 0 && kind != 1) {
+    om_set_error("unknown surface kind %d", kind);
+    return OM_ERR_ARG;
+  }
+  if (kind == 1 && h->D != 3) {
+    om_set_error("the sphere surface needs 3D points");
+    return OM_ERR_ARG;
+  }
+  h->surf_kind = kind;
+  h->surf_tol = tol;
+  if (params) memcpy(h->surf_params, params, 4 * sizeof(double));
+  if (max_sweeps > 0) h->surf_max_sweeps = max_sweeps;
+  return OM_OK;
+}
+
+int om_set_solver(om_handle* h, double rtol, int max_iter) {
+  OM_ENTER(h);
+  h->solver_rtol = rtol;
+  h->solver_max_iter = max_iter;
+  return OM_OK;
+}
+
+int om_flip_until_delaunay(om_handle* h, double tol, int max_rounds, int64_t* n_flips,
+                           int32_t* n_rounds, int32_t* cap_hit) {
+  OM_ENTER(h);
+  return om_flip_impl(h, tol, max_rounds, n_flips, n_rounds, cap_hit);
+}
+
+int om_update_points(om_handle* h, double tol, om_step_stats* out) {
+  OM_ENTER(h);
+  if (out) memset(out, 0, sizeof(*out));
+  return om_update_points_impl(h, tol, out, false, nullptr);
+}
+
+int om_project(om_handle* h, int32_t* sweeps) {
+  OM_ENTER(h);
+  return om_project_impl(h, sweeps);
+}
+
+int om_step(om_handle* h, double tol, om_step_stats* out) {
+  OM_ENTER(h);
+  om_step_stats st;
+  memset(&st, 0, sizeof(st));
+  OM_TRY(om_update_points_impl(h, tol, &st, false, nullptr));
+  OM_TRY(om_project_impl(h, &st.surface_sweeps));
+  OM_TRY(om_flip_impl(h, 0.0, 100, &st.n_flips, &st.n_flip_rounds, &st.flip_cap_hit));
+  if (out) *out = st;
+  return OM_OK;
+}
+
+int om_run(om_handle* h, double tol, int64_t max_num_steps, int64_t* steps_done,
+           om_step_stats* last) {
+  OM_ENTER(h);
+  om_step_stats st;
+  memset(&st, 0, sizeof(st));
+  int64_t nf = 0;
+  int32_t nr = 0, cap = 0;
+  OM_TRY(om_flip_impl(h, 0.0, 100, &nf, &nr, &cap));
+  int64_t k = 0;
+  while (true) {
+    k++;
+    OM_TRY(om_step(h, tol, &st));
+    if (st.is_final || k >= max_num_steps) break;
+  }
+  if (steps_done) *steps_done = k;
+  if (last) *last = st;
+  return OM_OK;
+}
+
+int om_new_points(om_handle* h, double* out_host) {
+  OM_ENTER(h);
+  if (h->N == 0) return OM_OK;
+  double *target = nullptr, *flat = nullptr;
+  CUDA_TRY(cudaMalloc(&target, sizeof(double) * h->N * h->PD));
+  CUDA_TRY(cudaMalloc(&flat, sizeof(double) * h->N * h->D));
+  int rc = om_update_points_impl(h, 0.0, nullptr, true, target);
+  if (rc == OM_OK) {
+    const int B = 256, G = om_grid(h->N, B);
+    if (h->D == 2)
+      OM_LAUNCH(h, k_export_points<2>, G, B, target, h->perm, (int)h->N, flat);
+    else
+      OM_LAUNCH(h, k_export_points<3>, G, B, target, h->perm, (int)h->N, flat);
+    cudaMemcpyAsync(out_host, flat, sizeof(double) * h->N * h->D, cudaMemcpyDeviceToHost,
+                    h->stream);
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) {
+      om_set_error("copy of new points failed: %s", cudaGetErrorString(cudaGetLastError()));
+      rc = OM_ERR_CUDA;
+    }
+  }
+  cudaFree(target);
+  cudaFree(flat);
+  return rc;
+}
+
+int om_solve_graph_laplacian(om_handle* h, double rtol, int max_iter, int32_t* iters,
+                             double* rel_residual) {
+  OM_ENTER(h);
+  OM_TRY(om_pcg_impl(h, rtol, max_iter, iters, rel_residual, h->xnew));
+  std::swap(h->x, h->xnew);
+  return OM_OK;
+}
+
+int om_stats(om_handle* h, int64_t* angle_hist72, int64_t* q_hist40, double* summary8) {
+  OM_ENTER(h);
+  return om_stats_impl(h, angle_hist72, q_hist40, summary8);
+}
+
+int om_get_points(om_handle* h, double* out_host) {
+  OM_ENTER(h);
+  if (h->N == 0) return OM_OK;
+  double* flat = nullptr;
+  CUDA_TRY(cudaMalloc(&flat, sizeof(double) * h->N * h->D));
+  const int B = 256, G = om_grid(h->N, B);
+  if (h->D == 2)
+    OM_LAUNCH(h, k_export_points<2>, G, B, h->x, h->perm, (int)h->N, flat);
+  else
+    OM_LAUNCH(h, k_export_points<3>, G, B, h->x, h->perm, (int)h->N, flat);
+  cudaMemcpyAsync(out_host, flat, sizeof(double) * h->N * h->D, cudaMemcpyDeviceToHost, h->stream);
+  cudaError_t e = cudaStreamSynchronize(h->stream);
+  cudaFree(flat);
+  CUDA_TRY(e);
+  return OM_OK;
+}
+
+int om_set_points(om_handle* h, const double* in_host) {
+  OM_ENTER(h);
+  if (h->N == 0) return OM_OK;
+  double* flat = nullptr;
+  CUDA_TRY(cudaMalloc(&flat, sizeof(double) * h->N * h->D));
+  cudaMemcpyAsync(flat, in_host, sizeof(double) * h->N * h->D, cudaMemcpyHostToDevice, h->stream);
+  const int B = 256, G = om_grid(h->N, B);
+  if (h->D == 2)
+    OM_LAUNCH(h, k_import_points<2>, G, B, flat, h->perm, (int)h->N, h->x);
+  else
+    OM_LAUNCH(h, k_import_points<3>, G, B, flat, h->perm, (int)h->N, h->x);
+  cudaError_t e = cudaStreamSynchronize(h->stream);
+  cudaFree(flat);
+  CUDA_TRY(e);
+  return OM_OK;
+}
+
+int om_get_cells(om_handle* h, void* out_host, int itemsize) {
+  OM_ENTER(h);
+  if (itemsize != 4 && itemsize != 8) {
+    om_set_error("itemsize must be 4 or 8");
+    return OM_ERR_ARG;
+  }
+  if (h->C == 0) return OM_OK;
+  void* flat = nullptr;
+  const size_t bytes = (size_t)itemsize * 3 * h->C;
+  CUDA_TRY(cudaMalloc(&flat, bytes));
+  const int B = 256, G = om_grid(h->C, B);
+  if (itemsize == 4)
+    OM_LAUNCH(h, k_export_cells<int>, G, B, h->cells, h->perm, (int)h->C, (int*)flat);
+  else
+    OM_LAUNCH(h, k_export_cells<long long>, G, B, h->cells, h->perm, (int)h->C, (long long*)flat);
+  cudaMemcpyAsync(out_host, flat, bytes, cudaMemcpyDeviceToHost, h->stream);
+  cudaError_t e = cudaStreamSynchronize(h->stream);
+  cudaFree(flat);
+  CUDA_TRY(e);
+  return OM_OK;
+}
+
+int om_get_boundary_flags(om_handle* h, uint8_t* out_host) {
+  OM_ENTER(h);
+  if (h->N == 0) return OM_OK;
+  uint8_t* flat = nullptr;
+  CUDA_TRY(cudaMalloc(&flat, h->N));
+  OM_LAUNCH(h, k_export_flags, om_grid(h->N, 256), 256, h->bflag, h->perm, (int)h->N, flat);
+  cudaMemcpyAsync(out_host, flat, h->N, cudaMemcpyDeviceToHost, h->stream);
+  cudaError_t e = cudaStreamSynchronize(h->stream);
+  cudaFree(flat);
+  CUDA_TRY(e);
+  return OM_OK;
+}
+
+int om_device_ptrs(om_handle* h, double** points, int32_t** cells4, int32_t** perm,
+                   int32_t* point_stride) {
+  OM_ENTER(h);
+  if (points) *points = h->x;
+  if (cells4) *cells4 = (int32_t*)h->cells;
+  if (perm) *perm = h->perm;
+  if (point_stride) *point_stride = h->PD;
+  return OM_OK;
+}
+
+int om_pack_points(om_handle* h, const int32_t* idx_dev, int64_t n, double* buf_dev) {
+  OM_ENTER(h);
+  if (n == 0) return OM_OK;
+  if (h->D == 2)
+    OM_LAUNCH(h, k_pack<2>, om_grid(n, 256), 256, h->x, h->inv_perm, idx_dev, n, buf_dev);
+  else
+    OM_LAUNCH(h, k_pack<3>, om_grid(n, 256), 256, h->x, h->inv_perm, idx_dev, n, buf_dev);
+  CUDA_TRY(cudaGetLastError());
+  return OM_OK;
+}
+
+int om_unpack_points(om_handle* h, const int32_t* idx_dev, int64_t n, const double* buf_dev) {
+  OM_ENTER(h);
+  if (n == 0) return OM_OK;
+  if (h->D == 2)
+    OM_LAUNCH(h, k_unpack<2>, om_grid(n, 256), 256, h->x, h->inv_perm, idx_dev, n, buf_dev);
+  else
+    OM_LAUNCH(h, k_unpack<3>, om_grid(n, 256), 256, h->x, h->inv_perm, idx_dev, n, buf_dev);
+  CUDA_TRY(cudaGetLastError());
+  return OM_OK;
+}
+
+int om_pin_vertices(om_handle* h, const int32_t* idx_host, int64_t n) {
+  OM_ENTER(h);
+  if (n == 0) return OM_OK;
+  int* d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, sizeof(int) * n));
+  cudaMemcpyAsync(d, idx_host, sizeof(int) * n, cudaMemcpyHostToDevice, h->stream);
+  OM_LAUNCH(h, k_pin, om_grid(n, 256), 256, h->bflag, h->inv_perm, d, n);
+  cudaError_t e = cudaStreamSynchronize(h->stream);
+  cudaFree(d);
+  CUDA_TRY(e);
+  h->nbr_valid = false;
+  return OM_OK;
+}
+
+int om_launch_count(om_handle* h, int64_t* n) {
+  OM_ENTER(h);
+  if (n) *n = h->launches;
+  return OM_OK;
+}
+
+int om_synchronize(om_handle* h) {
+  OM_ENTER(h);
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return OM_OK;
+}
+
+int om_stream(om_handle* h, void** stream) {
+  OM_ENTER(h);
+  if (stream) *stream = (void*)h->stream;
+  return OM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,118 @@
+// Shared declarations for the optimesh_b200 device library (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/optimesh_b200.h"
+
+#define OM_NONE_CELL 0x7fffffff
+
+// ---------------------------------------------------------------- error plumbing
+void om_set_error(const char* fmt, ...);
+
+#define CUDA_TRY(expr)                                                              \
+  do {                                                                              \
+    cudaError_t _e = (expr);                                                        \
+    if (_e != cudaSuccess) {                                                        \
+      om_set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__,    \
+                   __LINE__, cudaGetErrorString(_e));                               \
+      return OM_ERR_CUDA;                                                           \
+    }                                                                               \
+  } while (0)
+
+#define OM_TRY(expr)            \
+  do {                          \
+    int _r = (expr);            \
+    if (_r != OM_OK) return _r; \
+  } while (0)
+
+// error bits raised by kernels
+enum { OM_DEV_DEGENERATE = 1, OM_DEV_NONMANIFOLD = 2, OM_DEV_INDEX = 4, OM_DEV_WALK = 8 };
+
+// device-side scalars, mirrored into pinned host memory after each phase
+struct DevScalars {
+  unsigned long long max_diff2_bits;  // non-negative double compared as integer
+  unsigned long long max_f_bits;      // surface: max |f|
+  unsigned long long n_limited;
+  int n_flagged;   // non-Delaunay half-edges found in the last check
+  int n_flips;     // flips applied in the last round
+  int err;         // OM_DEV_* bits
+  int pad;
+  double dot[4];   // PCG dot products
+};
+
+struct om_handle {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int64_t N = 0, C = 0;
+  int D = 2, PD = 2;
+  int cells_itemsize = 8;
+  // mesh state (internal numbering)
+  double* x = nullptr;       // N*PD current points
+  double* xnew = nullptr;    // N*PD next points (ping-pong)
+  int4* cells = nullptr;     // C: vertex ids, .w = caller's cell row
+  int4* adj = nullptr;       // C: twin half-edge (4*cell + slot) per local edge, -1 = boundary
+  int* v2c = nullptr;        // N: one incident cell (OM_NONE_CELL for orphans)
+  uint8_t* bflag = nullptr;  // N: 1 = pinned (boundary / ghost)
+  int* perm = nullptr;       // internal -> caller vertex id (nullptr: identity)
+  int* inv_perm = nullptr;   // caller -> internal
+  // flip scratch
+  double* ce = nullptr;      // 4C covolume/edge ratios indexed by half-edge
+  int8_t* best = nullptr;    // C: locally most negative flagged edge or -1
+  int* flip_epoch = nullptr; // C
+  int epoch = 0;
+  int* reloc = nullptr;      // 4C
+  int4* adj_tmp = nullptr;   // C
+  // PCG scratch (allocated on first use)
+  int* nbr_ptr = nullptr;    // N+1
+  int* nbr_idx = nullptr;    // nnz
+  float* nbr_w = nullptr;    // nnz edge multiplicities
+  int64_t nnz = 0;
+  double* pcg_buf = nullptr; // 4 vectors of N*PD
+  bool nbr_valid = false;
+  // scalars
+  DevScalars* ds = nullptr;  // device
+  DevScalars* hs = nullptr;  // pinned host
+  double* partials = nullptr;  // per-block partial sums (stats)
+  // settings
+  int method = OM_LLOYD;
+  double omega = 1.0;
+  int limiter = 1;
+  int surf_kind = 0;
+  double surf_tol = 1e-10;
+  double surf_params[4] = {0, 0, 0, 1};
+  int surf_max_sweeps = 100;
+  double solver_rtol = 1e-13;
+  int solver_max_iter = 100000;
+  int64_t launches = 0;
+};
+
+#define OM_LAUNCH(h, kernel, grid, block, ...)                         \
+  do {                                                                 \
+    kernel<<<(grid), (block), 0, (h)->stream>>>(__VA_ARGS__);          \
+    (h)->launches++;                                                   \
+  } while (0)
+
+static inline int om_grid(int64_t n, int block) { return (int)((n + block - 1) / block); }
+
+// fetch DevScalars to host (synchronises the stream)
+int om_fetch_scalars(om_handle* h);
+int om_check_dev_err(om_handle* h);
+
+// setup.cu
+int om_setup_mesh(om_handle* h, const double* points_dev, const void* cells_dev, int flags);
+// flip.cu
+int om_flip_impl(om_handle* h, double tol, int max_rounds, int64_t* n_flips, int32_t* n_rounds,
+                 int32_t* cap_hit);
+// step.cu
+int om_update_points_impl(om_handle* h, double tol, om_step_stats* out, bool target_only,
+                          double* target_out);
+int om_project_impl(om_handle* h, int32_t* sweeps);
+// pcg.cu
+int om_pcg_impl(om_handle* h, double rtol, int max_iter, int32_t* iters, double* relres,
+                double* out /* N*PD, may alias h->xnew */);
+// stats.cu
+int om_stats_impl(om_handle* h, int64_t* angle_hist72, int64_t* q_hist40, double* summary8);

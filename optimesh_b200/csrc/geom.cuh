@@ -1,0 +1,116 @@
+// Per-cell fp64 geometry shared by the step, flip and statistics kernels.
+// Arithmetic: SURVEY.md Appendix A.1-A.3 (meshplex MeshTri quantities; reference call
+// site /root/reference/README.md:131).
+#pragma once
+#include "common.cuh"
+
+template <int D>
+struct Vec {
+  double v[D];
+};
+
+template <int D>
+__device__ __forceinline__ Vec<D> ld_point(const double* __restrict__ x, int i);
+
+template <>
+__device__ __forceinline__ Vec<2> ld_point<2>(const double* __restrict__ x, int i) {
+  double2 t = __ldg(reinterpret_cast<const double2*>(x) + i);
+  Vec<2> r;
+  r.v[0] = t.x;
+  r.v[1] = t.y;
+  return r;
+}
+template <>
+__device__ __forceinline__ Vec<3> ld_point<3>(const double* __restrict__ x, int i) {
+  const double2* p = reinterpret_cast<const double2*>(x) + 2 * (size_t)i;
+  double2 a = __ldg(p), b = __ldg(p + 1);
+  Vec<3> r;
+  r.v[0] = a.x;
+  r.v[1] = a.y;
+  r.v[2] = b.x;
+  return r;
+}
+
+// coherent loads, for arrays that the same kernel also writes
+template <int D>
+__device__ __forceinline__ Vec<D> ld_point_rw(const double* x, int i) {
+  Vec<D> r;
+  if (D == 2) {
+    double2 t = reinterpret_cast<const double2*>(x)[i];
+    r.v[0] = t.x;
+    r.v[1] = t.y;
+  } else {
+    const double2* p = reinterpret_cast<const double2*>(x) + 2 * (size_t)i;
+    double2 a = p[0], b = p[1];
+    r.v[0] = a.x;
+    r.v[1] = a.y;
+    r.v[D - 1] = b.x;
+  }
+  return r;
+}
+
+template <int D>
+__device__ __forceinline__ void st_point(double* __restrict__ x, int i, const Vec<D>& p);
+template <>
+__device__ __forceinline__ void st_point<2>(double* __restrict__ x, int i, const Vec<2>& p) {
+  reinterpret_cast<double2*>(x)[i] = make_double2(p.v[0], p.v[1]);
+}
+template <>
+__device__ __forceinline__ void st_point<3>(double* __restrict__ x, int i, const Vec<3>& p) {
+  double2* q = reinterpret_cast<double2*>(x) + 2 * (size_t)i;
+  q[0] = make_double2(p.v[0], p.v[1]);
+  q[1] = make_double2(p.v[2], 0.0);
+}
+
+template <int D>
+__device__ __forceinline__ Vec<D> vsub(const Vec<D>& a, const Vec<D>& b) {
+  Vec<D> r;
+#pragma unroll
+  for (int k = 0; k < D; k++) r.v[k] = a.v[k] - b.v[k];
+  return r;
+}
+template <int D>
+__device__ __forceinline__ double vdot(const Vec<D>& a, const Vec<D>& b) {
+  double s = a.v[0] * b.v[0];
+#pragma unroll
+  for (int k = 1; k < D; k++) s += a.v[k] * b.v[k];
+  return s;
+}
+
+__device__ __forceinline__ int cell_get(const int4& c, int k) {
+  return k == 0 ? c.x : (k == 1 ? c.y : c.z);
+}
+__device__ __forceinline__ int slot_of(const int4& c, int v) {
+  return c.x == v ? 0 : (c.y == v ? 1 : (c.z == v ? 2 : -1));
+}
+
+// Edge vectors and dot products of one cell with vertices (P0,P1,P2):
+// e_k runs from vertex (k+1)%3 to (k+2)%3; ee_k = e_k.e_k; ed_k = e_{k+1}.e_{k+2}.
+template <int D>
+struct CellGeo {
+  Vec<D> e0, e1, e2;
+  double ee0, ee1, ee2, ed0, ed1, ed2;
+  double vol2;  // squared area
+};
+
+template <int D>
+__device__ __forceinline__ CellGeo<D> cell_geo(const Vec<D>& P0, const Vec<D>& P1,
+                                                const Vec<D>& P2) {
+  CellGeo<D> g;
+  g.e0 = vsub<D>(P2, P1);
+  g.e1 = vsub<D>(P0, P2);
+  g.e2 = vsub<D>(P1, P0);
+  g.ee0 = vdot<D>(g.e0, g.e0);
+  g.ee1 = vdot<D>(g.e1, g.e1);
+  g.ee2 = vdot<D>(g.e2, g.e2);
+  g.ed0 = vdot<D>(g.e1, g.e2);
+  g.ed1 = vdot<D>(g.e2, g.e0);
+  g.ed2 = vdot<D>(g.e0, g.e1);
+  g.vol2 = 0.25 * (g.ed2 * g.ed0 + g.ed0 * g.ed1 + g.ed1 * g.ed2);
+  return g;
+}
+
+// ordered-integer encoding of non-negative doubles for atomicMax
+__device__ __forceinline__ void atomic_max_nonneg(unsigned long long* addr, double v) {
+  atomicMax(addr, (unsigned long long)__double_as_longlong(v));
+}

@@ -1,0 +1,157 @@
+"""The reference's Python API for the smoothing path, backed by the CUDA library.
+
+    optimize_points_cells(points, cells, method, tol, max_num_steps, omega=...)
+        /root/reference/README.md:124-126 (kwargs :166-175)
+    optimize(mesh, method, tol, max_num_steps, ...)        README.md:131-132
+    get_new_points(mesh, method)                           README.md:141
+
+Loop semantics: flip-until-Delaunay once, then per step: new points,
+pin boundary, diff = omega (new - x), is_final = all |diff|^2 < tol^2 or k >=
+max_num_steps, step limiter, implicit-surface projection, flip-until-Delaunay, stop if
+is_final.  Everything per-step runs on the GPU; Python only keeps the signature,
+argument checking and the optional hooks (callback, step dumps, generic surfaces).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .helpers import print_stats
+from .mesh import DeviceMesh, MeshTri, method_id, normalize_method_name
+from .surfaces import Sphere
+
+
+def _project_host(dm: DeviceMesh, surface, tol: float, max_iter: int = 100):
+    """Generic implicit surface (objects with f/grad, README.md:157-162): the user's
+    Python callables run on the host between the point update and the flips."""
+    x = dm.points.T.copy()
+    changed = False
+    for _ in range(max_iter):
+        fval = surface.f(x)
+        if np.all(np.abs(fval) <= tol):
+            break
+        grad = surface.grad(x)
+        x = x - grad * (fval / np.einsum("ij,ij->j", grad, grad))
+        changed = True
+    if changed:
+        dm.points = x.T
+
+
+def _run_loop(dm: DeviceMesh, method: str, tol: float, max_num_steps: int, omega: float = 1.0,
+              verbose: bool = False, callback=None, step_filename_format=None,
+              implicit_surface=None, implicit_surface_tol: float = 1.0e-10, boundary_step=None,
+              cells_dtype=None, log=None):
+    if boundary_step is not None:
+        raise NotImplementedError("boundary_step callbacks are outside this build")
+    if max_num_steps < 1:
+        raise ValueError("max_num_steps must be >= 1")
+    dm.set_method(method, omega)
+    host_surface = None
+    if implicit_surface is None:
+        dm.clear_surface()
+    elif isinstance(implicit_surface, Sphere):
+        dm.set_sphere(implicit_surface.center, implicit_surface.radius, implicit_surface_tol)
+    else:
+        if not (hasattr(implicit_surface, "f") and hasattr(implicit_surface, "grad")):
+            raise TypeError("implicit_surface must provide f(x) and grad(x)")
+        dm.clear_surface()
+        host_surface = implicit_surface
+
+    if verbose:
+        print("Before:")
+        print_stats(*dm.stats())
+
+    hooks = callback is not None or step_filename_format is not None or host_surface is not None \
+        or log is not None
+    if not hooks:
+        steps, last = dm.run(tol, max_num_steps)
+    else:
+        dm.flip_until_delaunay()
+        steps = 0
+        if callback is not None:
+            callback(0, _snapshot(dm, cells_dtype))
+        while True:
+            steps += 1
+            if host_surface is None:
+                st = dm.step(tol)
+            else:
+                st = dm.update_points(tol)
+                _project_host(dm, host_surface, implicit_surface_tol)
+                nf, nr = dm.flip_until_delaunay()
+                st["n_flips"], st["n_flip_rounds"] = nf, nr
+            is_final = bool(st["is_final"]) or steps >= max_num_steps
+            if log is not None:
+                log.append(dict(step=steps, **st))
+            if step_filename_format is not None:
+                from . import io
+
+                io.write(step_filename_format.format(steps), dm.points, dm.cells(cells_dtype))
+            if callback is not None:
+                callback(steps, _snapshot(dm, cells_dtype))
+            if is_final:
+                break
+    if verbose:
+        print(f"\nFinal ({steps} steps):")
+        print_stats(*dm.stats())
+    return steps
+
+
+def _snapshot(dm: DeviceMesh, cells_dtype):
+    return MeshTri(dm.points, dm.cells(cells_dtype))
+
+
+def optimize_points_cells(points, cells, method: str, tol: float, max_num_steps: int,
+                          omega: float = 1.0, verbose: bool = False, callback=None,
+                          step_filename_format=None, implicit_surface=None,
+                          implicit_surface_tol: float = 1.0e-10, boundary_step=None,
+                          method_name=None, device: int = 0, log=None):
+    """Returns ``(points, cells)``; the inputs are not modified (README.md:124-126)."""
+    method_id(method)  # validate before touching the device
+    cells = np.asarray(cells)
+    with DeviceMesh(points, cells, device=device) as dm:
+        _run_loop(dm, method, tol, max_num_steps, omega, verbose, callback, step_filename_format,
+                  implicit_surface, implicit_surface_tol, boundary_step, cells.dtype, log)
+        return dm.points, dm.cells(cells.dtype)
+
+
+def optimize(mesh, method: str, tol: float, max_num_steps: int, **kwargs):
+    """In-place variant on an object exposing ``.points`` and ``.cells``
+    (``meshplex.MeshTri`` or ``optimesh_b200.MeshTri``), README.md:131-133."""
+    cells = _mesh_cells(mesh)
+    points, new_cells = optimize_points_cells(mesh.points, cells, method, tol, max_num_steps,
+                                              **kwargs)
+    _mesh_assign(mesh, points, new_cells)
+    return mesh
+
+
+def get_new_points(mesh, method: str, device: int = 0) -> np.ndarray:
+    """One un-relaxed update, ``(N, d)`` array (README.md:141)."""
+    method_id(method)
+    with DeviceMesh(mesh.points, _mesh_cells(mesh), device=device) as dm:
+        dm.set_method(method, 1.0)
+        return dm.new_points()
+
+
+def _mesh_cells(mesh):
+    cells = mesh.cells
+    if callable(cells) and not isinstance(cells, np.ndarray):
+        cells = cells("points")
+    elif isinstance(cells, dict):
+        cells = cells["points"]
+    return np.asarray(cells)
+
+
+def _mesh_assign(mesh, points, cells):
+    if isinstance(mesh, MeshTri):
+        mesh.points = points
+        mesh._set_cells(cells)
+        return
+    # foreign mesh classes (meshplex): rebuild through the constructor protocol
+    try:
+        mesh.__init__(points, cells)
+    except Exception:
+        mesh.points = points
+        if isinstance(getattr(mesh, "cells", None), dict):
+            mesh.cells["points"] = cells
+
+
+__all__ = ["optimize_points_cells", "optimize", "get_new_points", "normalize_method_name"]

@@ -1,0 +1,233 @@
+"""Host-side mesh objects.
+
+``DeviceMesh`` owns one ``om_handle`` (the mesh resident in HBM).  ``MeshTri`` mirrors
+the small part of ``meshplex.MeshTri`` that the reference API exposes
+(/root/reference/README.md:128-133: constructor, ``.points``, ``.cells``) so that
+``optimesh.optimize(mesh, ...)`` keeps working without meshplex.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import warnings
+
+import numpy as np
+
+from . import _lib
+from ._lib import check
+
+METHOD_IDS = {
+    "lloyd": _lib.OM_LLOYD,
+    "cvt-block-diagonal": _lib.OM_CVT_BLOCK_DIAGONAL,
+    "cpt-fixed-point": _lib.OM_CPT_FIXED_POINT,
+    "odt-fixed-point": _lib.OM_ODT_FIXED_POINT,
+    "cpt-linear-solve": _lib.OM_CPT_LINEAR_SOLVE,
+}
+# names the reference knows (README.md:80, :90, :104, :194) that are outside this build
+NOT_IMPLEMENTED = ("cvt-full", "cvt-uniform-qnf", "cpt-quasi-newton", "odt-dp-fp", "odt-bfgs")
+
+
+def normalize_method_name(name: str) -> str:
+    """'CVT (block-diagonal)' -> 'cvt-block-diagonal' (README.md:80 vs :125)."""
+    return "-".join(name.lower().replace("(", "").replace(")", "").split())
+
+
+def method_id(name: str) -> int:
+    key = normalize_method_name(name)
+    if key in NOT_IMPLEMENTED:
+        raise NotImplementedError(
+            f"method {key!r} is known to optimesh but not part of this build; "
+            f"available: {sorted(METHOD_IDS)}"
+        )
+    if key not in METHOD_IDS:
+        raise KeyError(f"unknown method {name!r}; available: {sorted(METHOD_IDS)}")
+    return METHOD_IDS[key]
+
+
+class DeviceMesh:
+    """A triangular mesh resident on one GPU."""
+
+    def __init__(self, points, cells, device: int = 0, renumber: bool = True, stream=None):
+        lib = _lib.load()
+        points = np.ascontiguousarray(points, dtype=np.float64)
+        cells = np.asarray(cells)
+        if points.ndim != 2 or points.shape[1] not in (2, 3):
+            raise ValueError("points must have shape (N, 2) or (N, 3)")
+        if cells.ndim != 2 or cells.shape[1] != 3:
+            raise ValueError("cells must have shape (C, 3)")
+        if not np.issubdtype(cells.dtype, np.integer):
+            raise ValueError("cells must be an integer array")
+        self.cells_dtype = cells.dtype
+        if cells.dtype.itemsize not in (4, 8) or cells.dtype.kind == "u" and cells.dtype.itemsize == 8:
+            cells = cells.astype(np.int64)
+        cells = np.ascontiguousarray(cells)
+        self.n, self.dim = points.shape
+        self.c = cells.shape[0]
+        self._h = C.c_void_p()
+        self._lib = lib
+        check(lib.om_create(C.byref(self._h), device, stream, self.n, self.dim, self.c,
+                            points.ctypes.data, cells.ctypes.data, cells.dtype.itemsize,
+                            _lib.OM_RENUMBER if renumber else 0))
+
+    # -- lifetime
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.om_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- settings
+    def set_method(self, method: str, omega: float = 1.0):
+        check(self._lib.om_set_method(self._h, method_id(method), float(omega)))
+
+    def set_limiter(self, on: bool):
+        check(self._lib.om_set_limiter(self._h, int(bool(on))))
+
+    def set_sphere(self, center=(0.0, 0.0, 0.0), radius=1.0, tol=1.0e-10, max_sweeps=100):
+        params = (C.c_double * 4)(center[0], center[1], center[2], radius)
+        check(self._lib.om_set_surface(self._h, 1, float(tol), params, int(max_sweeps)))
+
+    def clear_surface(self):
+        check(self._lib.om_set_surface(self._h, 0, 0.0, None, 0))
+
+    def set_solver(self, rtol=1.0e-13, max_iter=100000):
+        check(self._lib.om_set_solver(self._h, float(rtol), int(max_iter)))
+
+    # -- the hot path
+    def flip_until_delaunay(self, tol: float = 0.0, max_steps: int = 100):
+        nf, nr, cap = C.c_int64(), C.c_int32(), C.c_int32()
+        check(self._lib.om_flip_until_delaunay(self._h, float(tol), int(max_steps), C.byref(nf),
+                                               C.byref(nr), C.byref(cap)))
+        if cap.value:
+            warnings.warn("Maximum number of edge flips reached.")
+        return nf.value, nr.value
+
+    def step(self, tol: float = 0.0) -> dict:
+        st = _lib.StepStats()
+        check(self._lib.om_step(self._h, float(tol), C.byref(st)))
+        if st.flip_cap_hit:
+            warnings.warn("Maximum number of edge flips reached.")
+        return st.as_dict()
+
+    def update_points(self, tol: float = 0.0) -> dict:
+        st = _lib.StepStats()
+        check(self._lib.om_update_points(self._h, float(tol), C.byref(st)))
+        return st.as_dict()
+
+    def project(self) -> int:
+        n = C.c_int32()
+        check(self._lib.om_project(self._h, C.byref(n)))
+        return n.value
+
+    def run(self, tol: float, max_num_steps: int):
+        steps = C.c_int64()
+        st = _lib.StepStats()
+        check(self._lib.om_run(self._h, float(tol), int(max_num_steps), C.byref(steps),
+                               C.byref(st)))
+        if st.flip_cap_hit:
+            warnings.warn("Maximum number of edge flips reached.")
+        return steps.value, st.as_dict()
+
+    def new_points(self) -> np.ndarray:
+        out = np.empty((self.n, self.dim), dtype=np.float64)
+        check(self._lib.om_new_points(self._h, out.ctypes.data))
+        return out
+
+    def solve_graph_laplacian(self, rtol=1.0e-13, max_iter=100000):
+        it, res = C.c_int32(), C.c_double()
+        check(self._lib.om_solve_graph_laplacian(self._h, float(rtol), int(max_iter),
+                                                 C.byref(it), C.byref(res)))
+        return it.value, res.value
+
+    def stats(self):
+        ah = np.zeros(72, dtype=np.int64)
+        qh = np.zeros(40, dtype=np.int64)
+        s = np.zeros(8, dtype=np.float64)
+        check(self._lib.om_stats(self._h, ah.ctypes.data, qh.ctypes.data, s.ctypes.data))
+        keys = ("angle_min", "angle_max", "angle_avg", "angle_std", "q_min", "q_avg", "q_max",
+                "q_std")
+        return ah, qh, dict(zip(keys, s.tolist()))
+
+    # -- data movement
+    @property
+    def points(self) -> np.ndarray:
+        out = np.empty((self.n, self.dim), dtype=np.float64)
+        check(self._lib.om_get_points(self._h, out.ctypes.data))
+        return out
+
+    @points.setter
+    def points(self, new):
+        new = np.ascontiguousarray(new, dtype=np.float64)
+        if new.shape != (self.n, self.dim):
+            raise ValueError(f"points must have shape {(self.n, self.dim)}")
+        check(self._lib.om_set_points(self._h, new.ctypes.data))
+
+    def cells(self, dtype=None) -> np.ndarray:
+        dtype = np.dtype(dtype or self.cells_dtype)
+        wire = np.int32 if dtype.itemsize <= 4 and dtype != np.uint32 else np.int64
+        out = np.empty((self.c, 3), dtype=wire)
+        check(self._lib.om_get_cells(self._h, out.ctypes.data, out.dtype.itemsize))
+        return out.astype(dtype, copy=False)
+
+    @property
+    def is_boundary_point(self) -> np.ndarray:
+        out = np.zeros(self.n, dtype=np.uint8)
+        check(self._lib.om_get_boundary_flags(self._h, out.ctypes.data))
+        return out.astype(bool)
+
+    def pin_vertices(self, idx):
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        check(self._lib.om_pin_vertices(self._h, idx.ctypes.data, idx.size))
+
+    @property
+    def launch_count(self) -> int:
+        n = C.c_int64()
+        check(self._lib.om_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    def synchronize(self):
+        check(self._lib.om_synchronize(self._h))
+
+    @property
+    def stream(self) -> int:
+        p = C.c_void_p()
+        check(self._lib.om_stream(self._h, C.byref(p)))
+        return p.value or 0
+
+    @property
+    def handle(self):
+        return self._h
+
+
+class _Cells(np.ndarray):
+    """ndarray that can also be called like meshplex's ``mesh.cells("points")``."""
+
+    def __call__(self, which="points"):
+        if which != "points":
+            raise KeyError(which)
+        return np.asarray(self)
+
+
+class MeshTri:
+    """Minimal stand-in for ``meshplex.MeshTri(points, cells)`` (README.md:131)."""
+
+    def __init__(self, points, cells):
+        self.points = np.array(points, dtype=np.float64)
+        self._set_cells(cells)
+
+    def _set_cells(self, cells):
+        self._cells = np.array(cells).view(_Cells)
+
+    @property
+    def cells(self):
+        return self._cells

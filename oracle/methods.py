@@ -79,8 +79,8 @@ def cvt_block_diagonal(mesh: MeshTri) -> np.ndarray:
         np.add.at(blocks, idx[1, k], m)
     rhs = -2 * (X - cen) * cv[:, None]
     bnd = mesh.is_boundary_point
-    # vertices without any unmasked cell (cv == 0) and orphan vertices stay put
-    dead = bnd | ~(cv > 0.0)
+    # vertices without any unmasked cell (cv == 0, centroid 0/0) and orphans stay put
+    dead = bnd | (cv == 0.0)
     blocks[dead] = 0.0
     for k in range(d):
         blocks[dead, k, k] = 1.0

@@ -1,0 +1,126 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol the header declares,
+and the host logic (method names, I/O, CLI parsing, mesh mirror) behaves.  No compute."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__
+
+    __graft_entry__.build()
+    from optimesh_b200 import _lib
+
+    return _lib.load()
+
+
+def header_symbols():
+    with open(os.path.join(ROOT, "include", "optimesh_b200.h")) as f:
+        text = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    return sorted(set(re.findall(r"\b(om_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from optimesh_b200 import _lib
+
+    syms = header_symbols()
+    assert len(syms) >= 25
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/optimesh_b200.h but not exported"
+    assert sorted(_lib.SIGNATURES) == syms  # the ctypes table covers the header exactly
+
+
+def test_struct_layout_matches_header():
+    from optimesh_b200 import _lib
+
+    # double + 2*int64 + 6*int32 = 48 bytes
+    assert ctypes.sizeof(_lib.StepStats) == 48
+
+
+def test_no_gpu_fails_loudly(lib):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import optimesh_b200
+    from optimesh_b200 import generators as G
+
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        optimesh_b200.optimize_points_cells(*G.SIMPLE1, "lloyd", 1e-2, 10)
+
+
+def test_method_names():
+    from optimesh_b200.mesh import method_id, normalize_method_name
+
+    assert normalize_method_name("CVT (block-diagonal)") == "cvt-block-diagonal"
+    assert method_id("Lloyd") == 0 and method_id("CVT (block-diagonal)") == 1
+    assert method_id("cpt-fixed-point") == 2 and method_id("ODT (fixed-point)") == 3
+    assert method_id("cpt-linear-solve") == 4
+    for name in ("cvt-full", "cvt-uniform-qnf", "cpt-quasi-newton", "odt-dp-fp", "odt-bfgs"):
+        with pytest.raises(NotImplementedError):
+            method_id(name)
+    with pytest.raises(KeyError):
+        method_id("laplace")
+
+
+def test_drop_in_alias_exposes_reference_api():
+    import optimesh
+
+    for name in ("optimize_points_cells", "optimize", "get_new_points"):
+        assert callable(getattr(optimesh, name))
+    assert callable(optimesh.odt.fixed_point) and callable(optimesh.cpt.linear_solve)
+    assert callable(optimesh.cvt.quasi_newton_uniform_lloyd)
+
+
+def test_meshtri_mirror():
+    from optimesh_b200 import MeshTri
+    from optimesh_b200.main import _mesh_cells
+
+    m = MeshTri([[0, 0], [1, 0], [0, 1]], [[0, 1, 2]])
+    assert m.points.dtype == np.float64
+    assert np.array_equal(m.cells, [[0, 1, 2]])
+    assert np.array_equal(m.cells("points"), [[0, 1, 2]])
+    assert np.array_equal(_mesh_cells(m), [[0, 1, 2]])
+
+
+def test_io_roundtrip(tmp_path):
+    from optimesh_b200 import generators as G, io
+
+    pts, cells = G.disk(20, 0)
+    for ext in (".vtk", ".npz"):
+        path = str(tmp_path / f"m{ext}")
+        io.write(path, pts, cells)
+        p, c = io.read(path)
+        assert np.array_equal(p, pts) and np.array_equal(c, cells)
+    sp, sc = G.tetra_sphere(3)
+    io.write(str(tmp_path / "s.vtk"), sp, sc)
+    p, c = io.read(str(tmp_path / "s.vtk"))
+    assert np.array_equal(p, sp) and np.array_equal(c, sc)
+    with pytest.raises(ValueError):
+        io.read(str(tmp_path / "m.xyz"))
+
+
+def test_cli_arguments():
+    from optimesh_b200.cli import _parser
+
+    a = _parser().parse_args(["in.vtk", "out.vtk", "-m", "lloyd", "--omega", "2.0", "-n", "7",
+                              "-t", "1e-3", "-q"])
+    assert (a.method, a.omega, a.max_num_steps, a.tolerance, a.quiet) == ("lloyd", 2.0, 7, 1e-3,
+                                                                         True)
+    assert _parser().parse_args(["a", "b"]).method == "cvt-block-diagonal"
+
+
+def test_print_stats_runs(capsys):
+    from optimesh_b200.helpers import print_stats
+    import oracle
+    from optimesh_b200 import generators as G
+
+    print_stats(*oracle.stats(oracle.MeshTri(*G.disk(30, 0))))
+    out = capsys.readouterr().out
+    assert "angles" in out and "quality" in out

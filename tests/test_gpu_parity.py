@@ -1,0 +1,398 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the CPU oracle.
+
+Bar (BASELINE.json north_star): cell arrays bit-exact on non-degenerate meshes, point
+coordinates within 1e-10 relative per step (1e-8 after convergence), angle/quality
+histograms equal.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import scipy.spatial
+
+import oracle
+from oracle.meshtri import MeshTri as OMesh, canonical_cells
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+STEP_TOL = 1.0e-10  # relative to max |x|, per step
+METHODS = ["lloyd", "cvt-block-diagonal", "cpt-fixed-point", "odt-fixed-point"]
+
+
+@pytest.fixture(scope="module")
+def ob():
+    import optimesh_b200
+
+    return optimesh_b200
+
+
+@pytest.fixture(scope="module")
+def G():
+    from optimesh_b200 import generators
+
+    return generators
+
+
+def rel_err(a, b):
+    return np.abs(a - b).max() / np.abs(b).max()
+
+
+def norms(p):
+    return np.abs(p).sum(), np.sqrt((p * p).sum()), np.abs(p).max()
+
+
+# ------------------------------------------------------------------ known answers
+def test_simple1_lloyd_known_answer(ob, G):
+    p, c = ob.optimize_points_cells(*G.SIMPLE1, "lloyd", 1.0e-2, 100)
+    n1, n2, ninf = norms(p)
+    assert abs(n1 - 4.986335452622451) <= 1e-12 * n1
+    assert abs(n2 - 2.1181412069258942) <= 1e-12 * n2
+    assert ninf == 1.0
+    assert np.array_equal(c, G.SIMPLE1[1])
+
+
+@pytest.mark.parametrize("method", ["cpt-fixed-point", "cpt-linear-solve", "odt-fixed-point"])
+def test_simple1_cpt_odt_known_answer(ob, G, method):
+    p, c = ob.optimize_points_cells(*G.SIMPLE1, method, 1.0e-2, 100)
+    n1, n2, ninf = norms(p)
+    assert abs(n1 - 5.0) < 1e-11 and abs(n2 - 2.1213203435596424) < 1e-11 and ninf == 1.0
+
+
+def test_simple1_step_counts(ob, G):
+    for method, expect in (("lloyd", [5, 10, 22]), ("CVT (block-diagonal)", [3, 5, 10])):
+        for tol, n in zip((1e-2, 1e-3, 1e-5), expect):
+            log = []
+            ob.optimize_points_cells(*G.SIMPLE1, method, tol, 100, log=log)
+            assert len(log) == n, (method, tol)
+
+
+# ------------------------------------------------------------------ single step
+def _meshes(G):
+    out = {}
+    out["disk40"] = G.disk(40, 3)
+    out["disk120"] = G.disk(120, 0)
+    out["square"] = G.square(30, 0.25, 1)
+    sp, sc = G.tetra_sphere(6)
+    rs = np.random.RandomState(5)
+    sp = sp + rs.normal(scale=0.02, size=sp.shape)
+    sp /= np.linalg.norm(sp, axis=1)[:, None]
+    m = OMesh(sp, sc)
+    m.flip_until_delaunay()
+    out["sphere6"] = (sp, m.cells("points").copy())
+    sp, sc = G.tetra_sphere(24)
+    out["sphere24"] = (sp, sc)
+    return out
+
+
+@pytest.mark.parametrize("name", ["disk40", "disk120", "square", "sphere6", "sphere24"])
+@pytest.mark.parametrize("method", METHODS + ["cpt-linear-solve"])
+@pytest.mark.parametrize("renumber", [True, False])
+def test_get_new_points_matches_oracle(ob, G, name, method, renumber):
+    pts, cells = _meshes(G)[name]
+    if method == "cpt-linear-solve" and name.startswith("sphere"):
+        pytest.skip("closed surface: the graph Laplacian is singular")
+    ref = oracle.get_new_points(OMesh(pts, cells), method)
+    with ob.DeviceMesh(pts, cells, renumber=renumber) as dm:
+        dm.set_method(method)
+        got = dm.new_points()
+    tol = 1e-9 if method == "cpt-linear-solve" else STEP_TOL
+    assert rel_err(got, ref) <= tol
+
+
+def test_get_new_points_matches_golden_fixture(ob, G):
+    z = np.load(os.path.join(GOLDEN, "single_steps.npz"))
+    pts, cells = G.disk(40, 3)
+    for m in METHODS:
+        got = ob.get_new_points(ob.MeshTri(pts, cells), m)
+        assert rel_err(got, z[f"disk40_{m}"]) <= STEP_TOL
+    sp, sc = z["sphere6_points"], z["sphere6_cells"]
+    for m in METHODS:
+        got = ob.get_new_points(ob.MeshTri(sp, sc), m)
+        assert rel_err(got, z[f"sphere6_{m}"]) <= STEP_TOL
+
+
+@pytest.mark.parametrize("name", ["disk120", "square", "sphere24"])
+@pytest.mark.parametrize("method", METHODS)
+@pytest.mark.parametrize("omega", [1.0, 2.0])
+def test_update_points_matches_oracle_step(ob, G, name, method, omega):
+    """Pin + omega + limiter, from identical input state."""
+    pts, cells = _meshes(G)[name]
+    om = OMesh(pts, cells)
+    max_diff2, n_limited = oracle.driver.step(om, method, omega=omega)
+    with ob.DeviceMesh(pts, cells) as dm:
+        dm.set_method(method, omega)
+        st = dm.update_points(0.0)
+        got = dm.points
+    assert rel_err(got, om.points) <= STEP_TOL
+    assert st["n_limited"] == n_limited
+    assert abs(st["max_diff2"] - max_diff2) <= 1e-9 * max_diff2
+    bnd = om.is_boundary_point
+    assert np.array_equal(got[bnd], pts[bnd])
+
+
+# ------------------------------------------------------------------ flips
+def _jittered(G, nb, seed, frac=0.45):
+    pts, cells = G.disk(nb, seed)
+    pts, cells = oracle.optimize_points_cells(pts, cells, "cpt-fixed-point", 0.0, 5)
+    m = OMesh(pts, cells)
+    rs = np.random.RandomState(seed)
+    rmin = np.full(len(pts), np.inf)
+    np.minimum.at(rmin, cells.reshape(-1), np.repeat(m.cell_inradius, 3))
+    step = rs.uniform(-1, 1, size=pts.shape) * (frac * rmin / np.sqrt(2))[:, None]
+    bnd = m.is_boundary_point
+    p2 = pts.copy()
+    p2[~bnd] += step[~bnd]
+    return p2, cells
+
+
+@pytest.mark.parametrize("seed", range(4))
+@pytest.mark.parametrize("renumber", [True, False])
+def test_flips_bit_exact_vs_oracle_and_qhull(ob, G, seed, renumber):
+    pts, cells = _jittered(G, 80, seed)
+    om = OMesh(pts, cells)
+    nf, nr = om.flip_until_delaunay()
+    with ob.DeviceMesh(pts, cells, renumber=renumber) as dm:
+        gf, gr = dm.flip_until_delaunay()
+        got = dm.cells()
+        # the twin table must still be consistent: a second pass finds nothing,
+        # and a smoothing step walks every star without error
+        assert dm.flip_until_delaunay() == (0, 0)
+        dm.set_method("lloyd")
+        dm.update_points(0.0)
+    assert (gf, gr) == (nf, nr) and nf > 0
+    assert np.array_equal(got, om.cells("points"))  # row for row, slot for slot
+    ref = scipy.spatial.Delaunay(pts).simplices
+    assert np.array_equal(canonical_cells(got), canonical_cells(ref))
+
+
+def test_flips_on_sphere_match_convex_hull(ob, G):
+    pts, cells = G.tetra_sphere(12)
+    rs = np.random.RandomState(0)
+    p2 = pts + rs.normal(scale=0.02, size=pts.shape)
+    p2 /= np.linalg.norm(p2, axis=1)[:, None]
+    om = OMesh(p2, cells)
+    om.flip_until_delaunay()
+    with ob.DeviceMesh(p2, cells) as dm:
+        dm.flip_until_delaunay()
+        got = dm.cells()
+    assert np.array_equal(got, om.cells("points"))
+    hull = scipy.spatial.ConvexHull(p2).simplices
+    assert np.array_equal(canonical_cells(got), canonical_cells(hull))
+
+
+def test_mapped_grid_flips_to_delaunay(ob, G):
+    pts, cells = G.disk_mapped_grid(120, 0.25, 0, shuffle=True)
+    om = OMesh(pts, cells)
+    nf, nr = om.flip_until_delaunay()
+    with ob.DeviceMesh(pts, cells) as dm:
+        gf, gr = dm.flip_until_delaunay()
+        got = dm.cells()
+    assert (gf, gr) == (nf, nr)
+    assert np.array_equal(got, om.cells("points"))
+
+
+# ------------------------------------------------------------------ trajectories
+def test_config1_trajectory(ob, G):
+    """BASELINE.json configs[0]: Lloyd omega=1, disk(120) (1,383 vertices), 50 steps,
+    tol 1e-5 -- cells identical, points within 1e-8, histograms equal."""
+    with open(os.path.join(GOLDEN, "config1_lloyd.json")) as f:
+        gold = json.load(f)
+    fin = np.load(os.path.join(GOLDEN, "config1_lloyd_final.npz"))
+    pts, cells = G.disk(120, 0)
+    log = []
+    p, c = ob.optimize_points_cells(pts, cells, "lloyd", 1.0e-5, 50, log=log)
+    assert len(log) == 50
+    assert [l["n_flips"] for l in log] == gold["n_flips"]
+    assert [l["n_flip_rounds"] for l in log] == gold["n_rounds"]
+    assert [l["n_limited"] for l in log] == gold["n_limited"]
+    assert np.array_equal(c, fin["cells"])
+    assert rel_err(p, fin["points"]) <= 1e-8
+    # same result without the per-step hooks (whole loop inside om_run)
+    p2, c2 = ob.optimize_points_cells(pts, cells, "lloyd", 1.0e-5, 50)
+    assert np.array_equal(p2, p) and np.array_equal(c2, c)
+    with ob.DeviceMesh(p, c) as dm:
+        ah, qh, s = dm.stats()
+    assert np.abs(ah - np.array(gold["angle_hist"])).max() <= 1
+    assert np.abs(qh - np.array(gold["q_hist"])).max() <= 1
+    assert ah.sum() == 3 * len(c) and qh.sum() == len(c)
+    for k, v in gold["summary"].items():
+        assert abs(s[k] - v) <= 1e-7 * max(1.0, abs(v)), k
+
+
+@pytest.mark.parametrize("method,omega", [("lloyd", 2.0), ("cvt-block-diagonal", 1.0),
+                                          ("cpt-fixed-point", 1.0), ("odt-fixed-point", 1.0)])
+def test_short_trajectories(ob, G, method, omega):
+    pts, cells = G.disk(60, 7)
+    olog, glog = [], []
+    rp, rc = oracle.optimize_points_cells(pts, cells, method, 1e-6, 12, omega=omega, log=olog)
+    p, c = ob.optimize_points_cells(pts, cells, method, 1e-6, 12, omega=omega, log=glog)
+    assert [l["n_flips"] for l in glog] == [l["n_flips"] for l in olog]
+    assert np.array_equal(c, rc)
+    assert rel_err(p, rp) <= 1e-8
+
+
+def test_sphere_odt_with_projection(ob, G):
+    """Config 4 in miniature: ODT fixed-point on a sphere, projection every step."""
+    pts, cells = G.tetra_sphere(16)
+    olog, glog = [], []
+    rp, rc = oracle.optimize_points_cells(pts, cells, "odt-fixed-point", 1e-4, 8,
+                                          implicit_surface=ob.Sphere(), log=olog)
+    p, c = ob.optimize_points_cells(pts, cells, "odt-fixed-point", 1e-4, 8,
+                                    implicit_surface=ob.Sphere(), log=glog)
+    assert np.abs(np.linalg.norm(p, axis=1) - 1.0).max() < 1e-10
+    assert [l["n_flips"] for l in glog] == [l["n_flips"] for l in olog]
+    assert np.array_equal(c, rc)
+    assert rel_err(p, rp) <= 1e-8
+
+    class UserSphere:  # the README's object: generic host path
+        def f(self, x):
+            return 1.0 - (x[0] ** 2 + x[1] ** 2 + x[2] ** 2)
+
+        def grad(self, x):
+            return -2 * x
+
+    p2, c2 = ob.optimize_points_cells(pts, cells, "odt-fixed-point", 1e-4, 8,
+                                      implicit_surface=UserSphere())
+    assert np.array_equal(c2, rc) and rel_err(p2, rp) <= 1e-8
+
+
+def test_cpt_linear_solve_vs_spsolve(ob, G):
+    """Config 3 in miniature: Laplacian smoothing on a jittered square, boundary pinned."""
+    pts, cells = G.square(60, 0.25, 0)
+    ref = oracle.get_new_points(OMesh(pts, cells), "cpt-linear-solve")
+    with ob.DeviceMesh(pts, cells) as dm:
+        its, res = dm.solve_graph_laplacian(1e-14, 20000)
+        got = dm.points
+    assert res <= 1e-13 and its > 0
+    assert rel_err(got, ref) <= 1e-10
+    bnd = OMesh(pts, cells).is_boundary_point
+    assert np.array_equal(got[bnd], pts[bnd])
+
+
+# ------------------------------------------------------------------ properties, edge cases
+def test_bitwise_deterministic(ob, G):
+    pts, cells = G.disk(100, 4)
+    a = ob.optimize_points_cells(pts, cells, "lloyd", 0.0, 10, omega=2.0)
+    b = ob.optimize_points_cells(pts, cells, "lloyd", 0.0, 10, omega=2.0)
+    assert a[0].tobytes() == b[0].tobytes() and a[1].tobytes() == b[1].tobytes()
+
+
+def test_inputs_untouched_and_dtypes(ob, G):
+    pts, cells = G.disk(40, 1)
+    for dt in (np.int32, np.int64, np.uint32):
+        p0, c0 = pts.copy(), cells.astype(dt)
+        p, c = ob.optimize_points_cells(p0, c0, "cpt-fixed-point", 1e-3, 5)
+        assert np.array_equal(p0, pts) and np.array_equal(c0, cells.astype(dt))
+        assert c.dtype == dt and p.dtype == np.float64 and p.shape == pts.shape
+
+
+def test_vertex_numbering_is_preserved(ob, G):
+    pts, cells = G.disk(50, 2)
+    ps, cs = G.shuffle_vertices(pts, cells, 3)
+    p1, c1 = ob.optimize_points_cells(pts, cells, "lloyd", 0.0, 6)
+    p2, c2 = ob.optimize_points_cells(ps, cs, "lloyd", 0.0, 6)
+    rs = np.random.RandomState(3 + 12345)
+    perm = rs.permutation(len(pts))
+    assert rel_err(p2, p1[perm]) < 1e-9
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(len(perm))
+    assert np.array_equal(canonical_cells(c2), canonical_cells(inv[c1]))
+
+
+def test_mixed_orientation_and_orphans(ob, G):
+    pts, cells = G.square(12, 0.2, 3)
+    cells = cells.copy()
+    cells[::3] = cells[::3][:, [0, 2, 1]]  # flip the orientation of every third cell
+    pts = np.concatenate([pts, [[5.0, 5.0]]])  # an orphan vertex
+    for m in METHODS:
+        ref = oracle.get_new_points(OMesh(pts, cells), m)
+        got = ob.get_new_points(ob.MeshTri(pts, cells), m)
+        assert rel_err(got, ref) <= STEP_TOL
+        assert np.array_equal(got[-1], [5.0, 5.0])
+
+
+def test_single_triangle_and_masked_cells(ob):
+    pts = np.array([[0.0, 0.0], [1.0, 0.0], [0.3, 0.8]])
+    cells = np.array([[0, 1, 2]])
+    p, c = ob.optimize_points_cells(pts, cells, "lloyd", 1e-3, 3)
+    assert np.array_equal(p, pts) and np.array_equal(c, cells)
+    # interior vertex whose cells are all obtuse (> 135 deg) -> fully masked -> stays
+    pts = np.array([[0.0, 0.0], [10.0, 0.0], [5.0, 0.3], [5.0, -0.3], [5.0, 0.0]])
+    cells = np.array([[0, 4, 2], [4, 1, 2], [0, 3, 4], [3, 1, 4]])
+    for m in ("lloyd", "cvt-block-diagonal"):
+        ref = oracle.get_new_points(OMesh(pts, cells), m)
+        got = ob.get_new_points(ob.MeshTri(pts, cells), m)
+        assert np.allclose(got, ref, rtol=0, atol=1e-12)
+
+
+def test_errors(ob, G):
+    from optimesh_b200._lib import DegenerateCellsError, MeshTopologyError
+
+    pts = np.array([[0.0, 0.0], [1.0, 0.0], [2.0, 0.0], [1.0, 1.0]])
+    with pytest.raises(DegenerateCellsError):
+        ob.optimize_points_cells(pts, np.array([[0, 1, 2], [0, 1, 3]]), "lloyd", 1e-3, 2)
+    with pytest.raises(MeshTopologyError):
+        ob.optimize_points_cells(pts, np.array([[0, 1, 9]]), "lloyd", 1e-3, 2)
+    with pytest.raises(KeyError):
+        ob.optimize_points_cells(*G.SIMPLE1, "nope", 1e-3, 2)
+    with pytest.raises(NotImplementedError):
+        ob.optimize_points_cells(*G.SIMPLE1, "CVT (full)", 1e-3, 2)
+    tri3 = np.array([[0, 1, 3], [0, 1, 2], [0, 1, 3]])
+    with pytest.raises(MeshTopologyError):
+        ob.DeviceMesh(np.array([[0.0, 0], [1, 0], [0, 1], [1, 1.0]]),
+                      np.array([[0, 1, 2], [0, 1, 3], [1, 0, 3]]))
+    del tri3
+
+
+def test_stats_match_oracle(ob, G):
+    for pts, cells in (G.disk(90, 5), G.tetra_sphere(10)):
+        ah, qh, s = oracle.stats(OMesh(pts, cells))
+        with ob.DeviceMesh(pts, cells) as dm:
+            gah, gqh, gs = dm.stats()
+        assert np.abs(gah - ah).max() <= 1 and np.abs(gqh - qh).max() <= 1
+        assert gah.sum() == ah.sum() and gqh.sum() == qh.sum()
+        for k, v in s.items():
+            assert abs(gs[k] - v) <= 1e-9 * max(1.0, abs(v)), k
+
+
+# ------------------------------------------------------------------ larger sizes
+def test_single_step_100k(ob, G):
+    pts, cells = G.disk_mapped_grid(330, 0.25, 1, shuffle=True)  # 108,900 vertices
+    om = OMesh(pts, cells)
+    om.flip_until_delaunay()
+    c0 = om.cells("points").copy()
+    for method in ("lloyd", "cvt-block-diagonal"):
+        om2 = OMesh(pts, c0)
+        oracle.driver.step(om2, method)
+        with ob.DeviceMesh(pts, c0) as dm:
+            dm.set_method(method)
+            dm.update_points(0.0)
+            got = dm.points
+        assert rel_err(got, om2.points) <= STEP_TOL
+
+
+def test_full_size_properties(ob, G):
+    """~1M vertices: properties that need no oracle run at this size."""
+    pts, cells = G.disk_mapped_grid(1000, 0.25, 0)
+    with ob.DeviceMesh(pts, cells) as dm:
+        nf, nr = dm.flip_until_delaunay()
+        assert nf > 0 and dm.flip_until_delaunay() == (0, 0)  # idempotent
+        c = dm.cells()
+        # flips conserve the cell count, every vertex's presence and the total area
+        assert c.shape == cells.shape and np.array_equal(np.unique(c), np.arange(len(pts)))
+        dm.set_method("lloyd", 1.0)
+        bnd = dm.is_boundary_point
+        assert bnd.sum() == 4 * 999
+        for _ in range(3):
+            st = dm.step(0.0)
+        p = dm.points
+        assert np.array_equal(p[bnd], pts[bnd])  # boundary pinned
+        ah, qh, s = dm.stats()
+        assert ah.sum() == 3 * len(cells) and qh.sum() == len(cells)
+        a = p[dm.cells()]
+        area = 0.5 * np.abs(np.cross(a[:, 1] - a[:, 0], a[:, 2] - a[:, 0])).sum()
+        a0 = pts[cells]
+        area0 = 0.5 * np.abs(np.cross(a0[:, 1] - a0[:, 0], a0[:, 2] - a0[:, 0])).sum()
+        assert abs(area - area0) < 1e-9 * area0
