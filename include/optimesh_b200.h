@@ -145,6 +145,13 @@ int om_unpack_points(om_handle* h, const int32_t* idx_dev, int64_t n, const doub
 /* Vertices listed here are treated as pinned (ghost vertices of a partition). */
 int om_pin_vertices(om_handle* h, const int32_t* idx_host, int64_t n);
 
+/* Per-kernel timing with CUDA events on the handle's stream (bench.py's roofline line):
+ * when on, the fused step kernel (K1) and each flip-until-Delaunay pass are bracketed by
+ * events; om_get_timing returns the accumulated device times and counts. */
+int om_set_timing(om_handle* h, int on);
+int om_get_timing(om_handle* h, double* step_kernel_ms, int64_t* step_kernel_launches,
+                  double* flip_pass_ms, int64_t* flip_passes);
+
 /* kernels launched by this handle so far (bench.py's gpu_launches) */
 int om_launch_count(om_handle* h, int64_t* n);
 int om_synchronize(om_handle* h);

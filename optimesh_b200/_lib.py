@@ -68,6 +68,9 @@ SIGNATURES = {
     "om_pack_points": (C.c_int, [_H, C.c_void_p, C.c_int64, C.c_void_p]),
     "om_unpack_points": (C.c_int, [_H, C.c_void_p, C.c_int64, C.c_void_p]),
     "om_pin_vertices": (C.c_int, [_H, C.c_void_p, C.c_int64]),
+    "om_set_timing": (C.c_int, [_H, C.c_int]),
+    "om_get_timing": (C.c_int, [_H, _P(C.c_double), _P(C.c_int64), _P(C.c_double),
+                                _P(C.c_int64)]),
     "om_launch_count": (C.c_int, [_H, _P(C.c_int64)]),
     "om_synchronize": (C.c_int, [_H]),
     "om_stream": (C.c_int, [_H, _P(C.c_void_p)]),

@@ -271,6 +271,8 @@ int om_destroy(om_handle* h) {
   cudaFree(h->ds);
   cudaFree(h->partials);
   if (h->hs) cudaFreeHost(h->hs);
+  for (int i = 0; i < 4; i++)
+    if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return OM_OK;
@@ -514,6 +516,26 @@ int om_pin_vertices(om_handle* h, const int32_t* idx_host, int64_t n) {
   cudaFree(d);
   CUDA_TRY(e);
   h->nbr_valid = false;
+  return OM_OK;
+}
+
+int om_set_timing(om_handle* h, int on) {
+  OM_ENTER(h);
+  if (on && !h->ev[0])
+    for (int i = 0; i < 4; i++) CUDA_TRY(cudaEventCreate(&h->ev[i]));
+  h->timing = on != 0;
+  h->t_step_ms = h->t_flip_ms = 0.0;
+  h->n_step = h->n_flip = 0;
+  return OM_OK;
+}
+
+int om_get_timing(om_handle* h, double* step_kernel_ms, int64_t* step_kernel_launches,
+                  double* flip_pass_ms, int64_t* flip_passes) {
+  OM_ENTER(h);
+  if (step_kernel_ms) *step_kernel_ms = h->t_step_ms;
+  if (step_kernel_launches) *step_kernel_launches = h->n_step;
+  if (flip_pass_ms) *flip_pass_ms = h->t_flip_ms;
+  if (flip_passes) *flip_passes = h->n_flip;
   return OM_OK;
 }
 

@@ -88,6 +88,11 @@ struct om_handle {
   double solver_rtol = 1e-13;
   int solver_max_iter = 100000;
   int64_t launches = 0;
+  // optional event timing (om_set_timing)
+  bool timing = false;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  double t_step_ms = 0.0, t_flip_ms = 0.0;
+  int64_t n_step = 0, n_flip = 0;
 };
 
 #define OM_LAUNCH(h, kernel, grid, block, ...)                         \

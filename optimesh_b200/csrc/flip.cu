@@ -193,6 +193,17 @@ int om_flip_impl(om_handle* h, double tol, int max_rounds, int64_t* n_flips, int
   if (n_rounds) *n_rounds = 0;
   if (cap_hit) *cap_hit = 0;
   if (h->C == 0) return OM_OK;
-  if (h->D == 2) return flip_rounds<2>(h, tol, max_rounds, n_flips, n_rounds, cap_hit);
-  return flip_rounds<3>(h, tol, max_rounds, n_flips, n_rounds, cap_hit);
+  if (h->timing) cudaEventRecord(h->ev[2], h->stream);
+  int rc = (h->D == 2) ? flip_rounds<2>(h, tol, max_rounds, n_flips, n_rounds, cap_hit)
+                       : flip_rounds<3>(h, tol, max_rounds, n_flips, n_rounds, cap_hit);
+  if (h->timing && rc == OM_OK) {
+    cudaEventRecord(h->ev[3], h->stream);
+    cudaEventSynchronize(h->ev[3]);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]) == cudaSuccess) {
+      h->t_flip_ms += ms;
+      h->n_flip++;
+    }
+  }
+  return rc;
 }

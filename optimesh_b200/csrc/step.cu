@@ -438,6 +438,7 @@ int om_update_points_impl(om_handle* h, double tol, om_step_stats* out, bool tar
     }
   } else {
     StepParams p = make_params(h, target_only ? target_out : h->xnew);
+    if (h->timing) cudaEventRecord(h->ev[0], h->stream);
     if (h->D == 2) {
       if (target_only)
         OM_TRY((launch_step<2, true>(h, p)));
@@ -449,8 +450,16 @@ int om_update_points_impl(om_handle* h, double tol, om_step_stats* out, bool tar
       else
         OM_TRY((launch_step<3, false>(h, p)));
     }
+    if (h->timing) cudaEventRecord(h->ev[1], h->stream);
   }
   OM_TRY(om_fetch_scalars(h));
+  if (h->timing && h->method != OM_CPT_LINEAR_SOLVE) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]) == cudaSuccess) {
+      h->t_step_ms += ms;
+      h->n_step++;
+    }
+  }
   OM_TRY(om_check_dev_err(h));
   if (!target_only) std::swap(h->x, h->xnew);
   if (out) {

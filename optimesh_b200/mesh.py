@@ -189,6 +189,16 @@ class DeviceMesh:
         idx = np.ascontiguousarray(idx, dtype=np.int32)
         check(self._lib.om_pin_vertices(self._h, idx.ctypes.data, idx.size))
 
+    def set_timing(self, on: bool = True):
+        check(self._lib.om_set_timing(self._h, int(bool(on))))
+
+    def timing(self) -> dict:
+        a, b = C.c_double(), C.c_double()
+        na, nb = C.c_int64(), C.c_int64()
+        check(self._lib.om_get_timing(self._h, C.byref(a), C.byref(na), C.byref(b), C.byref(nb)))
+        return dict(step_kernel_ms=a.value, step_kernel_launches=na.value,
+                    flip_pass_ms=b.value, flip_passes=nb.value)
+
     @property
     def launch_count(self) -> int:
         n = C.c_int64()
