@@ -13,9 +13,7 @@ from __future__ import annotations
 import argparse
 import json
 import os
-import subprocess
 import sys
-import tempfile
 import time
 
 import numpy as np
@@ -66,55 +64,72 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons during the timed region."""
+    """SM clock and throttle reasons sampled through NVML during the timed region."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    def __init__(self, gpu_index, period_s=0.01):
+        import threading
 
-    def __init__(self, gpu_index):
         self.idx = gpu_index
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+        self.period = period_s
+        self.sm, self.reasons = [], set()
+        self.smax = None
+        self._stop = threading.Event()
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._ok = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = gpu_index
+            if visible:
+                ids = [v for v in visible.split(",") if v.strip() != ""]
+                if gpu_index < len(ids) and ids[gpu_index].strip().isdigit():
+                    phys = int(ids[gpu_index])
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self._ok = True
+        except Exception:
+            self._ok = False
+
+    def _sample(self):
+        nv = self.nv
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        try:
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        for name, bit in (("hw_slowdown", 0x8), ("sw_power_cap", 0x4),
+                          ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+                          ("hw_power_brake_slowdown", 0x80)):
+            if r & bit:
+                self.reasons.add(name)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self._sample()
+            except Exception:
+                pass
+            self._stop.wait(self.period)
 
     def start(self):
-        try:
-            self.p = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
-                stderr=subprocess.DEVNULL)
-        except Exception:
-            self.p = None
+        if self._ok:
+            self._thread.start()
 
     def stop(self):
-        if self.p is not None:
-            self.p.terminate()
+        if self._ok:
+            self._stop.set()
+            self._thread.join(timeout=2)
             try:
-                self.p.wait(timeout=5)
+                self._sample()
             except Exception:
-                self.p.kill()
-        self.f.flush()
-        self.f.seek(0)
-        sm, smax, reasons = [], [], set()
-        for line in self.f.read().splitlines():
-            t = [x.strip() for x in line.split(",")]
-            if len(t) < 9:
-                continue
-            try:
-                sm.append(float(t[1]))
-                smax.append(float(t[2]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
-                                  "sw_power_cap"), t[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        self.f.close()
-        os.unlink(self.f.name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)),
-                "reasons": sorted(reasons), "samples": len(sm)}
+                pass
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.smax, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.smax,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
 def make_mesh(grid, seed):

@@ -260,7 +260,11 @@ int om_destroy(om_handle* h) {
   cudaFree(h->bflag);
   cudaFree(h->perm);
   cudaFree(h->inv_perm);
-  cudaFree(h->ce);
+  cudaFree(h->cand);
+  cudaFree(h->work);
+  cudaFree(h->work_epoch);
+  cudaFree(h->cand_epoch);
+  cudaFree(h->sarr);
   cudaFree(h->best);
   cudaFree(h->flip_epoch);
   cudaFree(h->reloc);

@@ -38,6 +38,8 @@ struct DevScalars {
   unsigned long long n_limited;
   int n_flagged;   // non-Delaunay half-edges found in the last check
   int n_flips;     // flips applied in the last round
+  int n_cand;      // candidate list length
+  int n_work;      // work list length
   int err;         // OM_DEV_* bits
   int pad;
   double dot[4];   // PCG dot products
@@ -60,7 +62,11 @@ struct om_handle {
   int* perm = nullptr;       // internal -> caller vertex id (nullptr: identity)
   int* inv_perm = nullptr;   // caller -> internal
   // flip scratch
-  double* ce = nullptr;      // 4C covolume/edge ratios indexed by half-edge
+  int* cand = nullptr;       // C: cells with a flagged edge in the current round
+  int* work = nullptr;       // C: cells to re-check in the next round
+  int* work_epoch = nullptr; // C: dedupe stamps for the work list
+  int* cand_epoch = nullptr; // C: dedupe stamps for the candidate list
+  double* sarr = nullptr;    // 4C: s of flagged half-edges (+inf when not flagged)
   int8_t* best = nullptr;    // C: locally most negative flagged edge or -1
   int* flip_epoch = nullptr; // C
   int epoch = 0;
@@ -88,6 +94,7 @@ struct om_handle {
   double solver_rtol = 1e-13;
   int solver_max_iter = 100000;
   int64_t launches = 0;
+  double limited_frac = 1.0;  // share of vertices limited in the previous step
   // optional event timing (om_set_timing)
   bool timing = false;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};

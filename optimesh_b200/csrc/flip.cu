@@ -2,118 +2,205 @@
 //
 // Replaces meshplex's MeshTri.flip_until_delaunay() called by the optimize() loop after
 // every step (/root/reference/README.md:131-132).  Per round:
-//   k_ce      one thread per cell: covolume/edge ratios ce_k = -ed_k / (4A) of its 3 edges
-//   k_select  one thread per cell: s = ce(own) + ce(twin) per interior edge; flag s < -tol;
-//             keep the most negative flagged edge of the cell (ties: lowest local index)
-//   k_flip1   an edge kept by BOTH adjacent cells is flipped (an independent set: every
-//             cell takes part in at most one flip); rewrites the two cells, records where
-//             the four outer half-edges move
-//   k_flip2   patches the twin table using the relocation records (race-free when two
-//             neighbouring cells flip in the same round)
-// iterated until no edge is flagged.  (a0,k0) of a flip is the half-edge with the smaller
-// id 3*row+k in the caller's cell numbering, so the cell array is identical to the
-// oracle's, row for row.
+//   k_suspect one thread per cell: an edge can only violate the Delaunay criterion
+//             s = ce_k(c) + ce_k'(c') < -tol (ce_k = -ed_k / (4A)) if one of its two opposite
+//             angles is obtuse, and a triangle has at most one obtuse angle -- so each cell
+//             examines at most one edge, and only then touches its neighbour (whose term is
+//             recomputed from the opposite vertex; no per-cell intermediate array).
+//   k_select  flagged cells only: most negative flagged edge of the cell (ties: lowest
+//             local index).
+//   k_flip1   candidates only: an edge kept by BOTH adjacent cells is flipped (an
+//             independent set: every cell takes part in at most one flip); rewrites the two
+//             cells and records where the four outer half-edges move.
+//   k_flip2   candidates only: patches the twin table from the relocation records
+//             (race-free when neighbouring cells flip in the same round) and builds the
+//             work list of the next round: flipped cells, their outer neighbours and the
+//             candidates that lost -- the only cells whose edges can still be flagged.
+// Round 1 checks every cell, later rounds only the work list, until nothing is flagged.
+// (a0,k0) of a flip is the half-edge with the smaller id 3*row+k in the caller's cell
+// numbering, so the cell array is identical to the oracle's, row for row.  All dot
+// products are explicit fma chains: both cells of an edge see bit-identical s.
 #include "common.cuh"
 #include "geom.cuh"
 
 namespace {
 
 template <int D>
-__global__ void __launch_bounds__(256)
-    k_ce(const double* __restrict__ x, const int4* __restrict__ cells, int C,
-         double* __restrict__ ce, DevScalars* ds) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  int4 cl = cells[c];
-  Vec<D> P0 = ld_point<D>(x, cl.x), P1 = ld_point<D>(x, cl.y), P2 = ld_point<D>(x, cl.z);
-  CellGeo<D> g = cell_geo<D>(P0, P1, P2);
-  if (!(g.vol2 > 0.0)) {
-    atomicOr(&ds->err, OM_DEV_DEGENERATE);
-    return;
-  }
-  const double inv4A = 0.25 / sqrt(g.vol2);
-  double2* o = reinterpret_cast<double2*>(ce + 4 * (size_t)c);
-  o[0] = make_double2(-g.ed0 * inv4A, -g.ed1 * inv4A);
-  o[1] = make_double2(-g.ed2 * inv4A, 0.0);
+__device__ __forceinline__ double fdot(const Vec<D>& a, const Vec<D>& b) {
+  double s = __dmul_rn(a.v[0], b.v[0]);
+#pragma unroll
+  for (int k = 1; k < D; k++) s = __fma_rn(a.v[k], b.v[k], s);
+  return s;
 }
 
+// ed_k = e_{k+1} . e_{k+2} of a cell with vertices Q[0..2] (slot order)
+template <int D>
+__device__ __forceinline__ void cell_ed(const Vec<D> (&Q)[3], double (&ed)[3]) {
+  const Vec<D> e0 = vsub<D>(Q[2], Q[1]), e1 = vsub<D>(Q[0], Q[2]), e2 = vsub<D>(Q[1], Q[0]);
+  ed[0] = fdot<D>(e1, e2);
+  ed[1] = fdot<D>(e2, e0);
+  ed[2] = fdot<D>(e0, e1);
+}
+__device__ __forceinline__ double vol2_of(const double (&ed)[3]) {
+  // 0.25 (ed2 ed0 + ed0 ed1 + ed1 ed2)
+  double s = __dmul_rn(ed[2], ed[0]);
+  s = __fma_rn(ed[0], ed[1], s);
+  s = __fma_rn(ed[1], ed[2], s);
+  return 0.25 * s;
+}
+__device__ __forceinline__ double sel3(const double (&a)[3], int k) {
+  return k == 0 ? a[0] : (k == 1 ? a[1] : a[2]);
+}
+__device__ __forceinline__ int sel3i(const int (&a)[3], int k) {
+  return k == 0 ? a[0] : (k == 1 ? a[1] : a[2]);
+}
+
+// warp-aggregated append; must be called by all 32 lanes
+__device__ __forceinline__ void warp_append(int* counter, int* list, bool pred, int value) {
+  const unsigned m = __ballot_sync(0xffffffffu, pred);
+  if (!m) return;
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(m) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(counter, __popc(m));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (pred) list[base + __popc(m & ((1u << lane) - 1u))] = value;
+}
+
+// One thread per cell (all cells, or the work list).  A triangle has at most one obtuse
+// angle, and an edge can only violate the Delaunay criterion if one of its two opposite
+// angles is obtuse (ed > 0): so every cell examines at most ONE edge -- the one opposite
+// its own obtuse angle -- and the cheap path touches nothing but the cell's own vertices.
+// A flagged edge writes s into the slots of both half-edges and enlists both cells.
+template <int D, bool LIST>
 __global__ void __launch_bounds__(256)
-    k_select(const int4* __restrict__ adj, const double* __restrict__ ce, int C, double tol,
-             int8_t* __restrict__ best, DevScalars* ds) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  int nflag = 0;
-  if (c < C) {
-    int4 a = adj[c];
-    const double2* o = reinterpret_cast<const double2*>(ce + 4 * (size_t)c);
-    double2 c01 = o[0], c2 = o[1];
-    double own[3] = {c01.x, c01.y, c2.x};
-    int tw[3] = {a.x, a.y, a.z};
-    int b = -1;
-    double sb = 0.0;
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-      if (tw[k] >= 0) {
-        double s = own[k] + __ldg(ce + tw[k]);
-        if (s < -tol) {
-          nflag++;
-          if (b < 0 || s < sb) {
-            b = k;
-            sb = s;
-          }
-        }
-      }
+    k_suspect(const double* __restrict__ x, const int4* __restrict__ cells,
+              const int* __restrict__ adj, int n, const int* __restrict__ list, double tol,
+              double* __restrict__ sarr, int* __restrict__ cand, int* __restrict__ cand_epoch,
+              int epoch, DevScalars* ds) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool flag = false;
+  int c = -1, cn = -1;
+  do {  // no early return: the list appends below are warp-collective
+    if (i >= n) break;
+    c = LIST ? list[i] : i;
+    const int4 cl = cells[c];
+    // fetched up front (coalesced) so the slow path does not wait for it after the geometry
+    const int4 tw = __ldg(reinterpret_cast<const int4*>(adj) + c);
+    Vec<D> P[3] = {ld_point<D>(x, cl.x), ld_point<D>(x, cl.y), ld_point<D>(x, cl.z)};
+    double ed[3];
+    cell_ed<D>(P, ed);
+    const double vol2 = vol2_of(ed);
+    if (!(vol2 > 0.0)) {
+      atomicOr(&ds->err, OM_DEV_DEGENERATE);
+      break;
     }
-    best[c] = (int8_t)b;
-  }
-  for (int o = 16; o > 0; o >>= 1) nflag += __shfl_xor_sync(0xffffffffu, nflag, o);
-  if ((threadIdx.x & 31) == 0 && nflag) atomicAdd(&ds->n_flagged, nflag);
+    const int k = ed[0] > 0.0 ? 0 : (ed[1] > 0.0 ? 1 : (ed[2] > 0.0 ? 2 : -1));
+    if (k < 0) break;  // all angles <= 90 deg: nothing to examine from this side
+    const int t = k == 0 ? tw.x : (k == 1 ? tw.y : tw.z);
+    if (t < 0) break;  // boundary edge
+    cn = t >> 2;
+    const int kn = t & 3;
+    const int4 cln = __ldg(cells + cn);
+    const int nid[3] = {cln.x, cln.y, cln.z};
+    // neighbour's vertices in ITS slot order: slot kn is the opposite vertex, the other
+    // two are shared with this cell (slots (k+1)%3 and (k+2)%3 here)
+    const Vec<D> O = ld_point<D>(x, sel3i(nid, kn));
+    const int vid[3] = {cl.x, cl.y, cl.z};
+    const int ia = sel3i(vid, (k + 1) % 3);
+    const Vec<D> Pa = k == 0 ? P[1] : (k == 1 ? P[2] : P[0]);
+    const Vec<D> Pb = k == 0 ? P[2] : (k == 1 ? P[0] : P[1]);
+    Vec<D> Q[3];
+#pragma unroll
+    for (int s = 0; s < 3; s++) Q[s] = (s == kn) ? O : (nid[s] == ia ? Pa : Pb);
+    double edn[3];
+    cell_ed<D>(Q, edn);
+    const double vol2n = vol2_of(edn);
+    if (!(vol2n > 0.0)) break;  // reported by the neighbour itself
+    const double inv4A = 0.25 / sqrt(vol2), inv4An = 0.25 / sqrt(vol2n);
+    const double s =
+        __dadd_rn(__dmul_rn(-sel3(ed, k), inv4A), __dmul_rn(-sel3(edn, kn), inv4An));
+    if (s < -tol) {
+      sarr[4 * (size_t)c + k] = s;
+      sarr[t] = s;
+      flag = true;
+    }
+  } while (false);
+  // enlist both cells once (stamp dedupes; one atomic per warp on the shared counter)
+  const bool add0 = flag && atomicExch(&cand_epoch[c], epoch) != epoch;
+  warp_append(&ds->n_cand, cand, add0, c);
+  const bool add1 = flag && atomicExch(&cand_epoch[cn], epoch) != epoch;
+  warp_append(&ds->n_cand, cand, add1, cn);
+}
+
+// candidates: most negative flagged edge (ties: lowest local index); clears the s slots
+__global__ void __launch_bounds__(256)
+    k_select(double* __restrict__ sarr, const int* __restrict__ cand, int n,
+             int8_t* __restrict__ best) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = cand[i];
+  double2* p = reinterpret_cast<double2*>(sarr + 4 * (size_t)c);
+  const double2 s01 = p[0], s2 = p[1];
+  const double sv[3] = {s01.x, s01.y, s2.x};
+  int b = -1;
+  double sb = 0.0;
+#pragma unroll
+  for (int k = 0; k < 3; k++)
+    if (sv[k] < INFINITY && (b < 0 || sv[k] < sb)) {
+      b = k;
+      sb = sv[k];
+    }
+  best[c] = (int8_t)b;
+  p[0] = make_double2(INFINITY, INFINITY);
+  p[1] = make_double2(INFINITY, INFINITY);
 }
 
 __global__ void __launch_bounds__(256)
     k_flip1(int4* __restrict__ cells, const int4* __restrict__ adj, const int8_t* __restrict__ best,
-            int C, int epoch, int* __restrict__ flip_epoch, int* __restrict__ reloc,
-            int4* __restrict__ adj_tmp, int* __restrict__ v2c, DevScalars* ds) {
-  int a0 = blockIdx.x * blockDim.x + threadIdx.x;
+            const int* __restrict__ cand, int n, int epoch, int* __restrict__ flip_epoch,
+            int* __restrict__ reloc, int4* __restrict__ adj_tmp, int* __restrict__ v2c,
+            DevScalars* ds) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
   int nf = 0;
-  if (a0 < C) {
+  if (i < n) {
+    const int a0 = cand[i];
     const int k0 = best[a0];
-    if (k0 >= 0) {
-      const int4 adjA = adj[a0];
-      const int t = cell_get(adjA, k0);
-      const int a1 = t >> 2, k1 = t & 3;
-      if (best[a1] == k1) {
-        const int4 A = cells[a0];
-        const int4 Bc = cells[a1];
-        // the half-edge with the smaller caller-numbering id owns the flip
-        const long long hA = 3ll * A.w + k0, hB = 3ll * Bc.w + k1;
-        if (hA < hB) {
-          const int4 adjB = adj[a1];
-          const int v0 = cell_get(A, k0), v2 = cell_get(A, (k0 + 1) % 3),
-                    v3 = cell_get(A, (k0 + 2) % 3), v1 = cell_get(Bc, k1);
-          const int s2 = slot_of(Bc, v2), s3 = slot_of(Bc, v3);
-          if (s2 < 0 || s3 < 0) {
-            atomicOr(&ds->err, OM_DEV_NONMANIFOLD);
-          } else {
-            const int tA1 = cell_get(adjA, (k0 + 1) % 3);  // across (v3,v0)
-            const int tA2 = cell_get(adjA, (k0 + 2) % 3);  // across (v0,v2)
-            const int tB2 = cell_get(adjB, s2);            // across (v1,v3)
-            const int tB3 = cell_get(adjB, s3);            // across (v1,v2)
-            cells[a0] = make_int4(v0, v1, v2, A.w);
-            cells[a1] = make_int4(v0, v1, v3, Bc.w);
-            // new outer edges, still naming the OLD twins; slot 2 is the shared new edge
-            adj_tmp[a0] = make_int4(tB3, tA2, 4 * a1 + 2, 0);
-            adj_tmp[a1] = make_int4(tB2, tA1, 4 * a0 + 2, 0);
-            reloc[4 * a0 + (k0 + 1) % 3] = 4 * a1 + 1;
-            reloc[4 * a0 + (k0 + 2) % 3] = 4 * a0 + 1;
-            reloc[4 * a1 + s2] = 4 * a1 + 0;
-            reloc[4 * a1 + s3] = 4 * a0 + 0;
-            flip_epoch[a0] = epoch;
-            flip_epoch[a1] = epoch;
-            // v2 lost a1, v3 lost a0 (at most one flip per round can own v2c[v])
-            if (v2c[v2] == a1) v2c[v2] = a0;
-            if (v2c[v3] == a0) v2c[v3] = a1;
-            nf = 1;
-          }
+    const int4 adjA = adj[a0];
+    const int t = cell_get(adjA, k0);
+    const int a1 = t >> 2, k1 = t & 3;
+    if (best[a1] == k1) {
+      const int4 A = cells[a0];
+      const int4 Bc = cells[a1];
+      // the half-edge with the smaller caller-numbering id owns the flip
+      const long long hA = 3ll * A.w + k0, hB = 3ll * Bc.w + k1;
+      if (hA < hB) {
+        const int4 adjB = adj[a1];
+        const int v0 = cell_get(A, k0), v2 = cell_get(A, (k0 + 1) % 3),
+                  v3 = cell_get(A, (k0 + 2) % 3), v1 = cell_get(Bc, k1);
+        const int s2 = slot_of(Bc, v2), s3 = slot_of(Bc, v3);
+        if (s2 < 0 || s3 < 0) {
+          atomicOr(&ds->err, OM_DEV_NONMANIFOLD);
+        } else {
+          const int tA1 = cell_get(adjA, (k0 + 1) % 3);  // across (v3,v0)
+          const int tA2 = cell_get(adjA, (k0 + 2) % 3);  // across (v0,v2)
+          const int tB2 = cell_get(adjB, s2);            // across (v1,v3)
+          const int tB3 = cell_get(adjB, s3);            // across (v1,v2)
+          cells[a0] = make_int4(v0, v1, v2, A.w);
+          cells[a1] = make_int4(v0, v1, v3, Bc.w);
+          // new outer edges, still naming the OLD twins; slot 2 is the shared new edge
+          adj_tmp[a0] = make_int4(tB3, tA2, 4 * a1 + 2, 0);
+          adj_tmp[a1] = make_int4(tB2, tA1, 4 * a0 + 2, 0);
+          reloc[4 * a0 + (k0 + 1) % 3] = 4 * a1 + 1;
+          reloc[4 * a0 + (k0 + 2) % 3] = 4 * a0 + 1;
+          reloc[4 * a1 + s2] = 4 * a1 + 0;
+          reloc[4 * a1 + s3] = 4 * a0 + 0;
+          flip_epoch[a0] = epoch;
+          flip_epoch[a1] = epoch;
+          // v2 lost a1, v3 lost a0 (at most one flip per round can own v2c[v])
+          if (v2c[v2] == a1) v2c[v2] = a0;
+          if (v2c[v3] == a0) v2c[v3] = a1;
+          nf = 1;
         }
       }
     }
@@ -124,60 +211,90 @@ __global__ void __launch_bounds__(256)
 
 __global__ void __launch_bounds__(256)
     k_flip2(int* __restrict__ adj, const int4* __restrict__ adj_tmp,
-            const int* __restrict__ flip_epoch, const int* __restrict__ reloc, int C, int epoch) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  if (flip_epoch[c] != epoch) return;
-  const int4 t = adj_tmp[c];
-  const int told[2] = {t.x, t.y};
+            const int* __restrict__ flip_epoch, const int* __restrict__ reloc,
+            const int* __restrict__ cand, int n, int epoch, int* __restrict__ work_epoch,
+            int* __restrict__ work, int8_t* __restrict__ best, DevScalars* ds) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  // cells to enlist for the next round: self (flipped or lost), the two outer neighbours
+  // and the flip partner
+  int add[4] = {-1, -1, -1, -1};
+  if (i < n) {
+    const int c = cand[i];
+    best[c] = -1;  // k_flip1 is done with it; non-candidates must read "no flagged edge"
+    add[0] = c;
+    if (flip_epoch[c] == epoch) {
+      const int4 t = adj_tmp[c];
+      const int told[2] = {t.x, t.y};
 #pragma unroll
-  for (int s = 0; s < 2; s++) {
-    const int to = told[s];
-    int tn = to;
-    if (to >= 0) {
-      if (flip_epoch[to >> 2] == epoch)
-        tn = reloc[to];  // the neighbour flipped too: it patches its own side
-      else
-        adj[to] = 4 * c + s;
+      for (int s = 0; s < 2; s++) {
+        const int to = told[s];
+        int tn = to;
+        if (to >= 0) {
+          if (flip_epoch[to >> 2] == epoch)
+            tn = reloc[to];  // the neighbour flipped too: it patches its own side
+          else
+            adj[to] = 4 * c + s;
+          add[1 + s] = tn >> 2;
+        }
+        adj[4 * c + s] = tn;
+      }
+      adj[4 * c + 2] = t.z;
+      add[3] = t.z >> 2;
     }
-    adj[4 * c + s] = tn;
   }
-  adj[4 * c + 2] = t.z;
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const bool pred = add[q] >= 0 && atomicExch(&work_epoch[add[q]], epoch) != epoch;
+    warp_append(&ds->n_work, work, pred, add[q]);
+  }
 }
 
-__global__ void k_reset_flip_scalars(DevScalars* ds) {
+__global__ void k_reset_flip_scalars(DevScalars* ds, int keep_work) {
   ds->n_flagged = 0;
   ds->n_flips = 0;
+  ds->n_cand = 0;
+  if (!keep_work) ds->n_work = 0;
 }
 
 template <int D>
 int flip_rounds(om_handle* h, double tol, int max_rounds, int64_t* n_flips, int32_t* n_rounds,
                 int32_t* cap_hit) {
   const int C = (int)h->C;
-  const int B = 256, G = om_grid(C, B);
+  const int B = 256;
   int64_t total = 0;
   int rounds = 0;
   int cap = 0;
+  int n_work = 0;
   for (int r = 0;; r++) {
-    OM_LAUNCH(h, k_reset_flip_scalars, 1, 1, h->ds);
-    OM_LAUNCH(h, k_ce<D>, G, B, h->x, h->cells, C, h->ce, h->ds);
-    OM_LAUNCH(h, k_select, G, B, h->adj, h->ce, C, tol, h->best, h->ds);
+    OM_LAUNCH(h, k_reset_flip_scalars, 1, 1, h->ds, 0);
+    h->epoch++;
+    if (r == 0)
+      OM_LAUNCH(h, (k_suspect<D, false>), om_grid(C, B), B, h->x, h->cells, (const int*)h->adj, C,
+                (const int*)nullptr, tol, h->sarr, h->cand, h->cand_epoch, h->epoch, h->ds);
+    else if (n_work > 0)
+      OM_LAUNCH(h, (k_suspect<D, true>), om_grid(n_work, B), B, h->x, h->cells,
+                (const int*)h->adj, n_work, h->work, tol, h->sarr, h->cand, h->cand_epoch,
+                h->epoch, h->ds);
     OM_TRY(om_fetch_scalars(h));
     OM_TRY(om_check_dev_err(h));
-    if (h->hs->n_flagged == 0) break;
+    const int n_cand = h->hs->n_cand;
+    if (n_cand == 0) break;
     if (r >= max_rounds) {
       cap = 1;
       break;
     }
-    h->epoch++;
-    OM_LAUNCH(h, k_flip1, G, B, h->cells, h->adj, h->best, C, h->epoch, h->flip_epoch, h->reloc,
-              h->adj_tmp, h->v2c, h->ds);
-    OM_LAUNCH(h, k_flip2, G, B, (int*)h->adj, h->adj_tmp, h->flip_epoch, h->reloc, C, h->epoch);
+    OM_LAUNCH(h, k_select, om_grid(n_cand, B), B, h->sarr, h->cand, n_cand, h->best);
+    OM_LAUNCH(h, k_flip1, om_grid(n_cand, B), B, h->cells, h->adj, h->best, h->cand, n_cand,
+              h->epoch, h->flip_epoch, h->reloc, h->adj_tmp, h->v2c, h->ds);
+    OM_LAUNCH(h, k_flip2, om_grid(n_cand, B), B, (int*)h->adj, h->adj_tmp, h->flip_epoch, h->reloc,
+              h->cand, n_cand, h->epoch, h->work_epoch, h->work, h->best, h->ds);
     OM_TRY(om_fetch_scalars(h));
     OM_TRY(om_check_dev_err(h));
     total += h->hs->n_flips;
+    n_work = h->hs->n_work;
     rounds++;
     h->nbr_valid = false;
+    if (h->hs->n_flips == 0) break;  // flagged edges but no mutual pair (exact ties)
   }
   if (n_flips) *n_flips = total;
   if (n_rounds) *n_rounds = rounds;

@@ -112,5 +112,7 @@ __device__ __forceinline__ CellGeo<D> cell_geo(const Vec<D>& P0, const Vec<D>& P
 
 // ordered-integer encoding of non-negative doubles for atomicMax
 __device__ __forceinline__ void atomic_max_nonneg(unsigned long long* addr, double v) {
-  atomicMax(addr, (unsigned long long)__double_as_longlong(v));
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+  // a stale read can only under-estimate the maximum: skipping is safe when bits <= it
+  if (bits > *(volatile unsigned long long*)addr) atomicMax(addr, bits);
 }

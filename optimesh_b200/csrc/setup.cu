@@ -188,6 +188,11 @@ __global__ void k_pair_twins(const unsigned long long* __restrict__ keys,
   }
 }
 
+__global__ void k_fill_double(double* p, int64_t n, double v) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
 __global__ void k_fill_int(int* p, int64_t n, int v) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -272,8 +277,12 @@ int om_setup_mesh(om_handle* h, const double* points_dev, const void* cells_dev,
   CUDA_TRY(cudaMalloc(&h->adj_tmp, sizeof(int4) * std::max<int64_t>(C, 1)));
   CUDA_TRY(cudaMalloc(&h->v2c, sizeof(int) * N));
   CUDA_TRY(cudaMalloc(&h->bflag, N));
-  CUDA_TRY(cudaMalloc(&h->ce, sizeof(double) * 4 * std::max<int64_t>(C, 1)));
+  CUDA_TRY(cudaMalloc(&h->cand, sizeof(int) * std::max<int64_t>(C, 1)));
+  CUDA_TRY(cudaMalloc(&h->work, sizeof(int) * std::max<int64_t>(C, 1)));
+  CUDA_TRY(cudaMalloc(&h->work_epoch, sizeof(int) * std::max<int64_t>(C, 1)));
   CUDA_TRY(cudaMalloc(&h->best, std::max<int64_t>(C, 1)));
+  CUDA_TRY(cudaMalloc(&h->cand_epoch, sizeof(int) * std::max<int64_t>(C, 1)));
+  CUDA_TRY(cudaMalloc(&h->sarr, sizeof(double) * 4 * std::max<int64_t>(C, 1)));
   CUDA_TRY(cudaMalloc(&h->flip_epoch, sizeof(int) * std::max<int64_t>(C, 1)));
   CUDA_TRY(cudaMalloc(&h->reloc, sizeof(int) * 4 * std::max<int64_t>(C, 1)));
   CUDA_TRY(cudaMalloc(&h->ds, sizeof(DevScalars)));
@@ -281,6 +290,11 @@ int om_setup_mesh(om_handle* h, const double* points_dev, const void* cells_dev,
   CUDA_TRY(cudaMalloc(&h->partials, sizeof(double) * 8 * 2048));
   CUDA_TRY(cudaMemsetAsync(h->ds, 0, sizeof(DevScalars), h->stream));
   CUDA_TRY(cudaMemsetAsync(h->flip_epoch, 0, sizeof(int) * std::max<int64_t>(C, 1), h->stream));
+  CUDA_TRY(cudaMemsetAsync(h->work_epoch, 0, sizeof(int) * std::max<int64_t>(C, 1), h->stream));
+  CUDA_TRY(cudaMemsetAsync(h->cand_epoch, 0, sizeof(int) * std::max<int64_t>(C, 1), h->stream));
+  CUDA_TRY(cudaMemsetAsync(h->best, 0xff, std::max<int64_t>(C, 1), h->stream));
+  OM_LAUNCH(h, k_fill_double, om_grid(4 * std::max<int64_t>(C, 1), B), B, h->sarr,
+            4 * std::max<int64_t>(C, 1), (double)INFINITY);
   CUDA_TRY(cudaMemsetAsync(h->bflag, 0, N, h->stream));
   CUDA_TRY(cudaMemsetAsync(h->adj, 0xff, sizeof(int4) * std::max<int64_t>(C, 1), h->stream));
 
