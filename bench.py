@@ -40,13 +40,10 @@ def parse():
 
 
 def workload(args):
-    """BASELINE.json configs[1] at N=1; configs[4] (Lloyd omega=2) when sharded."""
-    if args.gpus == 1:
-        method = args.method or "cvt-block-diagonal"
-        omega = 1.0 if args.omega is None else args.omega
-    else:
-        method = args.method or "lloyd"
-        omega = 2.0 if args.omega is None else args.omega
+    """BASELINE.json configs[1] (CVT block-diagonal, ~10M vertices, fp64) per GPU: the mesh
+    grows with the number of GPUs (weak scaling), each rank updates its share of it."""
+    method = args.method or "cvt-block-diagonal"
+    omega = 1.0 if args.omega is None else args.omega
     return method, omega, args.grid or DEFAULT_GRID
 
 
@@ -207,14 +204,70 @@ def run_b200(args):
     import optimesh_b200 as ob
 
     method, omega, grid = workload(args)
-    pts, cells = make_mesh(grid, rank)
-    n, d = pts.shape
-    c = cells.shape[0]
-    stream = torch.cuda.current_stream().cuda_stream
+    from optimesh_b200.dist import torch_stream_handle
 
-    dm = ob.DeviceMesh(pts, cells.astype(np.int32), device=local, stream=stream)
+    stream = torch_stream_handle()
+    if world == 1:
+        pts, cells = make_mesh(grid, 0)
+        n, d = pts.shape
+        c = cells.shape[0]
+        dm = ob.DeviceMesh(pts, cells.astype(np.int32), device=local, stream=stream)
+        total_grid = grid
+    else:
+        # one mesh of world x (per-GPU size) vertices, built on every GPU from the same seed
+        from optimesh_b200 import generators as G
+
+        total_grid = int(round(grid * np.sqrt(world)))
+        tp, tc = G.disk_mapped_grid_torch(total_grid, 0.25, 0, device=f"cuda:{local}")
+        n, d = int(tp.shape[0]), int(tp.shape[1])
+        c = int(tc.shape[0])
+        dm = ob.DeviceMesh.from_torch(tp, tc, stream=stream)
+        del tp, tc
+        torch.cuda.empty_cache()
     dm.set_method(method, omega)
     dm.flip_until_delaunay()  # the loop's initial flip pass (setup, untimed)
+    if world > 1:
+        from optimesh_b200.dist import chunk_of, device_points_tensor, owned_range, sharded_flip
+
+        lo, hi = owned_range(n, rank, world)
+        chunk = chunk_of(n, world)
+        dm.set_owned_range(lo, hi)
+
+    breakdown = [0.0, 0.0, 0.0, 0.0] if os.environ.get("OM_BENCH_BREAKDOWN") else None
+
+    def one_step():
+        """One loop iteration; at world > 1 the update is sharded, coordinates all-gathered
+        in place over NCCL, statistics all-reduced, flips replicated (dist.run_sharded)."""
+        if world == 1:
+            return dm.step(0.0)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if breakdown is not None \
+            else None
+        if ev:
+            ev[0].record()
+        st = dm.update_points(0.0)
+        if ev:
+            ev[1].record()
+        red = torch.tensor([st["max_diff2"], float(st["n_limited"])], dtype=torch.float64,
+                           device="cuda")
+        dist.all_reduce(red[:1], op=dist.ReduceOp.MAX)
+        dist.all_reduce(red[1:], op=dist.ReduceOp.SUM)
+        if ev:
+            ev[2].record()
+        x = device_points_tensor(dm)
+        out = x[: world * chunk]
+        send = out[rank * chunk:(rank + 1) * chunk].clone()
+        dist.all_gather_into_tensor(out, send)
+        if ev:
+            ev[3].record()
+        nf, nr = sharded_flip(dm)
+        if ev:
+            ev[4].record()
+            torch.cuda.synchronize()
+            for q in range(4):
+                breakdown[q] += ev[q].elapsed_time(ev[q + 1])
+        st["n_flips"], st["n_flip_rounds"] = nf, nr
+        st["max_diff2"], st["n_limited"] = float(red[0].item()), int(red[1].item())
+        return st
 
     def barrier():
         torch.cuda.synchronize()
@@ -223,7 +276,7 @@ def run_b200(args):
             torch.cuda.synchronize()
 
     for _ in range(args.warmup):
-        dm.step(0.0)
+        one_step()
     dm.set_timing(True)
     sampler = ClockSampler(local)
     barrier()
@@ -235,7 +288,7 @@ def run_b200(args):
     limited = 0
     e0.record()
     for _ in range(args.steps):
-        st = dm.step(0.0)
+        st = one_step()
         flips += st["n_flips"]
         rounds += st["n_flip_rounds"]
         limited += st["n_limited"]
@@ -243,6 +296,18 @@ def run_b200(args):
     barrier()
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
+    if breakdown is not None:
+        print(f"[rank {rank}] ms per step: update {breakdown[0] / (args.steps + args.warmup):.3f} "
+              f"reduce {breakdown[1] / (args.steps + args.warmup):.3f} "
+              f"gather {breakdown[2] / (args.steps + args.warmup):.3f} "
+              f"flip {breakdown[3] / (args.steps + args.warmup):.3f}", file=sys.stderr)
+        from optimesh_b200 import dist as _d
+
+        if _d.PROFILE:
+            calls = max(_d.PROFILE.get("calls", 1), 1)
+            print(f"[rank {rank}] sharded_flip ms/call: " + " ".join(
+                f"{k}={1e3 * v / calls:.3f}" if k not in ("calls", "records_n") else f"{k}={v}"
+                for k, v in _d.PROFILE.items()), file=sys.stderr)
     launches = dm.launch_count - l0
     tim = dm.timing()
     dm.set_timing(False)
@@ -250,15 +315,16 @@ def run_b200(args):
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-        cnt = torch.tensor([launches, flips], dtype=torch.int64, device="cuda")
+        cnt = torch.tensor([launches], dtype=torch.int64, device="cuda")
         dist.all_reduce(cnt)
-        launches, flips = int(cnt[0].item()), int(cnt[1].item())
-    value = world * n * args.steps / (ms * 1e-3)
+        launches = int(cnt[0].item())
+    value = n * args.steps / (ms * 1e-3)  # n = vertices of the whole (sharded) mesh
 
     # roofline of the dominant kernel (K1, fused step)
     peak, peak_src = measured_peak()
     k1_ms = tim["step_kernel_ms"] / max(tim["step_kernel_launches"], 1)
-    b_alg = alg_bytes(n, c, d)
+    n_own = n if world == 1 else (hi - lo)
+    b_alg = alg_bytes(n_own, int(round(c * n_own / max(n, 1))), d)  # this rank's launch
     achieved = b_alg / (k1_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "k1_traffic.json")
@@ -282,10 +348,14 @@ def run_b200(args):
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {
-            "workload": f"{method} omega={omega}, disk_mapped_grid({grid}) per GPU: {n} vertices / "
-                        f"{c} cells, fp64, step = point update + limiter + flip-until-Delaunay",
+            "workload": f"{method} omega={omega}, disk_mapped_grid({total_grid}): {n} vertices / "
+                        f"{c} cells ({n // world} vertices per GPU), fp64, step = point update + "
+                        f"limiter + flip-until-Delaunay",
             "method": method, "omega": omega, "n_vertices": n, "n_cells": c,
-            "parallelism": "1 GPU" if world == 1 else f"{world} independent mesh replicas",
+            "parallelism": "1 GPU" if world == 1 else
+            f"{world} GPUs: vertex ranges of one mesh, update sharded, coordinates all-gathered "
+            f"over NCCL each step, first flip round sharded by cell range (records all-gathered), "
+            f"later rounds replicated",
             "l2": "inputs (points+cells+twins = %.0f MB) larger than the 126 MB L2"
                   % ((16 * n + 32 * c) / 1e6),
         },
@@ -297,7 +367,7 @@ def run_b200(args):
         "gpu_launches": launches,
     }
 
-    if rank == 0 and not args.no_e2e:
+    if rank == 0 and world == 1 and not args.no_e2e:
         # end to end through the public API with HOST buffers: upload, setup, K steps,
         # download -- all inside the timed region
         e2e_steps = args.steps
@@ -333,6 +403,11 @@ def run_b200(args):
 
 
 def main():
+    # the contract is ONE JSON line on stdout: keep a private copy of stdout for it and send
+    # everything else (e.g. NCCL's version banner) to stderr
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real
     args = parse()
     if args.impl == "reference":
         run_reference(args)

@@ -26,6 +26,9 @@ extern "C" {
 
 typedef struct om_handle om_handle;
 
+/* vertices of slack at the end of the device point array (see om_points_device) */
+#define OM_POINT_PAD 1024
+
 /* method ids (names: README.md:80, :90, :104) */
 enum {
   OM_LLOYD = 0,              /* --method lloyd                 README.md:80  */
@@ -73,7 +76,8 @@ int om_device_count(int* n);
  * (README.md:131) under optimize_points_cells (README.md:124-126).
  *   points_host: N x dim float64, C-contiguous (dim 2 or 3)
  *   cells_host : C x 3 integers of cells_itemsize bytes (4 or 8)
- *   stream     : a cudaStream_t to run on, or NULL for a private stream
+ *   stream     : a cudaStream_t to run on, or NULL for a private (non-blocking) stream;
+ *                pass cudaStreamLegacy ((void*)1) to share the legacy default stream
  * Does: upload, optional renumbering, half-edge twin table, boundary flags.      */
 int om_create(om_handle** h, int device, void* stream, int64_t N, int dim, int64_t C,
               const double* points_host, const void* cells_host, int cells_itemsize,
@@ -144,6 +148,29 @@ int om_pack_points(om_handle* h, const int32_t* idx_dev, int64_t n, double* buf_
 int om_unpack_points(om_handle* h, const int32_t* idx_dev, int64_t n, const double* buf_dev);
 /* Vertices listed here are treated as pinned (ghost vertices of a partition). */
 int om_pin_vertices(om_handle* h, const int32_t* idx_host, int64_t n);
+
+/* Sharding the point update across several handles that hold the SAME mesh (one process
+ * per GPU; identical inputs give identical internal numbering): the handle only updates
+ * the internal vertex range [lo, hi) in om_update_points / om_step; the caller then makes
+ * every range visible everywhere (NCCL all-gather straight on the point array:
+ * om_points_device gives its address, layout N x stride doubles + OM_POINT_PAD vertices of
+ * slack so equal-sized chunks may overrun N).  hi < 0 restores the whole mesh. */
+int om_set_owned_range(om_handle* h, int64_t lo, int64_t hi);
+/* Sharded first round of flip-until-Delaunay (the only round that scans every cell):
+ *   om_flip_check_range  examines the internal cell range [cell_lo, cell_hi) and leaves the
+ *                        flagged edges as 16-byte records {int32 half_edge, int32 twin,
+ *                        double s} in a device buffer owned by the handle;
+ *   om_flip_add_records  applies records (this rank's or gathered from other ranks; device
+ *                        memory) -- call once per segment;
+ *   om_flip_finish       runs the remaining rounds (work lists only) like
+ *                        om_flip_until_delaunay.
+ * Every rank must add the records of ALL ranks, so that topology stays identical. */
+int om_flip_check_range(om_handle* h, double tol, int64_t cell_lo, int64_t cell_hi,
+                        int64_t* n_records, void** records_dev);
+int om_flip_add_records(om_handle* h, const void* records_dev, int64_t n);
+int om_flip_finish(om_handle* h, double tol, int max_rounds, int64_t* n_flips,
+                   int32_t* n_rounds, int32_t* cap_hit);
+int om_points_device(om_handle* h, double** points, int64_t* n_alloc, int32_t* stride);
 
 /* Per-kernel timing with CUDA events on the handle's stream (bench.py's roofline line):
  * when on, the fused step kernel (K1) and each flip-until-Delaunay pass are bracketed by

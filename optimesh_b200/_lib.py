@@ -68,6 +68,13 @@ SIGNATURES = {
     "om_pack_points": (C.c_int, [_H, C.c_void_p, C.c_int64, C.c_void_p]),
     "om_unpack_points": (C.c_int, [_H, C.c_void_p, C.c_int64, C.c_void_p]),
     "om_pin_vertices": (C.c_int, [_H, C.c_void_p, C.c_int64]),
+    "om_set_owned_range": (C.c_int, [_H, C.c_int64, C.c_int64]),
+    "om_flip_check_range": (C.c_int, [_H, C.c_double, C.c_int64, C.c_int64, _P(C.c_int64),
+                                      _P(C.c_void_p)]),
+    "om_flip_add_records": (C.c_int, [_H, C.c_void_p, C.c_int64]),
+    "om_flip_finish": (C.c_int, [_H, C.c_double, C.c_int, _P(C.c_int64), _P(C.c_int32),
+                                 _P(C.c_int32)]),
+    "om_points_device": (C.c_int, [_H, _P(C.c_void_p), _P(C.c_int64), _P(C.c_int32)]),
     "om_set_timing": (C.c_int, [_H, C.c_int]),
     "om_get_timing": (C.c_int, [_H, _P(C.c_double), _P(C.c_int64), _P(C.c_double),
                                 _P(C.c_int64)]),

@@ -25,8 +25,8 @@ int om_fetch_scalars(om_handle* h) {
   return OM_OK;
 }
 
+// Evaluates the error bits of the LAST om_fetch_scalars (every caller fetches right before).
 int om_check_dev_err(om_handle* h) {
-  OM_TRY(om_fetch_scalars(h));
   const int e = h->hs->err;
   if (!e) return OM_OK;
   CUDA_TRY(cudaMemsetAsync(&h->ds->err, 0, sizeof(int), h->stream));
@@ -265,6 +265,7 @@ int om_destroy(om_handle* h) {
   cudaFree(h->work_epoch);
   cudaFree(h->cand_epoch);
   cudaFree(h->sarr);
+  cudaFree(h->recs);
   cudaFree(h->best);
   cudaFree(h->flip_epoch);
   cudaFree(h->reloc);
@@ -520,6 +521,50 @@ int om_pin_vertices(om_handle* h, const int32_t* idx_host, int64_t n) {
   cudaFree(d);
   CUDA_TRY(e);
   h->nbr_valid = false;
+  return OM_OK;
+}
+
+int om_flip_check_range(om_handle* h, double tol, int64_t cell_lo, int64_t cell_hi,
+                        int64_t* n_records, void** records_dev) {
+  OM_ENTER(h);
+  if (cell_lo < 0 || cell_hi < cell_lo || cell_hi > h->C) {
+    om_set_error("cell range [%lld, %lld) outside [0, %lld]", (long long)cell_lo,
+                 (long long)cell_hi, (long long)h->C);
+    return OM_ERR_ARG;
+  }
+  OM_TRY(om_flip_check_range_impl(h, tol, cell_lo, cell_hi, n_records));
+  if (records_dev) *records_dev = (void*)h->recs;
+  return OM_OK;
+}
+
+int om_flip_add_records(om_handle* h, const void* records_dev, int64_t n) {
+  OM_ENTER(h);
+  return om_flip_add_records_impl(h, records_dev, n);
+}
+
+int om_flip_finish(om_handle* h, double tol, int max_rounds, int64_t* n_flips, int32_t* n_rounds,
+                   int32_t* cap_hit) {
+  OM_ENTER(h);
+  return om_flip_impl(h, tol, max_rounds, n_flips, n_rounds, cap_hit, true);
+}
+
+int om_set_owned_range(om_handle* h, int64_t lo, int64_t hi) {
+  OM_ENTER(h);
+  if (hi >= 0 && (lo < 0 || lo > hi || hi > h->N)) {
+    om_set_error("owned range [%lld, %lld) outside [0, %lld]", (long long)lo, (long long)hi,
+                 (long long)h->N);
+    return OM_ERR_ARG;
+  }
+  h->own_lo = hi >= 0 ? lo : 0;
+  h->own_hi = hi;
+  return OM_OK;
+}
+
+int om_points_device(om_handle* h, double** points, int64_t* n_alloc, int32_t* stride) {
+  OM_ENTER(h);
+  if (points) *points = h->x;
+  if (n_alloc) *n_alloc = h->N + OM_POINT_PAD;
+  if (stride) *stride = h->PD;
   return OM_OK;
 }
 

@@ -31,6 +31,13 @@ void om_set_error(const char* fmt, ...);
 // error bits raised by kernels
 enum { OM_DEV_DEGENERATE = 1, OM_DEV_NONMANIFOLD = 2, OM_DEV_INDEX = 4, OM_DEV_WALK = 8 };
 
+// a flagged edge found by the sharded Delaunay check: both half-edges and s
+struct FlipRec {
+  int he;
+  int twin;
+  double s;
+};
+
 // device-side scalars, mirrored into pinned host memory after each phase
 struct DevScalars {
   unsigned long long max_diff2_bits;  // non-negative double compared as integer
@@ -40,6 +47,8 @@ struct DevScalars {
   int n_flips;     // flips applied in the last round
   int n_cand;      // candidate list length
   int n_work;      // work list length
+  int n_rec;       // flagged-edge records written by the sharded check
+  int pad2;
   int err;         // OM_DEV_* bits
   int pad;
   double dot[4];   // PCG dot products
@@ -67,6 +76,7 @@ struct om_handle {
   int* work_epoch = nullptr; // C: dedupe stamps for the work list
   int* cand_epoch = nullptr; // C: dedupe stamps for the candidate list
   double* sarr = nullptr;    // 4C: s of flagged half-edges (+inf when not flagged)
+  FlipRec* recs = nullptr;   // C: records of the sharded check (allocated on first use)
   int8_t* best = nullptr;    // C: locally most negative flagged edge or -1
   int* flip_epoch = nullptr; // C
   int epoch = 0;
@@ -94,6 +104,8 @@ struct om_handle {
   double solver_rtol = 1e-13;
   int solver_max_iter = 100000;
   int64_t launches = 0;
+  // owned vertex range (internal numbering) when the step is sharded across handles
+  int64_t own_lo = 0, own_hi = -1;  // hi < 0: whole mesh
   double limited_frac = 1.0;  // share of vertices limited in the previous step
   // optional event timing (om_set_timing)
   bool timing = false;
@@ -118,7 +130,10 @@ int om_check_dev_err(om_handle* h);
 int om_setup_mesh(om_handle* h, const double* points_dev, const void* cells_dev, int flags);
 // flip.cu
 int om_flip_impl(om_handle* h, double tol, int max_rounds, int64_t* n_flips, int32_t* n_rounds,
-                 int32_t* cap_hit);
+                 int32_t* cap_hit, bool first_round_given = false);
+int om_flip_check_range_impl(om_handle* h, double tol, int64_t clo, int64_t chi,
+                             int64_t* n_records);
+int om_flip_add_records_impl(om_handle* h, const void* recs, int64_t n);
 // step.cu
 int om_update_points_impl(om_handle* h, double tol, om_step_stats* out, bool target_only,
                           double* target_out);

@@ -20,6 +20,8 @@
 // (a0,k0) of a flip is the half-edge with the smaller id 3*row+k in the caller's cell
 // numbering, so the cell array is identical to the oracle's, row for row.  All dot
 // products are explicit fma chains: both cells of an edge see bit-identical s.
+#include <algorithm>
+
 #include "common.cuh"
 #include "geom.cuh"
 
@@ -72,18 +74,23 @@ __device__ __forceinline__ void warp_append(int* counter, int* list, bool pred, 
 // angles is obtuse (ed > 0): so every cell examines at most ONE edge -- the one opposite
 // its own obtuse angle -- and the cheap path touches nothing but the cell's own vertices.
 // A flagged edge writes s into the slots of both half-edges and enlists both cells.
-template <int D, bool LIST>
+// MODE 0: cells [off, off+n); MODE 1: cells list[0..n); MODE 2: cells [off, off+n), flagged
+// edges are appended to `recs` instead of being applied (sharded check: the records of all
+// ranks are exchanged and applied by k_apply_records).
+template <int D, int MODE>
 __global__ void __launch_bounds__(256)
     k_suspect(const double* __restrict__ x, const int4* __restrict__ cells,
-              const int* __restrict__ adj, int n, const int* __restrict__ list, double tol,
-              double* __restrict__ sarr, int* __restrict__ cand, int* __restrict__ cand_epoch,
-              int epoch, DevScalars* ds) {
+              const int* __restrict__ adj, int off, int n, const int* __restrict__ list,
+              double tol, double* __restrict__ sarr, int* __restrict__ cand,
+              int* __restrict__ cand_epoch, int epoch, FlipRec* __restrict__ recs,
+              DevScalars* ds) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   bool flag = false;
-  int c = -1, cn = -1;
+  int c = -1, cn = -1, he = -1, tt = -1;
+  double sval = 0.0;
   do {  // no early return: the list appends below are warp-collective
     if (i >= n) break;
-    c = LIST ? list[i] : i;
+    c = MODE == 1 ? list[i] : off + i;
     const int4 cl = cells[c];
     // fetched up front (coalesced) so the slow path does not wait for it after the geometry
     const int4 tw = __ldg(reinterpret_cast<const int4*>(adj) + c);
@@ -121,15 +128,57 @@ __global__ void __launch_bounds__(256)
     const double s =
         __dadd_rn(__dmul_rn(-sel3(ed, k), inv4A), __dmul_rn(-sel3(edn, kn), inv4An));
     if (s < -tol) {
-      sarr[4 * (size_t)c + k] = s;
-      sarr[t] = s;
+      he = 4 * c + k;
+      tt = t;
+      sval = s;
       flag = true;
+      if (MODE != 2) {
+        sarr[he] = s;
+        sarr[t] = s;
+      }
     }
   } while (false);
+  if (MODE == 2) {
+    const unsigned m = __ballot_sync(0xffffffffu, flag);
+    if (m) {
+      const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+      int base = 0;
+      if (lane == leader) base = atomicAdd(&ds->n_rec, __popc(m));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (flag) {
+        FlipRec r;
+        r.he = he;
+        r.twin = tt;
+        r.s = sval;
+        recs[base + __popc(m & ((1u << lane) - 1u))] = r;
+      }
+    }
+    return;
+  }
   // enlist both cells once (stamp dedupes; one atomic per warp on the shared counter)
   const bool add0 = flag && atomicExch(&cand_epoch[c], epoch) != epoch;
   warp_append(&ds->n_cand, cand, add0, c);
   const bool add1 = flag && atomicExch(&cand_epoch[cn], epoch) != epoch;
+  warp_append(&ds->n_cand, cand, add1, cn);
+}
+
+// flagged-edge records (own or received from other ranks) -> s slots + candidate list
+__global__ void __launch_bounds__(256)
+    k_apply_records(const FlipRec* __restrict__ recs, int n, double* __restrict__ sarr,
+                    int* __restrict__ cand, int* __restrict__ cand_epoch, int epoch,
+                    DevScalars* ds) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int c = -1, cn = -1;
+  if (i < n) {
+    const FlipRec r = recs[i];
+    sarr[r.he] = r.s;
+    sarr[r.twin] = r.s;
+    c = r.he >> 2;
+    cn = r.twin >> 2;
+  }
+  const bool add0 = c >= 0 && atomicExch(&cand_epoch[c], epoch) != epoch;
+  warp_append(&ds->n_cand, cand, add0, c);
+  const bool add1 = cn >= 0 && atomicExch(&cand_epoch[cn], epoch) != epoch;
   warp_append(&ds->n_cand, cand, add1, cn);
 }
 
@@ -253,12 +302,13 @@ __global__ void k_reset_flip_scalars(DevScalars* ds, int keep_work) {
   ds->n_flagged = 0;
   ds->n_flips = 0;
   ds->n_cand = 0;
+  ds->n_rec = 0;
   if (!keep_work) ds->n_work = 0;
 }
 
 template <int D>
 int flip_rounds(om_handle* h, double tol, int max_rounds, int64_t* n_flips, int32_t* n_rounds,
-                int32_t* cap_hit) {
+                int32_t* cap_hit, bool first_round_given) {
   const int C = (int)h->C;
   const int B = 256;
   int64_t total = 0;
@@ -266,15 +316,20 @@ int flip_rounds(om_handle* h, double tol, int max_rounds, int64_t* n_flips, int3
   int cap = 0;
   int n_work = 0;
   for (int r = 0;; r++) {
-    OM_LAUNCH(h, k_reset_flip_scalars, 1, 1, h->ds, 0);
-    h->epoch++;
-    if (r == 0)
-      OM_LAUNCH(h, (k_suspect<D, false>), om_grid(C, B), B, h->x, h->cells, (const int*)h->adj, C,
-                (const int*)nullptr, tol, h->sarr, h->cand, h->cand_epoch, h->epoch, h->ds);
-    else if (n_work > 0)
-      OM_LAUNCH(h, (k_suspect<D, true>), om_grid(n_work, B), B, h->x, h->cells,
-                (const int*)h->adj, n_work, h->work, tol, h->sarr, h->cand, h->cand_epoch,
-                h->epoch, h->ds);
+    if (r == 0 && first_round_given) {
+      // candidates and s slots were filled by om_flip_add_records (sharded check)
+    } else {
+      OM_LAUNCH(h, k_reset_flip_scalars, 1, 1, h->ds, 0);
+      h->epoch++;
+      if (r == 0)
+        OM_LAUNCH(h, (k_suspect<D, 0>), om_grid(C, B), B, h->x, h->cells, (const int*)h->adj, 0,
+                  C, (const int*)nullptr, tol, h->sarr, h->cand, h->cand_epoch, h->epoch,
+                  (FlipRec*)nullptr, h->ds);
+      else if (n_work > 0)
+        OM_LAUNCH(h, (k_suspect<D, 1>), om_grid(n_work, B), B, h->x, h->cells,
+                  (const int*)h->adj, 0, n_work, h->work, tol, h->sarr, h->cand, h->cand_epoch,
+                  h->epoch, (FlipRec*)nullptr, h->ds);
+    }
     OM_TRY(om_fetch_scalars(h));
     OM_TRY(om_check_dev_err(h));
     const int n_cand = h->hs->n_cand;
@@ -304,15 +359,48 @@ int flip_rounds(om_handle* h, double tol, int max_rounds, int64_t* n_flips, int3
 
 }  // namespace
 
+// ---- sharded first round (om_flip_check_range / om_flip_add_records / om_flip_finish)
+int om_flip_check_range_impl(om_handle* h, double tol, int64_t clo, int64_t chi,
+                             int64_t* n_records) {
+  const int B = 256;
+  if (!h->recs) CUDA_TRY(cudaMalloc(&h->recs, sizeof(FlipRec) * std::max<int64_t>(h->C, 1)));
+  OM_LAUNCH(h, k_reset_flip_scalars, 1, 1, h->ds, 0);
+  h->epoch++;
+  const int n = (int)(chi - clo);
+  if (n > 0) {
+    if (h->D == 2)
+      OM_LAUNCH(h, (k_suspect<2, 2>), om_grid(n, B), B, h->x, h->cells, (const int*)h->adj,
+                (int)clo, n, (const int*)nullptr, tol, h->sarr, h->cand, h->cand_epoch, h->epoch,
+                h->recs, h->ds);
+    else
+      OM_LAUNCH(h, (k_suspect<3, 2>), om_grid(n, B), B, h->x, h->cells, (const int*)h->adj,
+                (int)clo, n, (const int*)nullptr, tol, h->sarr, h->cand, h->cand_epoch, h->epoch,
+                h->recs, h->ds);
+  }
+  OM_TRY(om_fetch_scalars(h));
+  OM_TRY(om_check_dev_err(h));
+  if (n_records) *n_records = h->hs->n_rec;
+  return OM_OK;
+}
+
+int om_flip_add_records_impl(om_handle* h, const void* recs, int64_t n) {
+  if (n <= 0) return OM_OK;
+  OM_LAUNCH(h, k_apply_records, om_grid(n, 256), 256, (const FlipRec*)recs, (int)n, h->sarr,
+            h->cand, h->cand_epoch, h->epoch, h->ds);
+  CUDA_TRY(cudaGetLastError());
+  return OM_OK;
+}
+
 int om_flip_impl(om_handle* h, double tol, int max_rounds, int64_t* n_flips, int32_t* n_rounds,
-                 int32_t* cap_hit) {
+                 int32_t* cap_hit, bool first_round_given) {
   if (n_flips) *n_flips = 0;
   if (n_rounds) *n_rounds = 0;
   if (cap_hit) *cap_hit = 0;
   if (h->C == 0) return OM_OK;
   if (h->timing) cudaEventRecord(h->ev[2], h->stream);
-  int rc = (h->D == 2) ? flip_rounds<2>(h, tol, max_rounds, n_flips, n_rounds, cap_hit)
-                       : flip_rounds<3>(h, tol, max_rounds, n_flips, n_rounds, cap_hit);
+  int rc = (h->D == 2)
+               ? flip_rounds<2>(h, tol, max_rounds, n_flips, n_rounds, cap_hit, first_round_given)
+               : flip_rounds<3>(h, tol, max_rounds, n_flips, n_rounds, cap_hit, first_round_given);
   if (h->timing && rc == OM_OK) {
     cudaEventRecord(h->ev[3], h->stream);
     cudaEventSynchronize(h->ev[3]);

@@ -260,7 +260,7 @@ int setup_points(om_handle* h, const double* raw, bool renumber) {
     cudaFree(bbox);
   }
   OM_LAUNCH(h, k_gather_points<D>, om_grid(N, B), B, raw, h->perm, N, h->x);
-  CUDA_TRY(cudaMemsetAsync(h->xnew, 0, sizeof(double) * N * h->PD, h->stream));
+  CUDA_TRY(cudaMemsetAsync(h->xnew, 0, sizeof(double) * (N + OM_POINT_PAD) * h->PD, h->stream));
   return OM_OK;
 }
 
@@ -270,8 +270,10 @@ int om_setup_mesh(om_handle* h, const double* points_dev, const void* cells_dev,
   const int64_t N = h->N, C = h->C;
   const int B = 256;
   const bool renumber = (flags & OM_RENUMBER) != 0;
-  CUDA_TRY(cudaMalloc(&h->x, sizeof(double) * N * h->PD));
-  CUDA_TRY(cudaMalloc(&h->xnew, sizeof(double) * N * h->PD));
+  // OM_POINT_PAD extra vertices: lets a caller all-gather equal-sized chunks in place
+  CUDA_TRY(cudaMalloc(&h->x, sizeof(double) * (N + OM_POINT_PAD) * h->PD));
+  CUDA_TRY(cudaMalloc(&h->xnew, sizeof(double) * (N + OM_POINT_PAD) * h->PD));
+  CUDA_TRY(cudaMemsetAsync(h->x, 0, sizeof(double) * (N + OM_POINT_PAD) * h->PD, h->stream));
   CUDA_TRY(cudaMalloc(&h->cells, sizeof(int4) * std::max<int64_t>(C, 1)));
   CUDA_TRY(cudaMalloc(&h->adj, sizeof(int4) * std::max<int64_t>(C, 1)));
   CUDA_TRY(cudaMalloc(&h->adj_tmp, sizeof(int4) * std::max<int64_t>(C, 1)));
@@ -331,6 +333,7 @@ int om_setup_mesh(om_handle* h, const double* points_dev, const void* cells_dev,
   cudaFree(ckeys2);
   cudaFree(cvals);
   cudaFree(cperm);
+  OM_TRY(om_fetch_scalars(h));
   OM_TRY(om_check_dev_err(h));
 
   // half-edge twins
@@ -355,6 +358,7 @@ int om_setup_mesh(om_handle* h, const double* points_dev, const void* cells_dev,
   }
   OM_LAUNCH(h, k_fill_int, om_grid(N, B), B, h->v2c, N, OM_NONE_CELL);
   if (C > 0) OM_LAUNCH(h, k_v2c, om_grid(C, B), B, h->cells, C, h->v2c);
+  OM_TRY(om_fetch_scalars(h));
   OM_TRY(om_check_dev_err(h));
   return OM_OK;
 }

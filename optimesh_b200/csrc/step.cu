@@ -140,6 +140,7 @@ struct StepParams {
   const int* v2c;
   const uint8_t* bflag;
   int N;
+  int lo, hi;  // vertices [lo, hi) are processed
   double omega;
   int limiter;
   DevScalars* ds;
@@ -220,11 +221,11 @@ template <int D, int METHOD, int MODE>
 __global__ void __launch_bounds__(256, (D == 2 ? 4 : 3)) k_step(StepParams p) {
   constexpr bool TARGET = MODE == 2;
   constexpr bool EXACT = MODE == 0;
-  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  const int v = p.lo + blockIdx.x * blockDim.x + threadIdx.x;
   double diff2 = 0.0;
   int limited = 0;
   int err = 0;
-  if (v < p.N) {
+  if (v < p.hi) {
     const Vec<D> P0 = ld_point<D>(p.x, v);
     Vec<D> out = P0;
     const int c0 = p.v2c[v];
@@ -308,7 +309,8 @@ __global__ void __launch_bounds__(256, (D == 2 ? 4 : 3)) k_step(StepParams p) {
 template <int D, int MODE>
 int launch_step(om_handle* h, const StepParams& p) {
   const int B = 256;
-  const int G = om_grid(h->N, B);
+  const int G = om_grid(p.hi - p.lo, B);
+  if (G == 0) return OM_OK;
   switch (h->method) {
     case OM_LLOYD:
       OM_LAUNCH(h, (k_step<D, OM_LLOYD, MODE>), G, B, p);
@@ -442,6 +444,8 @@ StepParams make_params(om_handle* h, double* out) {
   p.v2c = h->v2c;
   p.bflag = h->bflag;
   p.N = (int)h->N;
+  p.lo = 0;
+  p.hi = (int)h->N;
   p.omega = h->omega;
   p.limiter = h->limiter;
   p.ds = h->ds;
@@ -483,6 +487,11 @@ int om_update_points_impl(om_handle* h, double tol, om_step_stats* out, bool tar
     }
   } else {
     StepParams p = make_params(h, target_only ? target_out : h->xnew);
+    const bool ranged = !target_only && h->own_hi >= 0;
+    if (ranged) {
+      p.lo = (int)h->own_lo;
+      p.hi = (int)h->own_hi;
+    }
     // the lazy limiter pays off once few vertices are limited (the previous step tells)
     const int mode = target_only ? 2 : ((h->limiter && h->limited_frac > 0.25) ? 0 : 1);
     if (h->timing) cudaEventRecord(h->ev[0], h->stream);
@@ -502,8 +511,18 @@ int om_update_points_impl(om_handle* h, double tol, om_step_stats* out, bool tar
   }
   OM_TRY(om_check_dev_err(h));
   if (!target_only) {
-    std::swap(h->x, h->xnew);
-    h->limited_frac = (double)h->hs->n_limited / (double)h->N;
+    if (h->own_hi >= 0 && h->method != OM_CPT_LINEAR_SOLVE) {
+      // sharded step: only [lo, hi) was written; fold it back, the rest of x stays
+      const size_t off = (size_t)h->own_lo * h->PD, cnt = (size_t)(h->own_hi - h->own_lo) * h->PD;
+      if (cnt)
+        CUDA_TRY(cudaMemcpyAsync(h->x + off, h->xnew + off, sizeof(double) * cnt,
+                                 cudaMemcpyDeviceToDevice, h->stream));
+      h->limited_frac =
+          (double)h->hs->n_limited / (double)std::max<int64_t>(h->own_hi - h->own_lo, 1);
+    } else {
+      std::swap(h->x, h->xnew);
+      h->limited_frac = (double)h->hs->n_limited / (double)h->N;
+    }
   }
   if (out) {
     out->max_diff2 = bits_to_double(h->hs->max_diff2_bits);

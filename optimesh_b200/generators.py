@@ -144,3 +144,44 @@ SIMPLE1 = (
     np.array([[0.0, 0.0], [1.0, 0.0], [1.0, 1.0], [0.0, 1.0], [0.4, 0.5]]),
     np.array([[0, 1, 4], [1, 2, 4], [2, 3, 4], [3, 0, 4]]),
 )
+
+
+def disk_mapped_grid_torch(n: int, jitter: float = 0.25, seed: int = 0, device="cuda"):
+    """`disk_mapped_grid` built on the device with torch (same construction, torch's RNG):
+    float64 (n*n, 2) points and int32 (2 (n-1)^2, 3) cells as CUDA tensors.  For meshes that
+    are too large to build on the host within the bench's time budget."""
+    import torch
+
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    h = 1.0 / (n - 1)
+    g = torch.arange(n, dtype=torch.float64, device=device) * h
+    X = g.repeat(n)                      # x varies fastest
+    Y = g.repeat_interleave(n)
+    ii = torch.arange(n, device=device).repeat(n)
+    jj = torch.arange(n, device=device).repeat_interleave(n)
+    interior = (ii > 0) & (ii < n - 1) & (jj > 0) & (jj < n - 1)
+    jit = (torch.rand(n * n, 2, dtype=torch.float64, device=device, generator=gen) * 2 - 1) \
+        * (jitter * h)
+    X = X + jit[:, 0] * interior
+    Y = Y + jit[:, 1] * interior
+    del jit
+    x = 2.0 * X - 1.0
+    y = 2.0 * Y - 1.0
+    u = x * torch.sqrt(1.0 - 0.5 * y * y)
+    v = y * torch.sqrt(1.0 - 0.5 * x * x)
+    bnd = ~interior
+    rr = torch.sqrt(u[bnd] ** 2 + v[bnd] ** 2)
+    u[bnd] = u[bnd] / rr
+    v[bnd] = v[bnd] / rr
+    pts = torch.stack([u, v], dim=1).contiguous()
+    i = torch.arange(n - 1, device=device, dtype=torch.int32).repeat(n - 1)
+    j = torch.arange(n - 1, device=device, dtype=torch.int32).repeat_interleave(n - 1)
+    a = j * n + i
+    b = a + 1
+    c = a + n
+    d = c + 1
+    lower = torch.stack([a, b, d], dim=1)
+    upper = torch.stack([a, d, c], dim=1)
+    cells = torch.stack([lower, upper], dim=1).reshape(-1, 3).contiguous()
+    return pts, cells

@@ -68,6 +68,26 @@ class DeviceMesh:
                             points.ctypes.data, cells.ctypes.data, cells.dtype.itemsize,
                             _lib.OM_RENUMBER if renumber else 0))
 
+    @classmethod
+    def from_torch(cls, points, cells, renumber: bool = True, stream=None):
+        """Builds the mesh from CUDA tensors already resident in HBM (float64 (N,d) and
+        int32/int64 (C,3), contiguous) through om_create_device: no host round trip."""
+        lib = _lib.load()
+        if not (points.is_cuda and cells.is_cuda and points.is_contiguous()
+                and cells.is_contiguous()):
+            raise ValueError("from_torch needs contiguous CUDA tensors")
+        self = cls.__new__(cls)
+        self.n, self.dim = int(points.shape[0]), int(points.shape[1])
+        self.c = int(cells.shape[0])
+        itemsize = cells.element_size()
+        self.cells_dtype = np.dtype(np.int32 if itemsize == 4 else np.int64)
+        self._h = C.c_void_p()
+        self._lib = lib
+        check(lib.om_create_device(C.byref(self._h), points.device.index or 0, stream, self.n,
+                                   self.dim, self.c, points.data_ptr(), cells.data_ptr(),
+                                   itemsize, _lib.OM_RENUMBER if renumber else 0))
+        return self
+
     # -- lifetime
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
@@ -188,6 +208,33 @@ class DeviceMesh:
     def pin_vertices(self, idx):
         idx = np.ascontiguousarray(idx, dtype=np.int32)
         check(self._lib.om_pin_vertices(self._h, idx.ctypes.data, idx.size))
+
+    def flip_check_range(self, cell_lo: int, cell_hi: int, tol: float = 0.0):
+        """Sharded first flip round: returns (device pointer of the records, count)."""
+        n, p = C.c_int64(), C.c_void_p()
+        check(self._lib.om_flip_check_range(self._h, float(tol), int(cell_lo), int(cell_hi),
+                                            C.byref(n), C.byref(p)))
+        return p.value, n.value
+
+    def flip_add_records(self, ptr: int, n: int):
+        check(self._lib.om_flip_add_records(self._h, C.c_void_p(ptr), int(n)))
+
+    def flip_finish(self, tol: float = 0.0, max_steps: int = 100):
+        nf, nr, cap = C.c_int64(), C.c_int32(), C.c_int32()
+        check(self._lib.om_flip_finish(self._h, float(tol), int(max_steps), C.byref(nf),
+                                       C.byref(nr), C.byref(cap)))
+        if cap.value:
+            warnings.warn("Maximum number of edge flips reached.")
+        return nf.value, nr.value
+
+    def set_owned_range(self, lo: int, hi: int):
+        check(self._lib.om_set_owned_range(self._h, int(lo), int(hi)))
+
+    def points_device(self):
+        """(device pointer, allocated vertices, stride) of the internal point array."""
+        p, n, s = C.c_void_p(), C.c_int64(), C.c_int32()
+        check(self._lib.om_points_device(self._h, C.byref(p), C.byref(n), C.byref(s)))
+        return p.value, n.value, s.value
 
     def set_timing(self, on: bool = True):
         check(self._lib.om_set_timing(self._h, int(bool(on))))

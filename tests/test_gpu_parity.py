@@ -396,3 +396,48 @@ def test_full_size_properties(ob, G):
         a0 = pts[cells]
         area0 = 0.5 * np.abs(np.cross(a0[:, 1] - a0[:, 0], a0[:, 2] - a0[:, 0])).sum()
         assert abs(area - area0) < 1e-9 * area0
+
+
+# ------------------------------------------------------------------ sharded update
+@pytest.mark.parametrize("method,omega", [("lloyd", 2.0), ("cvt-block-diagonal", 1.0)])
+def test_sharded_simulation(ob, G, method, omega):
+    """Partition simulator: P handles hold the same mesh in one process, each updates its own
+    internal vertex range, ranges are copied across (what the NCCL all-gather does between
+    GPUs).  Must be bit-identical to the single-handle run."""
+    import torch
+
+    from optimesh_b200.dist import device_points_tensor, owned_range
+
+    pts, cells = G.disk(90, 11)
+    P, steps = 3, 6
+    ref_p, ref_c = ob.optimize_points_cells(pts, cells, method, 0.0, steps, omega=omega)
+    hs = [ob.DeviceMesh(pts, cells) for _ in range(P)]
+    try:
+        for r, h in enumerate(hs):
+            h.set_method(method, omega)
+            h.flip_until_delaunay()
+            h.set_owned_range(*owned_range(h.n, r, P))
+        for _ in range(steps):
+            for h in hs:
+                h.update_points(0.0)
+            xs = [device_points_tensor(h) for h in hs]
+            torch.cuda.synchronize()
+            for r in range(P):
+                lo, hi = owned_range(hs[r].n, r, P)
+                for s in range(P):
+                    if s != r:
+                        xs[s][lo:hi] = xs[r][lo:hi]
+            torch.cuda.synchronize()
+            # first flip round sharded by cell range, records applied by every handle
+            recs = [h.flip_check_range(*owned_range(h.c, r, P)) for r, h in enumerate(hs)]
+            for h in hs:
+                for ptr, cnt in recs:
+                    if cnt:
+                        h.flip_add_records(ptr, cnt)
+            flips = [h.flip_finish() for h in hs]
+            assert all(f == flips[0] for f in flips)
+        for h in hs:
+            assert np.array_equal(h.points, ref_p) and np.array_equal(h.cells(), ref_c)
+    finally:
+        for h in hs:
+            h.close()
