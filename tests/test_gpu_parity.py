@@ -441,3 +441,58 @@ def test_sharded_simulation(ob, G, method, omega):
     finally:
         for h in hs:
             h.close()
+
+
+# ------------------------------------------------------------------ BASELINE configs 3, 4 at full size
+def test_config3_full_size_square_cpt(ob, G):
+    """configs[2]: CPT linear-solve and CPT fixed-point on the 5M-vertex jittered square,
+    boundary pinned.  Size-independent checks: the solve is harmonic on interior rows
+    (independent scipy matvec), boundary untouched, fixed-point steps keep the boundary."""
+    import scipy.sparse
+
+    n = 2236
+    pts, cells = G.square(n, 0.25, 0)
+    assert pts.shape[0] == 4999696 and cells.shape[0] == 9990450
+    with ob.DeviceMesh(pts, cells.astype(np.int32)) as dm:
+        bnd = dm.is_boundary_point
+        assert bnd.sum() == 4 * (n - 1)
+        dm.flip_until_delaunay()
+        c = dm.cells()
+        its, res = dm.solve_graph_laplacian(1e-10, 100000)
+        x = dm.points
+        assert res <= 1e-10 and its > 0
+        assert np.array_equal(x[bnd], pts[bnd])
+        # residual of the Dirichlet graph Laplacian, computed independently on the host
+        i = np.concatenate([c[:, 0], c[:, 1], c[:, 2], c[:, 1], c[:, 2], c[:, 0]])
+        j = np.concatenate([c[:, 1], c[:, 2], c[:, 0], c[:, 0], c[:, 1], c[:, 2]])
+        A = scipy.sparse.coo_matrix((np.ones(i.size), (i, j)), shape=(len(pts), len(pts))).tocsr()
+        deg = np.asarray(A.sum(axis=1)).ravel()
+        r = (deg[:, None] * x - A @ x)[~bnd]
+        assert np.abs(r).max() <= 1e-9 * deg.max()
+        dm.points = pts
+        dm.set_method("cpt-fixed-point")
+        for _ in range(3):
+            st = dm.step(0.0)
+        p = dm.points
+        assert np.array_equal(p[bnd], pts[bnd]) and np.isfinite(p).all()
+        assert dm.flip_until_delaunay() == (0, 0)
+
+
+def test_config4_full_size_sphere_odt(ob, G):
+    """configs[3]: ODT fixed-point on the 2M-vertex tetra-sphere with projection each step."""
+    pts, cells = G.tetra_sphere(1000)
+    assert pts.shape[0] == 2000002 and cells.shape[0] == 4000000
+    with ob.DeviceMesh(pts, cells.astype(np.int32)) as dm:
+        assert not dm.is_boundary_point.any()
+        dm.set_method("odt-fixed-point")
+        dm.set_sphere()
+        dm.flip_until_delaunay()
+        q0 = dm.stats()[2]["q_avg"]
+        for _ in range(5):
+            st = dm.step(0.0)
+        p, c = dm.points, dm.cells()
+        assert np.abs(np.linalg.norm(p, axis=1) - 1.0).max() <= 1e-10
+        assert c.shape[0] == 2 * p.shape[0] - 4  # closed genus-0 surface: F = 2V - 4
+        assert np.array_equal(np.unique(c), np.arange(len(p)))
+        assert dm.stats()[2]["q_avg"] > q0  # smoothing improves the average quality
+        assert dm.flip_until_delaunay() == (0, 0)
