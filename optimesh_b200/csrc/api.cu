@@ -1,5 +1,6 @@
 // C-ABI of liboptimesh_b200.so (see include/optimesh_b200.h).
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <cstring>
@@ -181,6 +182,7 @@ int create_common(om_handle** out, int device, void* stream, int64_t N, int dim,
   h->D = dim;
   h->PD = dim == 2 ? 2 : 4;
   h->cells_itemsize = itemsize;
+  if (getenv("OM_NO_RINGS")) h->use_rings = false;  // diagnostics: star walk only
   int rc = OM_OK;
   auto fail = [&](int code) {
     om_destroy(h);
@@ -258,6 +260,10 @@ int om_destroy(om_handle* h) {
   cudaFree(h->adj_tmp);
   cudaFree(h->v2c);
   cudaFree(h->bflag);
+  cudaFree(h->ring);
+  cudaFree(h->dirty);
+  cudaFree(h->dirty_epoch);
+  cudaFree(h->over);
   cudaFree(h->perm);
   cudaFree(h->inv_perm);
   cudaFree(h->cand);
@@ -521,6 +527,7 @@ int om_pin_vertices(om_handle* h, const int32_t* idx_host, int64_t n) {
   cudaFree(d);
   CUDA_TRY(e);
   h->nbr_valid = false;
+  OM_TRY(om_rebuild_rings(h, true));  // pinned vertices have no ring row
   return OM_OK;
 }
 

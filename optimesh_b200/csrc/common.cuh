@@ -8,6 +8,7 @@
 #include "../../include/optimesh_b200.h"
 
 #define OM_NONE_CELL 0x7fffffff
+#define OM_RING_W 8
 
 // ---------------------------------------------------------------- error plumbing
 void om_set_error(const char* fmt, ...);
@@ -48,7 +49,9 @@ struct DevScalars {
   int n_cand;      // candidate list length
   int n_work;      // work list length
   int n_rec;       // flagged-edge records written by the sharded check
-  int pad2;
+  int n_dirty;     // vertices whose ring row must be rebuilt after the flip pass
+  int n_over;      // vertices without a ring row met by the step kernel
+  int pad3;
   int err;         // OM_DEV_* bits
   int pad;
   double dot[4];   // PCG dot products
@@ -68,6 +71,12 @@ struct om_handle {
   int4* adj = nullptr;       // C: twin half-edge (4*cell + slot) per local edge, -1 = boundary
   int* v2c = nullptr;        // N: one incident cell (OM_NONE_CELL for orphans)
   uint8_t* bflag = nullptr;  // N: 1 = pinned (boundary / ghost)
+  int* ring = nullptr;       // N x OM_RING_W: one-ring vertex ids of free interior vertices
+  int* dirty = nullptr;      // N: vertices touched by flips (ring rows to rebuild)
+  int* dirty_epoch = nullptr;// N: dedupe stamps for `dirty`
+  int dirty_pass = 0;
+  int* over = nullptr;       // N: vertices the ring-row kernel left to the walk kernel
+  bool use_rings = true;
   int* perm = nullptr;       // internal -> caller vertex id (nullptr: identity)
   int* inv_perm = nullptr;   // caller -> internal
   // flip scratch
@@ -138,6 +147,7 @@ int om_flip_add_records_impl(om_handle* h, const void* recs, int64_t n);
 int om_update_points_impl(om_handle* h, double tol, om_step_stats* out, bool target_only,
                           double* target_out);
 int om_project_impl(om_handle* h, int32_t* sweeps);
+int om_rebuild_rings(om_handle* h, bool all);
 // pcg.cu
 int om_pcg_impl(om_handle* h, double rtol, int max_iter, int32_t* iters, double* relres,
                 double* out /* N*PD, may alias h->xnew */);

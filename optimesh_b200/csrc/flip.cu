@@ -57,18 +57,6 @@ __device__ __forceinline__ int sel3i(const int (&a)[3], int k) {
   return k == 0 ? a[0] : (k == 1 ? a[1] : a[2]);
 }
 
-// warp-aggregated append; must be called by all 32 lanes
-__device__ __forceinline__ void warp_append(int* counter, int* list, bool pred, int value) {
-  const unsigned m = __ballot_sync(0xffffffffu, pred);
-  if (!m) return;
-  const int lane = threadIdx.x & 31;
-  const int leader = __ffs(m) - 1;
-  int base = 0;
-  if (lane == leader) base = atomicAdd(counter, __popc(m));
-  base = __shfl_sync(0xffffffffu, base, leader);
-  if (pred) list[base + __popc(m & ((1u << lane) - 1u))] = value;
-}
-
 // One thread per cell (all cells, or the work list).  A triangle has at most one obtuse
 // angle, and an edge can only violate the Delaunay criterion if one of its two opposite
 // angles is obtuse (ed > 0): so every cell examines at most ONE edge -- the one opposite
@@ -124,6 +112,14 @@ __global__ void __launch_bounds__(256)
     cell_ed<D>(Q, edn);
     const double vol2n = vol2_of(edn);
     if (!(vol2n > 0.0)) break;  // reported by the neighbour itself
+    // Cheap rejection before any sqrt/division.  With ea = ed_k > 0 (obtuse here) and
+    // eb = ed_k' < 0 (acute there): s < 0  <=>  ea / A > -eb / A'  <=>  ea^2 A'^2 > eb^2 A^2.
+    // Edges within 1e-9 of equality still go through the exact evaluation below, so every
+    // flag decision is taken on the exact s.
+    {
+      const double ea = sel3(ed, k), eb = sel3(edn, kn);
+      if (tol >= 0.0 && eb < 0.0 && !(ea * ea * vol2n > eb * eb * vol2 * (1.0 - 1e-9))) break;
+    }
     const double inv4A = 0.25 / sqrt(vol2), inv4An = 0.25 / sqrt(vol2n);
     const double s =
         __dadd_rn(__dmul_rn(-sel3(ed, k), inv4A), __dmul_rn(-sel3(edn, kn), inv4An));
@@ -139,27 +135,37 @@ __global__ void __launch_bounds__(256)
     }
   } while (false);
   if (MODE == 2) {
+    // records: reserve one slot per flagged thread (block-aggregated), then write
+    __shared__ int r_warp[8];
+    __shared__ int r_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned m = __ballot_sync(0xffffffffu, flag);
-    if (m) {
-      const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
-      int base = 0;
-      if (lane == leader) base = atomicAdd(&ds->n_rec, __popc(m));
-      base = __shfl_sync(0xffffffffu, base, leader);
-      if (flag) {
-        FlipRec r;
-        r.he = he;
-        r.twin = tt;
-        r.s = sval;
-        recs[base + __popc(m & ((1u << lane) - 1u))] = r;
+    if (lane == 0) r_warp[warp] = __popc(m);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); w++) {
+        const int t2 = r_warp[w];
+        r_warp[w] = tot;
+        tot += t2;
       }
+      r_base = tot ? atomicAdd(&ds->n_rec, tot) : 0;
+    }
+    __syncthreads();
+    if (flag) {
+      FlipRec r;
+      r.he = he;
+      r.twin = tt;
+      r.s = sval;
+      recs[r_base + r_warp[warp] + __popc(m & ((1u << lane) - 1u))] = r;
     }
     return;
   }
-  // enlist both cells once (stamp dedupes; one atomic per warp on the shared counter)
-  const bool add0 = flag && atomicExch(&cand_epoch[c], epoch) != epoch;
-  warp_append(&ds->n_cand, cand, add0, c);
-  const bool add1 = flag && atomicExch(&cand_epoch[cn], epoch) != epoch;
-  warp_append(&ds->n_cand, cand, add1, cn);
+  // enlist both cells once (stamp dedupes; one atomic per block on the shared counter)
+  const int vals[2] = {c, cn};
+  const bool preds[2] = {flag && atomicExch(&cand_epoch[c], epoch) != epoch,
+                         flag && atomicExch(&cand_epoch[cn], epoch) != epoch};
+  block_append<2>(&ds->n_cand, cand, vals, preds);
 }
 
 // flagged-edge records (own or received from other ranks) -> s slots + candidate list
@@ -176,10 +182,10 @@ __global__ void __launch_bounds__(256)
     c = r.he >> 2;
     cn = r.twin >> 2;
   }
-  const bool add0 = c >= 0 && atomicExch(&cand_epoch[c], epoch) != epoch;
-  warp_append(&ds->n_cand, cand, add0, c);
-  const bool add1 = cn >= 0 && atomicExch(&cand_epoch[cn], epoch) != epoch;
-  warp_append(&ds->n_cand, cand, add1, cn);
+  const int vals[2] = {c, cn};
+  const bool preds[2] = {c >= 0 && atomicExch(&cand_epoch[c], epoch) != epoch,
+                         cn >= 0 && atomicExch(&cand_epoch[cn], epoch) != epoch};
+  block_append<2>(&ds->n_cand, cand, vals, preds);
 }
 
 // candidates: most negative flagged edge (ties: lowest local index); clears the s slots
@@ -209,9 +215,11 @@ __global__ void __launch_bounds__(256)
     k_flip1(int4* __restrict__ cells, const int4* __restrict__ adj, const int8_t* __restrict__ best,
             const int* __restrict__ cand, int n, int epoch, int* __restrict__ flip_epoch,
             int* __restrict__ reloc, int4* __restrict__ adj_tmp, int* __restrict__ v2c,
+            int* __restrict__ dirty, int* __restrict__ dirty_epoch, int dirty_pass,
             DevScalars* ds) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   int nf = 0;
+  int dv[4] = {0, 0, 0, 0};  // the four vertices of the flip this thread applied
   if (i < n) {
     const int a0 = cand[i];
     const int k0 = best[a0];
@@ -249,10 +257,22 @@ __global__ void __launch_bounds__(256)
           // v2 lost a1, v3 lost a0 (at most one flip per round can own v2c[v])
           if (v2c[v2] == a1) v2c[v2] = a0;
           if (v2c[v3] == a0) v2c[v3] = a1;
+          // the four stars changed: their ring rows are rebuilt after the pass
+          dv[0] = v0;
+          dv[1] = v1;
+          dv[2] = v2;
+          dv[3] = v3;
           nf = 1;
         }
       }
     }
+  }
+  if (dirty) {
+    bool dp[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+      dp[q] = nf && atomicExch(&dirty_epoch[dv[q]], dirty_pass) != dirty_pass;
+    block_append<4>(&ds->n_dirty, dirty, dv, dp);
   }
   for (int o = 16; o > 0; o >>= 1) nf += __shfl_xor_sync(0xffffffffu, nf, o);
   if ((threadIdx.x & 31) == 0 && nf) atomicAdd(&ds->n_flips, nf);
@@ -291,11 +311,11 @@ __global__ void __launch_bounds__(256)
       add[3] = t.z >> 2;
     }
   }
+  bool preds[4];
 #pragma unroll
-  for (int q = 0; q < 4; q++) {
-    const bool pred = add[q] >= 0 && atomicExch(&work_epoch[add[q]], epoch) != epoch;
-    warp_append(&ds->n_work, work, pred, add[q]);
-  }
+  for (int q = 0; q < 4; q++)
+    preds[q] = add[q] >= 0 && atomicExch(&work_epoch[add[q]], epoch) != epoch;
+  block_append<4>(&ds->n_work, work, add, preds);
 }
 
 __global__ void k_reset_flip_scalars(DevScalars* ds, int keep_work) {
@@ -340,7 +360,8 @@ int flip_rounds(om_handle* h, double tol, int max_rounds, int64_t* n_flips, int3
     }
     OM_LAUNCH(h, k_select, om_grid(n_cand, B), B, h->sarr, h->cand, n_cand, h->best);
     OM_LAUNCH(h, k_flip1, om_grid(n_cand, B), B, h->cells, h->adj, h->best, h->cand, n_cand,
-              h->epoch, h->flip_epoch, h->reloc, h->adj_tmp, h->v2c, h->ds);
+              h->epoch, h->flip_epoch, h->reloc, h->adj_tmp, h->v2c, h->dirty, h->dirty_epoch,
+              h->dirty_pass, h->ds);
     OM_LAUNCH(h, k_flip2, om_grid(n_cand, B), B, (int*)h->adj, h->adj_tmp, h->flip_epoch, h->reloc,
               h->cand, n_cand, h->epoch, h->work_epoch, h->work, h->best, h->ds);
     OM_TRY(om_fetch_scalars(h));
@@ -364,6 +385,8 @@ int om_flip_check_range_impl(om_handle* h, double tol, int64_t clo, int64_t chi,
                              int64_t* n_records) {
   const int B = 256;
   if (!h->recs) CUDA_TRY(cudaMalloc(&h->recs, sizeof(FlipRec) * std::max<int64_t>(h->C, 1)));
+  h->dirty_pass++;  // a new flip pass starts here
+  CUDA_TRY(cudaMemsetAsync(&h->ds->n_dirty, 0, sizeof(int), h->stream));
   OM_LAUNCH(h, k_reset_flip_scalars, 1, 1, h->ds, 0);
   h->epoch++;
   const int n = (int)(chi - clo);
@@ -393,14 +416,23 @@ int om_flip_add_records_impl(om_handle* h, const void* recs, int64_t n) {
 
 int om_flip_impl(om_handle* h, double tol, int max_rounds, int64_t* n_flips, int32_t* n_rounds,
                  int32_t* cap_hit, bool first_round_given) {
+  int64_t local_flips = 0;
+  if (!n_flips) n_flips = &local_flips;
   if (n_flips) *n_flips = 0;
   if (n_rounds) *n_rounds = 0;
   if (cap_hit) *cap_hit = 0;
   if (h->C == 0) return OM_OK;
+  if (!first_round_given) {
+    h->dirty_pass++;
+    CUDA_TRY(cudaMemsetAsync(&h->ds->n_dirty, 0, sizeof(int), h->stream));
+  }
   if (h->timing) cudaEventRecord(h->ev[2], h->stream);
   int rc = (h->D == 2)
                ? flip_rounds<2>(h, tol, max_rounds, n_flips, n_rounds, cap_hit, first_round_given)
                : flip_rounds<3>(h, tol, max_rounds, n_flips, n_rounds, cap_hit, first_round_given);
+  // ring rows of the vertices whose stars changed (hs->n_dirty is current: the last
+  // readback of the pass came after the last flip)
+  if (rc == OM_OK && n_flips && *n_flips > 0) rc = om_rebuild_rings(h, false);
   if (h->timing && rc == OM_OK) {
     cudaEventRecord(h->ev[3], h->stream);
     cudaEventSynchronize(h->ev[3]);

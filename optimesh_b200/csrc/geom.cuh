@@ -116,3 +116,44 @@ __device__ __forceinline__ void atomic_max_nonneg(unsigned long long* addr, doub
   // a stale read can only under-estimate the maximum: skipping is safe when bits <= it
   if (bits > *(volatile unsigned long long*)addr) atomicMax(addr, bits);
 }
+
+// Block-aggregated list append: every thread of the (256-thread) block calls it with up to K
+// (value, predicate) pairs; ONE returning atomic per block reserves the space.  The shared
+// counters live on a single address each, and a returning atomic per warp made the flip
+// kernels wait on the L2 atomic unit instead of on memory (ncu: > 50 % of the stall samples
+// sat on the shuffle that broadcasts the atomic's result).
+template <int K>
+__device__ __forceinline__ void block_append(int* counter, int* __restrict__ list,
+                                             const int (&vals)[K], const bool (&preds)[K]) {
+  __shared__ int s_warp[8];
+  __shared__ int s_base;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int cnt = 0;
+#pragma unroll
+  for (int q = 0; q < K; q++) cnt += preds[q] ? 1 : 0;
+  int incl = cnt;  // inclusive scan over the warp
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int up = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += up;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int tot = 0;
+    const int nw = (int)(blockDim.x >> 5);
+    for (int w = 0; w < nw; w++) {
+      const int t = s_warp[w];
+      s_warp[w] = tot;
+      tot += t;
+    }
+    s_base = tot ? atomicAdd(counter, tot) : 0;
+  }
+  __syncthreads();
+  int pos = s_base + s_warp[warp] + incl - cnt;
+#pragma unroll
+  for (int q = 0; q < K; q++)
+    if (preds[q]) list[pos++] = vals[q];
+  __syncthreads();  // s_warp / s_base may be reused by the next call
+}
+

@@ -358,6 +358,14 @@ int om_setup_mesh(om_handle* h, const double* points_dev, const void* cells_dev,
   }
   OM_LAUNCH(h, k_fill_int, om_grid(N, B), B, h->v2c, N, OM_NONE_CELL);
   if (C > 0) OM_LAUNCH(h, k_v2c, om_grid(C, B), B, h->cells, C, h->v2c);
+  if (N > 0) {
+    CUDA_TRY(cudaMalloc(&h->ring, sizeof(int) * OM_RING_W * N));
+    CUDA_TRY(cudaMalloc(&h->dirty, sizeof(int) * N));
+    CUDA_TRY(cudaMalloc(&h->dirty_epoch, sizeof(int) * N));
+    CUDA_TRY(cudaMalloc(&h->over, sizeof(int) * N));
+    CUDA_TRY(cudaMemsetAsync(h->dirty_epoch, 0, sizeof(int) * N, h->stream));
+    OM_TRY(om_rebuild_rings(h, true));
+  }
   OM_TRY(om_fetch_scalars(h));
   OM_TRY(om_check_dev_err(h));
   return OM_OK;

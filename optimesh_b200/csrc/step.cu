@@ -23,14 +23,35 @@
 
 namespace {
 
+// Per-vertex accumulators, kept in SCALED units so that constant factors are applied once
+// per vertex instead of once per cell visit (q = 1/(4A), t_k = ed_k q = -ce_k,
+// w_k = ee_k t_k = -4 part_k):
+//   Lloyd/CVT:  w   = sum (w_1 + w_2)               = -4 cv
+//               num = sum s2' e2 - s1' e1           = -12 cv (centroid - x)
+//               H   = sum t_1 e1 e1^T + t_2 e2 e2^T = 2 x (CVT Hessian block without 2 cv I)
+//   CPT/ODT:    w = sum A, num = 3 sum A (r_c - x)
 template <int D>
 struct Acc {
-  double w;                   // control volume (Lloyd/CVT) or summed cell area (CPT/ODT)
-  Vec<D> num;                 // 3 x weighted offsets from the vertex (thirds applied at the end)
-  double H[D * (D + 1) / 2];  // CVT block: sum -0.5 ce_k e_k e_k^T (upper triangle)
+  double w;
+  Vec<D> num;
+  double H[D * (D + 1) / 2];  // upper triangle
   double rmin;                // EXACT: smallest incident inradius
   double lb_num, lb_den;      // LAZY: cell minimising A^2 / sum(ee) (kept as a fraction)
 };
+
+// 1/sqrt(x) for positive, normal x (the caller has checked x > 0): hardware seed
+// (rsqrt.approx.f64, relative error < 2^-22) + two Newton steps, no special-case branch.
+__device__ __forceinline__ double fast_rsqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double hx = 0.5 * x;
+#pragma unroll
+  for (int it = 0; it < 2; it++) {
+    const double t = fma(-hx * y, y, 0.5);  // 0.5 - 0.5 x y^2
+    y = fma(y, t, y);
+  }
+  return y;
+}
 
 // exact inradius of one cell (A.3): 2A / (l0 + l1 + l2)
 template <int D>
@@ -40,65 +61,73 @@ __device__ __forceinline__ double inradius(const CellGeo<D>& g) {
 }
 
 // Contribution of one incident cell to vertex P0 (P1, P2 follow in slot order).
+// Only the two edges at the vertex are formed (e1 = P0 - P2, e2 = P1 - P0); since
+// e0 + e1 + e2 = 0 every other product follows from ee1, ee2 and ed0 = e1.e2:
+//   ed1 = -(ed0 + ee2), ed2 = -(ed0 + ee1), ee0 = ee1 + ee2 + 2 ed0, A^2 = (ee1 ee2 - ed0^2)/4.
 template <int D, int METHOD, bool EXACT>
 __device__ __forceinline__ void accumulate_cell(const Vec<D>& P0, const Vec<D>& P1,
                                                 const Vec<D>& P2, Acc<D>& a, int& err) {
-  const CellGeo<D> g = cell_geo<D>(P0, P1, P2);
-  if (!(g.vol2 > 0.0)) {
+  const Vec<D> e1 = vsub<D>(P0, P2), e2 = vsub<D>(P1, P0);
+  const double ee1 = vdot<D>(e1, e1), ee2 = vdot<D>(e2, e2), ed0 = vdot<D>(e1, e2);
+  const double vol2 = 0.25 * fma(ee1, ee2, -ed0 * ed0);
+  if (!(vol2 > 0.0)) {
     err |= OM_DEV_DEGENERATE;
     return;
   }
+  const double ed1 = -(ed0 + ee2), ed2 = -(ed0 + ee1);
+  const double S = 2.0 * (ee1 + ee2 + ed0);  // ee0 + ee1 + ee2
   if (EXACT) {
-    a.rmin = fmin(a.rmin, inradius<D>(g));
-  } else {
-    const double S = g.ee0 + g.ee1 + g.ee2;
-    if (g.vol2 * a.lb_den < a.lb_num * S) {
-      a.lb_num = g.vol2;
-      a.lb_den = S;
-    }
+    const double A = sqrt(vol2);
+    a.rmin = fmin(a.rmin, 2.0 * A / (sqrt(S - ee1 - ee2) + sqrt(ee1) + sqrt(ee2)));
+  } else if (vol2 * a.lb_den < a.lb_num * S) {
+    a.lb_num = vol2;
+    a.lb_den = S;
   }
-  const double r = rsqrt(g.vol2);  // 1/A
+  const double r = fast_rsqrt(vol2);  // 1/A
   if (METHOD == OM_CPT_FIXED_POINT) {
     // 3 (barycenter - P0) = e2 - e1
-    const double A = g.vol2 * r;
+    const double A = vol2 * r;
     a.w += A;
 #pragma unroll
-    for (int k = 0; k < D; k++) a.num.v[k] += A * (g.e2.v[k] - g.e1.v[k]);
+    for (int k = 0; k < D; k++) a.num.v[k] += A * (e2.v[k] - e1.v[k]);
     return;
   }
-  // circumcenter - P0 = alpha1 (P1 - P0) + alpha2 (P2 - P0) = alpha1 e2 - alpha2 e1 with
-  // alpha_k = ee_k ed_k / sum_j ee_j ed_j and sum_j ee_j ed_j = -8 A^2
-  const double inva = -0.125 * (r * r);
-  const double al1 = g.ee1 * g.ed1 * inva, al2 = g.ee2 * g.ed2 * inva;
   if (METHOD == OM_ODT_FIXED_POINT) {
-    const double A = g.vol2 * r;
-    a.w += A;
-    const double s2 = 3.0 * A * al1, s1 = 3.0 * A * al2;
+    // 3 A (circumcenter - P0) = 3 A (al1 e2 - al2 e1), al_k = ee_k ed_k / (-8 A^2), A = vol2 r
+    a.w += vol2 * r;
+    const double f = -0.375 * r;
+    const double s2 = ee1 * ed1 * f, s1 = ee2 * ed2 * f;
 #pragma unroll
-    for (int k = 0; k < D; k++) a.num.v[k] += s2 * g.e2.v[k] - s1 * g.e1.v[k];
+    for (int k = 0; k < D; k++) a.num.v[k] += s2 * e2.v[k] - s1 * e1.v[k];
     return;
   }
-  // Lloyd / CVT block-diagonal (A.4, A.9)
-  const double inv4A = 0.25 * r;
-  const double ce0 = -g.ed0 * inv4A, ce1 = -g.ed1 * inv4A, ce2 = -g.ed2 * inv4A;
-  if (ce0 < -0.5 || ce1 < -0.5 || ce2 < -0.5) return;  // cell masked (an angle > 135 deg)
-  const double part1 = 0.25 * g.ee1 * ce1, part2 = 0.25 * g.ee2 * ce2;
-  const double pw = part1 + part2;
-  a.w += pw;
-  // 3 x sub-triangle centroids relative to P0: part_k ((m_k - P0) + (cc - P0)) with
-  // m_1 - P0 = -e1/2, m_2 - P0 = e2/2, cc - P0 = al1 e2 - al2 e1
-  const double s2 = pw * al1 + 0.5 * part2, s1 = pw * al2 + 0.5 * part1;
+  // Lloyd / CVT block-diagonal (A.4, A.9), scaled as described at Acc
+  const double q = 0.25 * r;
+  const double t0 = ed0 * q, t1 = ed1 * q, t2 = ed2 * q;  // -ce_k
+  if (t0 > 0.5 || t1 > 0.5 || t2 > 0.5) return;  // cell masked (an angle > 135 deg)
+  const double w1 = ee1 * t1, w2 = ee2 * t2;  // -4 part_k
+  const double ws = w1 + w2;
+  a.w += ws;
+  // al_k = ee_k ed_k (-1/(8A^2)) = -2 q w_k;  -12 x [part1 (cc - e1/2) + part2 (cc + e2/2)]
+  //   = e2 (u w1 + w2/2 ... ) with u = -2 q ws:  s2' = u w1 - 0.5 w2 ... (signs folded below)
+  const double u = -2.0 * q * ws;
+  const double s2 = fma(u, w1, 0.5 * w2), s1 = fma(u, w2, 0.5 * w1);
 #pragma unroll
-  for (int k = 0; k < D; k++) a.num.v[k] += s2 * g.e2.v[k] - s1 * g.e1.v[k];
+  for (int k = 0; k < D; k++) a.num.v[k] += s2 * e2.v[k] - s1 * e1.v[k];
   if (METHOD == OM_CVT_BLOCK_DIAGONAL) {
-    const double h1 = -0.5 * ce1, h2 = -0.5 * ce2;
-    int q = 0;
+    Vec<D> a1, a2;
+#pragma unroll
+    for (int k = 0; k < D; k++) {
+      a1.v[k] = t1 * e1.v[k];
+      a2.v[k] = t2 * e2.v[k];
+    }
+    int qi = 0;
 #pragma unroll
     for (int i = 0; i < D; i++)
 #pragma unroll
       for (int j = i; j < D; j++) {
-        a.H[q] += h1 * g.e1.v[i] * g.e1.v[j] + h2 * g.e2.v[i] * g.e2.v[j];
-        q++;
+        a.H[qi] += a1.v[i] * e1.v[j] + a2.v[i] * e2.v[j];
+        qi++;
       }
   }
 }
@@ -139,6 +168,10 @@ struct StepParams {
   const int* adj;  // flat view of the int4 twin table: adj[4*c + k]
   const int* v2c;
   const uint8_t* bflag;
+  const int* ring;  // N x OM_RING_W ring rows, or nullptr
+  const int* list;  // SRC 2: vertices to process
+  int n_list;
+  int* over;        // SRC 0: vertices left to the walk kernel
   int N;
   int lo, hi;  // vertices [lo, hi) are processed
   double omega;
@@ -146,7 +179,7 @@ struct StepParams {
   DevScalars* ds;
 };
 
-// Block-level reduction of the step statistics (256 threads): one conditional atomic per
+// Block-level reduction of the step statistics (up to 256 threads): one conditional atomic per
 // block on the shared scalars (max and integer add are order independent).
 __device__ __forceinline__ void reduce_step_stats(double diff2, int limited, DevScalars* ds) {
   __shared__ double s_d[8];
@@ -163,8 +196,7 @@ __device__ __forceinline__ void reduce_step_stats(double diff2, int limited, Dev
   if (threadIdx.x == 0) {
     double d = s_d[0];
     int l = s_l[0];
-#pragma unroll
-    for (int w = 1; w < 8; w++) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); w++) {
       d = fmax(d, s_d[w]);
       l += s_l[w];
     }
@@ -214,25 +246,157 @@ __device__ __forceinline__ void walk_star(const StepParams& p, int v, int c0, co
   }
 }
 
-// MODE 0: step, exact inradius in the main walk (most vertices limited: early steps)
-// MODE 1: step, lazy limiter (bound first, exact re-walk only where needed)
+// ---- ring rows: the one-ring of a vertex as (up to) OM_RING_W neighbour vertex ids
+// Entry q holds n_q | (f_q << 30); cell q of the star is (v, n_q, n_{q+1 mod k}) and f_q says
+// whether its slot order is (v, n_{q+1}, n_q) instead of (v, n_q, n_{q+1}).  Unused entries are
+// -1; entry 0 == -2 marks a vertex the kernel must walk instead (pinned/boundary vertex, open
+// fan, or more than OM_RING_W cells).  The order is the walk order, so the sums are
+// bit-identical to the walk; the rows only remove the dependent adj -> cell -> point chains.
+// threads per block of the step kernels (3D: smaller, its ring staging is twice as wide)
+template <int D>
+__host__ __device__ constexpr int step_block() {
+  return D == 2 ? 256 : 128;
+}
+constexpr int RING_FLAG = 1 << 30;
+constexpr int RING_MASK = RING_FLAG - 1;
+
+template <bool LIST>
+__global__ void __launch_bounds__(256)
+    k_build_rings(const int4* __restrict__ cells, const int* __restrict__ adj,
+                  const int* __restrict__ v2c, const uint8_t* __restrict__ bflag, int n,
+                  const int* __restrict__ list, int* __restrict__ ring) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int v = LIST ? list[i] : i;
+  int e[OM_RING_W];
+#pragma unroll
+  for (int q = 0; q < OM_RING_W; q++) e[q] = -1;
+  bool ok = false;
+  const int c0 = v2c[v];
+  if (c0 != OM_NONE_CELL && !bflag[v]) {
+    const int4 cell0 = __ldg(cells + c0);
+    const int j = slot_of(cell0, v);
+    if (j >= 0) {
+      int k = 0;  // cells closed so far
+      int last = cell_get(cell0, (j + 2) % 3);
+      e[0] = cell_get(cell0, (j + 1) % 3);  // cell 0 = (v, n0, n1), slot order kept
+      int cur = c0, kexit = (j + 1) % 3;
+      ok = true;
+      while (true) {
+        k++;
+        const int t = __ldg(adj + 4 * (size_t)cur + kexit);
+        if (t < 0) {  // open fan
+          ok = false;
+          break;
+        }
+        const int cn = t >> 2, kn = t & 3;
+        if (cn == c0) break;  // closed: `last` is n0 again
+        if (k >= OM_RING_W) {
+          ok = false;
+          break;
+        }
+        const int4 cl = __ldg(cells + cn);
+        const int jn = slot_of(cl, v);
+        if (jn < 0 || jn == kn) {
+          ok = false;
+          break;
+        }
+        const int p1 = cell_get(cl, (jn + 1) % 3), p2 = cell_get(cl, (jn + 2) % 3);
+        // cell k = (v, last, new): slot order (v, last, new) iff p1 == last
+        const int flag = (p1 == last) ? 0 : RING_FLAG;
+        const int nxt = (p1 == last) ? p2 : p1;
+#pragma unroll
+        for (int q = 1; q < OM_RING_W; q++)
+          if (q == k) e[q] = last | flag;
+        last = nxt;
+        cur = cn;
+        kexit = 3 - jn - kn;
+      }
+    }
+  }
+  if (!ok) e[0] = -2;
+  int4* out = reinterpret_cast<int4*>(ring + (size_t)OM_RING_W * v);
+  out[0] = make_int4(e[0], e[1], e[2], e[3]);
+  out[1] = make_int4(e[4], e[5], e[6], e[7]);
+}
+
+// MODE 0: step, exact inradius in the main pass (most vertices limited: early steps)
+// MODE 1: step, lazy limiter (bound first, exact second pass only where needed)
 // MODE 2: write the un-relaxed, un-limited target (get_new_points)
-template <int D, int METHOD, int MODE>
-__global__ void __launch_bounds__(256, (D == 2 ? 4 : 3)) k_step(StepParams p) {
+// SRC 0: vertices [lo, hi), one-ring from the ring rows; vertices without a row that must
+//        move are appended to p.over and left to a SRC 2 launch
+// SRC 1: vertices [lo, hi), star walk
+// SRC 2: vertices p.list[0 .. n_list), star walk
+template <int D, int METHOD, int MODE, int SRC>
+__global__ void __launch_bounds__(step_block<D>(), (SRC == 0 ? (D == 2 ? 4 : 3) : (D == 2 ? 4 : 3)))
+    k_step(StepParams p) {
   constexpr bool TARGET = MODE == 2;
   constexpr bool EXACT = MODE == 0;
-  const int v = p.lo + blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = SRC == 2 ? (i < p.n_list) : (p.lo + i < p.hi);
   double diff2 = 0.0;
   int limited = 0;
   int err = 0;
-  if (v < p.hi) {
+  bool deferred = false;  // left to the list-driven exact launch
+  int vdef = 0;
+  if (active) {
+    const int v = SRC == 2 ? p.list[i] : p.lo + i;
+    vdef = v;
     const Vec<D> P0 = ld_point<D>(p.x, v);
     Vec<D> out = P0;
     const int c0 = p.v2c[v];
     const bool pinned = p.bflag[v] != 0;
     // the Lloyd target of a boundary vertex is its real control-volume centroid; every
     // other consumer pins boundary vertices
-    const bool walk = (c0 != OM_NONE_CELL) && (!pinned || (TARGET && METHOD == OM_LLOYD));
+    bool walk = (c0 != OM_NONE_CELL) && (!pinned || (TARGET && METHOD == OM_LLOYD));
+
+    // SRC 0: the ring vertices are staged in shared memory by cp.async (one 16-byte copy
+    // per vertex in 2D, two in 3D; all in flight at once, no registers held), slot
+    // [q][thread] so that a warp's accesses are conflict free.  Every thread only reads the
+    // slots it filled itself: no block barrier is needed.
+    __shared__ double2 ring_sm[SRC == 0 ? OM_RING_W * (D == 2 ? 1 : 2) * step_block<D>() : 1];
+    int nring = 0;         // cells (= ring vertices) in the row
+    unsigned rflags = 0u;  // bit q: cell q has slot order (v, n_{q+1}, n_q)
+    int4 cell = make_int4(0, 0, 0, 0);
+    int j = 0;
+    if (walk) {
+      if (SRC == 0) {
+        const int4* rp = reinterpret_cast<const int4*>(p.ring + (size_t)OM_RING_W * v);
+        const int4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+        const int e[OM_RING_W] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+        if (e[0] == -2) {
+          // no row (more than OM_RING_W cells, or an open fan): the walk kernel does it
+          deferred = true;
+          walk = false;
+        } else {
+          constexpr int PER = (D == 2) ? 1 : 2;  // 16-byte pieces per vertex
+#pragma unroll
+          for (int q = 0; q < OM_RING_W; q++)
+            if (e[q] >= 0) {
+              const double2* src =
+                  reinterpret_cast<const double2*>(p.x) + (size_t)PER * (e[q] & RING_MASK);
+#pragma unroll
+              for (int h2 = 0; h2 < PER; h2++) {
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(
+                    &ring_sm[(q * PER + h2) * step_block<D>() + threadIdx.x]);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst),
+                             "l"(src + h2));
+              }
+              nring = q + 1;
+              rflags |= (e[q] & RING_FLAG) ? (1u << q) : 0u;
+            }
+          asm volatile("cp.async.commit_group;");
+          asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+      } else {
+        cell = __ldg(p.cells + c0);
+        j = slot_of(cell, v);
+        if (j < 0) {
+          err |= OM_DEV_WALK;
+          walk = false;
+        }
+      }
+    }
     if (walk) {
       Acc<D> acc;
       acc.w = 0.0;
@@ -243,86 +407,122 @@ __global__ void __launch_bounds__(256, (D == 2 ? 4 : 3)) k_step(StepParams p) {
       for (int k = 0; k < D; k++) acc.num.v[k] = 0.0;
 #pragma unroll
       for (int k = 0; k < D * (D + 1) / 2; k++) acc.H[k] = 0.0;
-      const int4 cell = __ldg(p.cells + c0);
-      const int j = slot_of(cell, v);
-      if (j < 0) {
-        err |= OM_DEV_WALK;
-      } else {
-        walk_star<D>(p, v, c0, cell, j, err, [&](const Vec<D>& P1, const Vec<D>& P2) {
-          accumulate_cell<D, METHOD, EXACT>(P0, P1, P2, acc, err);
-        });
-        // method formula -> offset of the target from the vertex.  The reference divides
-        // by the control volume whatever its sign; only 0/0 (every adjacent cell masked)
-        // leaves the vertex where it is.
-        Vec<D> d;
-        bool ok = acc.w != 0.0;
-        if (METHOD == OM_CVT_BLOCK_DIAGONAL) {
-          Vec<D> rhs;  // -2 cv (x - c) = 2/3 num
+      // visits the cells of the star in walk order; f(P1, P2) gets the other two vertices
+      // of each cell in slot order
+      auto for_each_cell = [&](auto&& f) {
+        if (SRC == 0) {
+          constexpr int PER = (D == 2) ? 1 : 2;
+          auto ld_ring = [&](int q) {
+            Vec<D> r;
+            const double2 a = ring_sm[(q * PER) * step_block<D>() + threadIdx.x];
+            r.v[0] = a.x;
+            r.v[1] = a.y;
+            if (D == 3) r.v[D - 1] = ring_sm[(q * PER + PER - 1) * step_block<D>() + threadIdx.x].x;
+            return r;
+          };
+          Vec<D> A = ld_ring(0);
+#pragma unroll 2
+          for (int q = 0; q < nring; q++) {
+            const Vec<D> B = ld_ring(q + 1 < nring ? q + 1 : 0);
+            // select the operands (no divergent branch around the cell arithmetic)
+            const bool sw = (rflags >> q) & 1u;
+            Vec<D> X1, X2;
 #pragma unroll
-          for (int k = 0; k < D; k++) rhs.v[k] = (2.0 / 3.0) * acc.num.v[k];
-          ok = ok && solve_sym<D>(acc.H, 2.0 * acc.w, rhs, d);
-        } else if (ok) {
-          const double inv = 1.0 / (3.0 * acc.w);
-#pragma unroll
-          for (int k = 0; k < D; k++) d.v[k] = acc.num.v[k] * inv;
+            for (int k = 0; k < D; k++) {
+              X1.v[k] = sw ? B.v[k] : A.v[k];
+              X2.v[k] = sw ? A.v[k] : B.v[k];
+            }
+            f(X1, X2);
+            A = B;
+          }
+        } else {
+          walk_star<D>(p, v, c0, cell, j, err, f);
         }
-        if (ok && !(pinned && !TARGET)) {
-          if (!TARGET) {
+      };
+
+      for_each_cell([&](const Vec<D>& P1, const Vec<D>& P2) {
+        accumulate_cell<D, METHOD, EXACT>(P0, P1, P2, acc, err);
+      });
+      // method formula -> offset of the target from the vertex.  The reference divides by
+      // the control volume whatever its sign; only 0/0 (every adjacent cell masked) leaves
+      // the vertex where it is.
+      Vec<D> d;
+      bool ok = acc.w != 0.0;
+      if (METHOD == OM_CVT_BLOCK_DIAGONAL) {
+        // (2 cv I + Hess) d = -2 cv (x - c) in the scaled accumulators: (w I - H) d = num / 3
+        Vec<D> rhs;
+        double Hn[D * (D + 1) / 2];
 #pragma unroll
-            for (int k = 0; k < D; k++) d.v[k] *= p.omega;
-            diff2 = vdot<D>(d, d);
-            if (p.limiter) {
-              // limited iff |d| > r/2 with r the smallest incident inradius.  LAZY: every
-              // inradius satisfies r^2 >= 4 A^2 / (3 sum ee), so 3 |d|^2 sum_ee <= A^2 for
-              // the minimising cell proves "not limited" without a sqrt or a division.
-              bool check = EXACT || !(3.0 * diff2 * acc.lb_den * (1.0 + 1e-12) <= acc.lb_num);
-              if (check) {
-                if (!EXACT) {
-                  acc.rmin = INFINITY;
-                  walk_star<D>(p, v, c0, cell, j, err, [&](const Vec<D>& P1, const Vec<D>& P2) {
-                    const CellGeo<D> g = cell_geo<D>(P0, P1, P2);
-                    if (g.vol2 > 0.0) acc.rmin = fmin(acc.rmin, inradius<D>(g));
-                  });
-                }
-                const double len = sqrt(diff2);
-                const double maxs = 0.5 * acc.rmin;
-                if (len > maxs) {
-                  const double s = maxs / len;
+        for (int k = 0; k < D; k++) rhs.v[k] = acc.num.v[k] * (1.0 / 3.0);
 #pragma unroll
-                  for (int k = 0; k < D; k++) d.v[k] *= s;
-                  limited = 1;
-                }
+        for (int k = 0; k < D * (D + 1) / 2; k++) Hn[k] = -acc.H[k];
+        ok = ok && solve_sym<D>(Hn, acc.w, rhs, d);
+      } else if (ok) {
+        const double inv = 1.0 / (3.0 * acc.w);
+#pragma unroll
+        for (int k = 0; k < D; k++) d.v[k] = acc.num.v[k] * inv;
+      }
+      if (ok && !(pinned && !TARGET)) {
+        if (!TARGET) {
+#pragma unroll
+          for (int k = 0; k < D; k++) d.v[k] *= p.omega;
+          diff2 = vdot<D>(d, d);
+          if (p.limiter) {
+            // limited iff |d| > r/2 with r the smallest incident inradius.  LAZY: every
+            // inradius satisfies r^2 >= 4 A^2 / (3 sum ee), so 3 |d|^2 sum_ee <= A^2 for
+            // the minimising cell proves "not limited" without a sqrt or a division.
+            const bool check =
+                EXACT || !(3.0 * diff2 * acc.lb_den * (1.0 + 1e-12) <= acc.lb_num);
+            if (check && !EXACT) {
+              // rare (a few % of the vertices) and expensive: running it here would keep
+              // whole warps busy for one lane.  The vertex goes to the list-driven exact
+              // launch instead, where all lanes have work.
+              deferred = true;
+              diff2 = 0.0;
+            } else if (check) {
+              const double len = sqrt(diff2);
+              const double maxs = 0.5 * acc.rmin;
+              if (len > maxs) {
+                const double s = maxs / len;
+#pragma unroll
+                for (int k = 0; k < D; k++) d.v[k] *= s;
+                limited = 1;
               }
             }
           }
-#pragma unroll
-          for (int k = 0; k < D; k++) out.v[k] = P0.v[k] + d.v[k];
         }
+#pragma unroll
+        for (int k = 0; k < D; k++) out.v[k] = P0.v[k] + d.v[k];
       }
     }
-    st_point<D>(p.xout, v, out);
+    if (!deferred) st_point<D>(p.xout, v, out);
   }
   if (!TARGET) reduce_step_stats(diff2, limited, p.ds);
+  if (!TARGET && SRC != 2) {
+    const int vals[1] = {vdef};
+    const bool preds[1] = {deferred};
+    block_append<1>(&p.ds->n_over, p.over, vals, preds);
+  }
   if (err) atomicOr(&p.ds->err, err);
 }
 
-template <int D, int MODE>
+template <int D, int MODE, int SRC>
 int launch_step(om_handle* h, const StepParams& p) {
-  const int B = 256;
-  const int G = om_grid(p.hi - p.lo, B);
+  const int B = step_block<D>();
+  const int G = om_grid(SRC == 2 ? p.n_list : p.hi - p.lo, B);
   if (G == 0) return OM_OK;
   switch (h->method) {
     case OM_LLOYD:
-      OM_LAUNCH(h, (k_step<D, OM_LLOYD, MODE>), G, B, p);
+      OM_LAUNCH(h, (k_step<D, OM_LLOYD, MODE, SRC>), G, B, p);
       break;
     case OM_CVT_BLOCK_DIAGONAL:
-      OM_LAUNCH(h, (k_step<D, OM_CVT_BLOCK_DIAGONAL, MODE>), G, B, p);
+      OM_LAUNCH(h, (k_step<D, OM_CVT_BLOCK_DIAGONAL, MODE, SRC>), G, B, p);
       break;
     case OM_CPT_FIXED_POINT:
-      OM_LAUNCH(h, (k_step<D, OM_CPT_FIXED_POINT, MODE>), G, B, p);
+      OM_LAUNCH(h, (k_step<D, OM_CPT_FIXED_POINT, MODE, SRC>), G, B, p);
       break;
     case OM_ODT_FIXED_POINT:
-      OM_LAUNCH(h, (k_step<D, OM_ODT_FIXED_POINT, MODE>), G, B, p);
+      OM_LAUNCH(h, (k_step<D, OM_ODT_FIXED_POINT, MODE, SRC>), G, B, p);
       break;
     default:
       om_set_error("method %d has no fixed-point kernel", h->method);
@@ -332,11 +532,18 @@ int launch_step(om_handle* h, const StepParams& p) {
   return OM_OK;
 }
 
+// src: 0 ring rows over [lo,hi), 1 walk over [lo,hi), 2 walk over the overflow list
 template <int D>
-int launch_step_mode(om_handle* h, const StepParams& p, int mode) {
-  if (mode == 0) return launch_step<D, 0>(h, p);
-  if (mode == 1) return launch_step<D, 1>(h, p);
-  return launch_step<D, 2>(h, p);
+int launch_step_mode(om_handle* h, const StepParams& p, int mode, int src) {
+  if (mode == 2) return launch_step<D, 2, 1>(h, p);
+  if (mode == 0) {
+    if (src == 0) return launch_step<D, 0, 0>(h, p);
+    if (src == 1) return launch_step<D, 0, 1>(h, p);
+    return launch_step<D, 0, 2>(h, p);
+  }
+  if (src == 0) return launch_step<D, 1, 0>(h, p);
+  if (src == 1) return launch_step<D, 1, 1>(h, p);
+  return launch_step<D, 0, 2>(h, p);  // the deferred list is always done exactly
 }
 
 // x <- x + omega (target - x), limited: the driver-loop tail for methods whose target
@@ -429,6 +636,7 @@ __global__ void k_sphere_sweep(double* x, int N, double cx, double cy, double cz
 }
 
 __global__ void k_reset_step_scalars(DevScalars* ds) {
+  ds->n_over = 0;
   ds->max_diff2_bits = 0ull;
   ds->n_limited = 0ull;
   ds->max_f_bits = 0ull;
@@ -443,6 +651,10 @@ StepParams make_params(om_handle* h, double* out) {
   p.adj = (const int*)h->adj;
   p.v2c = h->v2c;
   p.bflag = h->bflag;
+  p.ring = h->ring;
+  p.list = nullptr;
+  p.n_list = 0;
+  p.over = h->over;
   p.N = (int)h->N;
   p.lo = 0;
   p.hi = (int)h->N;
@@ -494,12 +706,26 @@ int om_update_points_impl(om_handle* h, double tol, om_step_stats* out, bool tar
     }
     // the lazy limiter pays off once few vertices are limited (the previous step tells)
     const int mode = target_only ? 2 : ((h->limiter && h->limited_frac > 0.25) ? 0 : 1);
+    const int src = (mode != 2 && h->ring && h->use_rings) ? 0 : 1;
     if (h->timing) cudaEventRecord(h->ev[0], h->stream);
     if (h->D == 2)
-      OM_TRY(launch_step_mode<2>(h, p, mode));
+      OM_TRY(launch_step_mode<2>(h, p, mode, src));
     else
-      OM_TRY(launch_step_mode<3>(h, p, mode));
+      OM_TRY(launch_step_mode<3>(h, p, mode, src));
     if (h->timing) cudaEventRecord(h->ev[1], h->stream);
+    if (mode != 2) {
+      // vertices the main launch deferred (no ring row, or the lazy limiter bound failed):
+      // second, list-driven launch with the exact limiter
+      OM_TRY(om_fetch_scalars(h));
+      if (h->hs->n_over > 0) {
+        p.list = h->over;
+        p.n_list = h->hs->n_over;
+        if (h->D == 2)
+          OM_TRY(launch_step_mode<2>(h, p, mode, 2));
+        else
+          OM_TRY(launch_step_mode<3>(h, p, mode, 2));
+      }
+    }
   }
   OM_TRY(om_fetch_scalars(h));
   if (h->timing && h->method != OM_CPT_LINEAR_SOLVE) {
@@ -555,5 +781,22 @@ int om_project_impl(om_handle* h, int32_t* sweeps) {
     n++;
   }
   if (sweeps) *sweeps = n;
+  return OM_OK;
+}
+
+// (Re)builds ring rows: all vertices, or the vertices touched by flips since the last call.
+int om_rebuild_rings(om_handle* h, bool all) {
+  if (!h->ring || h->N == 0) return OM_OK;
+  const int B = 256;
+  if (all) {
+    OM_LAUNCH(h, (k_build_rings<false>), om_grid(h->N, B), B, h->cells, (const int*)h->adj, h->v2c,
+              h->bflag, (int)h->N, (const int*)nullptr, h->ring);
+  } else {
+    const int n = h->hs->n_dirty;  // fetched by the flip pass
+    if (n > 0)
+      OM_LAUNCH(h, (k_build_rings<true>), om_grid(n, B), B, h->cells, (const int*)h->adj, h->v2c,
+                h->bflag, n, h->dirty, h->ring);
+  }
+  CUDA_TRY(cudaGetLastError());
   return OM_OK;
 }
