@@ -26,7 +26,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC,-O3",
     "--expt-relaxed-constexpr",
     "-diag-suppress", "177,550",
-]
+] + os.environ.get("OM_NVCC_EXTRA", "").split()
 
 
 def _nvcc() -> str:

@@ -125,8 +125,10 @@ struct om_handle {
 
 #define OM_LAUNCH(h, kernel, grid, block, ...)                         \
   do {                                                                 \
-    kernel<<<(grid), (block), 0, (h)->stream>>>(__VA_ARGS__);          \
-    (h)->launches++;                                                   \
+    if ((grid) > 0) {                                                  \
+      kernel<<<(grid), (block), 0, (h)->stream>>>(__VA_ARGS__);        \
+      (h)->launches++;                                                 \
+    }                                                                  \
   } while (0)
 
 static inline int om_grid(int64_t n, int block) { return (int)((n + block - 1) / block); }

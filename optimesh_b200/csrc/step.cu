@@ -21,7 +21,17 @@
 #include "common.cuh"
 #include "geom.cuh"
 
+// tuning knobs of the ring-row step kernel
+#ifndef OM_K1_UNROLL
+#define OM_K1_UNROLL 2
+#endif
+#ifndef OM_K1_MINB
+#define OM_K1_MINB 4
+#endif
+
 namespace {
+
+constexpr int K1_UNROLL = OM_K1_UNROLL;
 
 // Per-vertex accumulators, kept in SCALED units so that constant factors are applied once
 // per vertex instead of once per cell visit (q = 1/(4A), t_k = ed_k q = -ce_k,
@@ -328,7 +338,7 @@ __global__ void __launch_bounds__(256)
 // SRC 1: vertices [lo, hi), star walk
 // SRC 2: vertices p.list[0 .. n_list), star walk
 template <int D, int METHOD, int MODE, int SRC>
-__global__ void __launch_bounds__(step_block<D>(), (SRC == 0 ? (D == 2 ? 4 : 3) : (D == 2 ? 4 : 3)))
+__global__ void __launch_bounds__(step_block<D>(), (D == 2 ? OM_K1_MINB : 3))
     k_step(StepParams p) {
   constexpr bool TARGET = MODE == 2;
   constexpr bool EXACT = MODE == 0;
@@ -421,7 +431,7 @@ __global__ void __launch_bounds__(step_block<D>(), (SRC == 0 ? (D == 2 ? 4 : 3) 
             return r;
           };
           Vec<D> A = ld_ring(0);
-#pragma unroll 2
+#pragma unroll K1_UNROLL
           for (int q = 0; q < nring; q++) {
             const Vec<D> B = ld_ring(q + 1 < nring ? q + 1 : 0);
             // select the operands (no divergent branch around the cell arithmetic)

@@ -391,10 +391,11 @@ def test_full_size_properties(ob, G):
         assert np.array_equal(p[bnd], pts[bnd])  # boundary pinned
         ah, qh, s = dm.stats()
         assert ah.sum() == 3 * len(cells) and qh.sum() == len(cells)
-        a = p[dm.cells()]
-        area = 0.5 * np.abs(np.cross(a[:, 1] - a[:, 0], a[:, 2] - a[:, 0])).sum()
-        a0 = pts[cells]
-        area0 = 0.5 * np.abs(np.cross(a0[:, 1] - a0[:, 0], a0[:, 2] - a0[:, 0])).sum()
+        def total_area(q, cc):
+            u, w = q[cc[:, 1]] - q[cc[:, 0]], q[cc[:, 2]] - q[cc[:, 0]]
+            return 0.5 * np.abs(u[:, 0] * w[:, 1] - u[:, 1] * w[:, 0]).sum()
+
+        area, area0 = total_area(p, dm.cells()), total_area(pts, cells)
         assert abs(area - area0) < 1e-9 * area0
 
 
@@ -496,3 +497,84 @@ def test_config4_full_size_sphere_odt(ob, G):
         assert np.array_equal(np.unique(c), np.arange(len(p)))
         assert dm.stats()[2]["q_avg"] > q0  # smoothing improves the average quality
         assert dm.flip_until_delaunay() == (0, 0)
+
+
+# ------------------------------------------------------------------ more edge cases
+def test_empty_and_tiny_inputs(ob):
+    p, c = ob.optimize_points_cells(np.zeros((0, 2)), np.zeros((0, 3), dtype=np.int64), "lloyd",
+                                    1e-3, 3)
+    assert p.shape == (0, 2) and c.shape == (0, 3)
+    # points but no cells: nothing moves
+    pts = np.array([[0.0, 0.0], [1.0, 0.0], [0.0, 1.0]])
+    p, c = ob.optimize_points_cells(pts, np.zeros((0, 3), dtype=np.int64), "cpt-fixed-point",
+                                    1e-3, 3)
+    assert np.array_equal(p, pts) and c.shape == (0, 3)
+    # two cells, everything on the boundary
+    pts = np.array([[0.0, 0.0], [1.0, 0.0], [1.0, 1.0], [0.0, 1.0]])
+    cells = np.array([[0, 1, 2], [0, 2, 3]])
+    for m in METHODS + ["cpt-linear-solve"]:
+        p, c = ob.optimize_points_cells(pts, cells, m, 1e-3, 3)
+        assert np.array_equal(p, pts)
+        assert np.array_equal(canonical_cells(c), canonical_cells(cells))
+
+
+def test_high_valence_vertices_use_the_walk_path(ob):
+    """A fan of 12 cells around one vertex: no ring row fits (OM_RING_W = 8), so the
+    list-driven walk kernel must produce the oracle's numbers."""
+    k = 12
+    t = np.arange(k) * 2 * np.pi / k
+    rs = np.random.RandomState(0)
+    ring = np.stack([np.cos(t), np.sin(t)], axis=1) * (1 + 0.2 * rs.rand(k))[:, None]
+    outer = 2.5 * np.stack([np.cos(t + 0.1), np.sin(t + 0.1)], axis=1)
+    pts = np.concatenate([[[0.05, -0.02]], ring, outer])
+    cells = [[0, 1 + i, 1 + (i + 1) % k] for i in range(k)]
+    cells += [[1 + i, 1 + k + i, 1 + (i + 1) % k] for i in range(k)]
+    cells += [[1 + (i + 1) % k, 1 + k + i, 1 + k + (i + 1) % k] for i in range(k)]
+    cells = np.array(cells)
+    for m in METHODS:
+        om = OMesh(pts, cells)
+        oracle.driver.step(om, m)
+        with ob.DeviceMesh(pts, cells) as dm:
+            dm.set_method(m)
+            st = dm.update_points(0.0)
+            got = dm.points
+        assert rel_err(got, om.points) <= STEP_TOL, m
+
+
+def test_random_meshes_property(ob, G):
+    """Property check over random valid meshes (seeded): one full step incl. flips equals
+    the oracle, for every method, boundary-heavy and tiny meshes included."""
+    rs = np.random.RandomState(123)
+    for trial in range(12):
+        nb = int(rs.randint(8, 60))
+        pts, cells = G.disk(nb, int(rs.randint(0, 1000)))
+        method = METHODS[trial % len(METHODS)]
+        omega = float(rs.choice([1.0, 1.5, 2.0]))
+        om = OMesh(pts, cells)
+        om.flip_until_delaunay()
+        oracle.driver.step(om, method, omega=omega)
+        of = om.flip_until_delaunay()
+        with ob.DeviceMesh(pts, cells) as dm:
+            dm.set_method(method, omega)
+            dm.flip_until_delaunay()
+            st = dm.step(0.0)
+            p, c = dm.points, dm.cells()
+        assert (st["n_flips"], st["n_flip_rounds"]) == of, (trial, method)
+        assert np.array_equal(c, om.cells("points")), (trial, method)
+        assert rel_err(p, om.points) <= STEP_TOL, (trial, method)
+
+
+def test_cli_end_to_end(ob, G, tmp_path):
+    from optimesh_b200 import cli, io
+
+    pts, cells = G.disk(40, 6)
+    src, dst = str(tmp_path / "in.vtk"), str(tmp_path / "out.vtk")
+    io.write(src, pts, cells)
+    assert cli.main([src, dst, "-m", "lloyd", "--omega", "2.0", "-n", "5", "-t", "0", "-q"]) == 0
+    p, c = io.read(dst)
+    rp, rc = oracle.optimize_points_cells(pts, cells, "lloyd", 0.0, 5, omega=2.0)
+    assert np.array_equal(c, rc) and rel_err(p, rp) <= 1e-8
+    # verbose path prints the two histograms; step dumps are written
+    fmt = str(tmp_path / "s{:02d}.npz")
+    assert cli.main([src, dst, "-m", "cpt-fixed-point", "-n", "2", "-t", "0", "-f", fmt]) == 0
+    assert os.path.exists(fmt.format(1)) and os.path.exists(fmt.format(2))
