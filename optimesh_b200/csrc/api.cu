@@ -351,9 +351,12 @@ int om_step(om_handle* h, double tol, om_step_stats* out) {
   OM_ENTER(h);
   om_step_stats st;
   memset(&st, 0, sizeof(st));
-  OM_TRY(om_update_points_impl(h, tol, &st, false, nullptr));
+  // the statistics of the point update ride on the first readback of the flip pass
+  const bool defer = h->surf_kind == 0 && h->C > 0 && h->method != OM_CPT_LINEAR_SOLVE;
+  OM_TRY(om_update_points_impl(h, tol, &st, false, nullptr, defer));
   OM_TRY(om_project_impl(h, &st.surface_sweeps));
   OM_TRY(om_flip_impl(h, 0.0, 100, &st.n_flips, &st.n_flip_rounds, &st.flip_cap_hit));
+  if (defer) om_step_stats_from_scalars(h, tol, &st);
   if (out) *out = st;
   return OM_OK;
 }

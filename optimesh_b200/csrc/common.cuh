@@ -51,6 +51,8 @@ struct DevScalars {
   int n_rec;       // flagged-edge records written by the sharded check
   int n_dirty;     // vertices whose ring row must be rebuilt after the flip pass
   int n_over;      // vertices without a ring row met by the step kernel
+  int n_rounds;    // rounds of the current flip pass that flipped at least one edge
+  int flips_prev;  // n_flips at the last round boundary
   int pad3;
   int err;         // OM_DEV_* bits
   int pad;
@@ -118,6 +120,7 @@ struct om_handle {
   double limited_frac = 1.0;  // share of vertices limited in the previous step
   // optional event timing (om_set_timing)
   bool timing = false;
+  bool ev_pending = false;  // ev[0..1] recorded, elapsed time not read yet
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   double t_step_ms = 0.0, t_flip_ms = 0.0;
   int64_t n_step = 0, n_flip = 0;
@@ -147,7 +150,8 @@ int om_flip_check_range_impl(om_handle* h, double tol, int64_t clo, int64_t chi,
 int om_flip_add_records_impl(om_handle* h, const void* recs, int64_t n);
 // step.cu
 int om_update_points_impl(om_handle* h, double tol, om_step_stats* out, bool target_only,
-                          double* target_out);
+                          double* target_out, bool defer_fetch = false);
+void om_step_stats_from_scalars(om_handle* h, double tol, om_step_stats* out);
 int om_project_impl(om_handle* h, int32_t* sweeps);
 int om_rebuild_rings(om_handle* h, bool all);
 // pcg.cu

@@ -71,8 +71,9 @@ __global__ void __launch_bounds__(256)
               const int* __restrict__ adj, int off, int n, const int* __restrict__ list,
               double tol, double* __restrict__ sarr, int* __restrict__ cand,
               int* __restrict__ cand_epoch, int epoch, FlipRec* __restrict__ recs,
-              DevScalars* ds) {
+              DevScalars* ds, const int* __restrict__ n_dev) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_dev) n = *n_dev;  // length known only on the device (chained rounds)
   bool flag = false;
   int c = -1, cn = -1, he = -1, tt = -1;
   double sval = 0.0;
@@ -191,8 +192,10 @@ __global__ void __launch_bounds__(256)
 // candidates: most negative flagged edge (ties: lowest local index); clears the s slots
 __global__ void __launch_bounds__(256)
     k_select(double* __restrict__ sarr, const int* __restrict__ cand, int n,
-             int8_t* __restrict__ best) {
+             int8_t* __restrict__ best, DevScalars* ds, const int* __restrict__ n_dev) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_dev) n = *n_dev;
+  if (i == 0) ds->n_work = 0;  // the work list was consumed by the check of this round
   if (i >= n) return;
   const int c = cand[i];
   double2* p = reinterpret_cast<double2*>(sarr + 4 * (size_t)c);
@@ -216,8 +219,9 @@ __global__ void __launch_bounds__(256)
             const int* __restrict__ cand, int n, int epoch, int* __restrict__ flip_epoch,
             int* __restrict__ reloc, int4* __restrict__ adj_tmp, int* __restrict__ v2c,
             int* __restrict__ dirty, int* __restrict__ dirty_epoch, int dirty_pass,
-            DevScalars* ds) {
+            DevScalars* ds, const int* __restrict__ n_dev) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_dev) n = *n_dev;
   int nf = 0;
   int dv[4] = {0, 0, 0, 0};  // the four vertices of the flip this thread applied
   if (i < n) {
@@ -282,8 +286,10 @@ __global__ void __launch_bounds__(256)
     k_flip2(int* __restrict__ adj, const int4* __restrict__ adj_tmp,
             const int* __restrict__ flip_epoch, const int* __restrict__ reloc,
             const int* __restrict__ cand, int n, int epoch, int* __restrict__ work_epoch,
-            int* __restrict__ work, int8_t* __restrict__ best, DevScalars* ds) {
+            int* __restrict__ work, int8_t* __restrict__ best, DevScalars* ds,
+            const int* __restrict__ n_dev) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_dev) n = *n_dev;
   // cells to enlist for the next round: self (flipped or lost), the two outer neighbours
   // and the flip partner
   int add[4] = {-1, -1, -1, -1};
@@ -318,61 +324,87 @@ __global__ void __launch_bounds__(256)
   block_append<4>(&ds->n_work, work, add, preds);
 }
 
-__global__ void k_reset_flip_scalars(DevScalars* ds, int keep_work) {
+// new_pass: also clears the per-pass counters (flips are counted over the whole pass)
+__global__ void k_reset_flip_scalars(DevScalars* ds, int new_pass) {
   ds->n_flagged = 0;
-  ds->n_flips = 0;
   ds->n_cand = 0;
   ds->n_rec = 0;
-  if (!keep_work) ds->n_work = 0;
+  if (new_pass) {
+    ds->n_flips = 0;
+    ds->n_work = 0;
+    ds->n_rounds = 0;
+    ds->flips_prev = 0;
+  } else if (ds->n_flips > ds->flips_prev) {
+    // the round that just ended flipped something (the reference counts only those)
+    ds->n_rounds++;
+    ds->flips_prev = ds->n_flips;
+  }
 }
 
+// Host loop of one flip pass.  Round 0 reads the candidate count back before flipping (its
+// grid cannot be bounded cheaply).  Every later round is launched as ONE chain -- check of the
+// work list, select, flip, twin patch -- whose kernels read their list lengths on the device
+// (grids are bounded by 4x / 8x the previous candidate count); a single readback per round
+// then tells whether anything was still flagged.
 template <int D>
 int flip_rounds(om_handle* h, double tol, int max_rounds, int64_t* n_flips, int32_t* n_rounds,
                 int32_t* cap_hit, bool first_round_given) {
   const int C = (int)h->C;
   const int B = 256;
-  int64_t total = 0;
-  int rounds = 0;
-  int cap = 0;
-  int n_work = 0;
-  for (int r = 0;; r++) {
-    if (r == 0 && first_round_given) {
-      // candidates and s slots were filled by om_flip_add_records (sharded check)
-    } else {
-      OM_LAUNCH(h, k_reset_flip_scalars, 1, 1, h->ds, 0);
-      h->epoch++;
-      if (r == 0)
-        OM_LAUNCH(h, (k_suspect<D, 0>), om_grid(C, B), B, h->x, h->cells, (const int*)h->adj, 0,
-                  C, (const int*)nullptr, tol, h->sarr, h->cand, h->cand_epoch, h->epoch,
-                  (FlipRec*)nullptr, h->ds);
-      else if (n_work > 0)
-        OM_LAUNCH(h, (k_suspect<D, 1>), om_grid(n_work, B), B, h->x, h->cells,
-                  (const int*)h->adj, 0, n_work, h->work, tol, h->sarr, h->cand, h->cand_epoch,
-                  h->epoch, (FlipRec*)nullptr, h->ds);
-    }
-    OM_TRY(om_fetch_scalars(h));
-    OM_TRY(om_check_dev_err(h));
-    const int n_cand = h->hs->n_cand;
-    if (n_cand == 0) break;
-    if (r >= max_rounds) {
-      cap = 1;
-      break;
-    }
-    OM_LAUNCH(h, k_select, om_grid(n_cand, B), B, h->sarr, h->cand, n_cand, h->best);
-    OM_LAUNCH(h, k_flip1, om_grid(n_cand, B), B, h->cells, h->adj, h->best, h->cand, n_cand,
+  int rounds = 0, cap = 0;
+  auto launch_flips = [&](int n_host, const int* n_dev, int bound) {
+    OM_LAUNCH(h, k_select, om_grid(bound, B), B, h->sarr, h->cand, n_host, h->best, h->ds, n_dev);
+    OM_LAUNCH(h, k_flip1, om_grid(bound, B), B, h->cells, h->adj, h->best, h->cand, n_host,
               h->epoch, h->flip_epoch, h->reloc, h->adj_tmp, h->v2c, h->dirty, h->dirty_epoch,
-              h->dirty_pass, h->ds);
-    OM_LAUNCH(h, k_flip2, om_grid(n_cand, B), B, (int*)h->adj, h->adj_tmp, h->flip_epoch, h->reloc,
-              h->cand, n_cand, h->epoch, h->work_epoch, h->work, h->best, h->ds);
-    OM_TRY(om_fetch_scalars(h));
-    OM_TRY(om_check_dev_err(h));
-    total += h->hs->n_flips;
-    n_work = h->hs->n_work;
-    rounds++;
+              h->dirty_pass, h->ds, n_dev);
+    OM_LAUNCH(h, k_flip2, om_grid(bound, B), B, (int*)h->adj, h->adj_tmp, h->flip_epoch, h->reloc,
+              h->cand, n_host, h->epoch, h->work_epoch, h->work, h->best, h->ds, n_dev);
     h->nbr_valid = false;
-    if (h->hs->n_flips == 0) break;  // flagged edges but no mutual pair (exact ties)
+  };
+  // ---- round 0: full check (or the records of the sharded check), then its flips
+  if (!first_round_given) {
+    OM_LAUNCH(h, k_reset_flip_scalars, 1, 1, h->ds, 1);
+    h->epoch++;
+    OM_LAUNCH(h, (k_suspect<D, 0>), om_grid(C, B), B, h->x, h->cells, (const int*)h->adj, 0, C,
+              (const int*)nullptr, tol, h->sarr, h->cand, h->cand_epoch, h->epoch,
+              (FlipRec*)nullptr, h->ds, (const int*)nullptr);
   }
-  if (n_flips) *n_flips = total;
+  OM_TRY(om_fetch_scalars(h));
+  OM_TRY(om_check_dev_err(h));
+  int prev_cand = h->hs->n_cand;
+  int flips_seen = 0;
+  if (prev_cand > 0) {
+    if (max_rounds <= 0) {
+      cap = 1;
+    } else {
+      launch_flips(prev_cand, nullptr, prev_cand);
+      // ---- rounds 1, 2, ...: check + flips chained, one readback each
+      for (int r = 1;; r++) {
+        const long long wb = std::min<long long>(4ll * prev_cand, C);   // bound on the work list
+        const long long cb = std::min<long long>(2ll * wb, C);          // bound on candidates
+        OM_LAUNCH(h, k_reset_flip_scalars, 1, 1, h->ds, 0);
+        h->epoch++;
+        OM_LAUNCH(h, (k_suspect<D, 1>), om_grid(wb, B), B, h->x, h->cells, (const int*)h->adj, 0,
+                  0, h->work, tol, h->sarr, h->cand, h->cand_epoch, h->epoch, (FlipRec*)nullptr,
+                  h->ds, (const int*)&h->ds->n_work);
+        const bool may_flip = r < max_rounds;
+        if (may_flip) launch_flips(0, &h->ds->n_cand, (int)cb);
+        OM_TRY(om_fetch_scalars(h));
+        OM_TRY(om_check_dev_err(h));
+        rounds = h->hs->n_rounds;  // rounds that flipped at least one edge
+        const int n_cand = h->hs->n_cand;
+        if (n_cand == 0) break;  // nothing flagged any more (the chained flips were no-ops)
+        if (!may_flip) {
+          cap = 1;
+          break;
+        }
+        if (h->hs->n_flips == flips_seen) break;  // flagged but no mutual pair (exact ties)
+        flips_seen = h->hs->n_flips;
+        prev_cand = n_cand;
+      }
+    }
+  }
+  if (n_flips) *n_flips = h->hs->n_flips;
   if (n_rounds) *n_rounds = rounds;
   if (cap_hit) *cap_hit = cap;
   return OM_OK;
@@ -387,18 +419,18 @@ int om_flip_check_range_impl(om_handle* h, double tol, int64_t clo, int64_t chi,
   if (!h->recs) CUDA_TRY(cudaMalloc(&h->recs, sizeof(FlipRec) * std::max<int64_t>(h->C, 1)));
   h->dirty_pass++;  // a new flip pass starts here
   CUDA_TRY(cudaMemsetAsync(&h->ds->n_dirty, 0, sizeof(int), h->stream));
-  OM_LAUNCH(h, k_reset_flip_scalars, 1, 1, h->ds, 0);
+  OM_LAUNCH(h, k_reset_flip_scalars, 1, 1, h->ds, 1);
   h->epoch++;
   const int n = (int)(chi - clo);
   if (n > 0) {
     if (h->D == 2)
       OM_LAUNCH(h, (k_suspect<2, 2>), om_grid(n, B), B, h->x, h->cells, (const int*)h->adj,
                 (int)clo, n, (const int*)nullptr, tol, h->sarr, h->cand, h->cand_epoch, h->epoch,
-                h->recs, h->ds);
+                h->recs, h->ds, (const int*)nullptr);
     else
       OM_LAUNCH(h, (k_suspect<3, 2>), om_grid(n, B), B, h->x, h->cells, (const int*)h->adj,
                 (int)clo, n, (const int*)nullptr, tol, h->sarr, h->cand, h->cand_epoch, h->epoch,
-                h->recs, h->ds);
+                h->recs, h->ds, (const int*)nullptr);
   }
   OM_TRY(om_fetch_scalars(h));
   OM_TRY(om_check_dev_err(h));

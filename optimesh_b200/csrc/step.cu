@@ -179,9 +179,7 @@ struct StepParams {
   const int* v2c;
   const uint8_t* bflag;
   const int* ring;  // N x OM_RING_W ring rows, or nullptr
-  const int* list;  // SRC 2: vertices to process
-  int n_list;
-  int* over;        // SRC 0: vertices left to the walk kernel
+  int* over;        // vertices the main launch leaves to the list-driven (SRC 2) launch
   int N;
   int lo, hi;  // vertices [lo, hi) are processed
   double omega;
@@ -342,15 +340,21 @@ __global__ void __launch_bounds__(step_block<D>(), (D == 2 ? OM_K1_MINB : 3))
     k_step(StepParams p) {
   constexpr bool TARGET = MODE == 2;
   constexpr bool EXACT = MODE == 0;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool active = SRC == 2 ? (i < p.n_list) : (p.lo + i < p.hi);
+  // SRC 2: the list and its length live on the device (written by the SRC 0/1 launch that
+  // precedes this one on the stream): block-stride loop, uniform trip count per block
+  const int n_list = SRC == 2 ? p.ds->n_over : 0;
+  for (int base = blockIdx.x * blockDim.x; SRC != 2 ? base == (int)(blockIdx.x * blockDim.x)
+                                                      : base < n_list;
+       base += gridDim.x * blockDim.x) {
+  const int i = base + threadIdx.x;
+  const bool active = SRC == 2 ? (i < n_list) : (p.lo + i < p.hi);
   double diff2 = 0.0;
   int limited = 0;
   int err = 0;
   bool deferred = false;  // left to the list-driven exact launch
   int vdef = 0;
   if (active) {
-    const int v = SRC == 2 ? p.list[i] : p.lo + i;
+    const int v = SRC == 2 ? p.over[i] : p.lo + i;
     vdef = v;
     const Vec<D> P0 = ld_point<D>(p.x, v);
     Vec<D> out = P0;
@@ -514,12 +518,13 @@ __global__ void __launch_bounds__(step_block<D>(), (D == 2 ? OM_K1_MINB : 3))
     block_append<1>(&p.ds->n_over, p.over, vals, preds);
   }
   if (err) atomicOr(&p.ds->err, err);
+  }  // block-stride loop (one trip unless SRC == 2)
 }
 
 template <int D, int MODE, int SRC>
 int launch_step(om_handle* h, const StepParams& p) {
   const int B = step_block<D>();
-  const int G = om_grid(SRC == 2 ? p.n_list : p.hi - p.lo, B);
+  const int G = SRC == 2 ? 148 * 4 : om_grid(p.hi - p.lo, B);
   if (G == 0) return OM_OK;
   switch (h->method) {
     case OM_LLOYD:
@@ -662,8 +667,6 @@ StepParams make_params(om_handle* h, double* out) {
   p.v2c = h->v2c;
   p.bflag = h->bflag;
   p.ring = h->ring;
-  p.list = nullptr;
-  p.n_list = 0;
   p.over = h->over;
   p.N = (int)h->N;
   p.lo = 0;
@@ -682,8 +685,28 @@ double bits_to_double(unsigned long long b) {
 
 }  // namespace
 
+// Fills the step statistics from the scalars of the last readback.
+void om_step_stats_from_scalars(om_handle* h, double tol, om_step_stats* out) {
+  if (h->timing && h->method != OM_CPT_LINEAR_SOLVE && h->ev_pending) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]) == cudaSuccess) {
+      h->t_step_ms += ms;
+      h->n_step++;
+    }
+    h->ev_pending = false;
+  }
+  const int64_t nown = h->own_hi >= 0 ? std::max<int64_t>(h->own_hi - h->own_lo, 1)
+                                      : std::max<int64_t>(h->N, 1);
+  h->limited_frac = (double)h->hs->n_limited / (double)nown;
+  if (out) {
+    out->max_diff2 = bits_to_double(h->hs->max_diff2_bits);
+    out->n_limited = (int64_t)h->hs->n_limited;
+    out->is_final = out->max_diff2 < tol * tol ? 1 : 0;
+  }
+}
+
 int om_update_points_impl(om_handle* h, double tol, om_step_stats* out, bool target_only,
-                          double* target_out) {
+                          double* target_out, bool defer_fetch) {
   if (h->N == 0) return OM_OK;
   OM_LAUNCH(h, k_reset_step_scalars, 1, 1, h->ds);
   int32_t iters = 0;
@@ -722,29 +745,33 @@ int om_update_points_impl(om_handle* h, double tol, om_step_stats* out, bool tar
       OM_TRY(launch_step_mode<2>(h, p, mode, src));
     else
       OM_TRY(launch_step_mode<3>(h, p, mode, src));
-    if (h->timing) cudaEventRecord(h->ev[1], h->stream);
+    if (h->timing) {
+      cudaEventRecord(h->ev[1], h->stream);
+      h->ev_pending = true;
+    }
     if (mode != 2) {
       // vertices the main launch deferred (no ring row, or the lazy limiter bound failed):
-      // second, list-driven launch with the exact limiter
-      OM_TRY(om_fetch_scalars(h));
-      if (h->hs->n_over > 0) {
-        p.list = h->over;
-        p.n_list = h->hs->n_over;
-        if (h->D == 2)
-          OM_TRY(launch_step_mode<2>(h, p, mode, 2));
-        else
-          OM_TRY(launch_step_mode<3>(h, p, mode, 2));
-      }
+      // second, list-driven launch with the exact limiter; it reads the list length on the
+      // device, so no readback is needed in between
+      if (h->D == 2)
+        OM_TRY(launch_step_mode<2>(h, p, mode, 2));
+      else
+        OM_TRY(launch_step_mode<3>(h, p, mode, 2));
     }
+  }
+  if (defer_fetch && !target_only && h->method != OM_CPT_LINEAR_SOLVE) {
+    // om_step reads the statistics back together with the first flip-round readback
+    if (h->own_hi >= 0) {
+      const size_t off = (size_t)h->own_lo * h->PD, cnt = (size_t)(h->own_hi - h->own_lo) * h->PD;
+      if (cnt)
+        CUDA_TRY(cudaMemcpyAsync(h->x + off, h->xnew + off, sizeof(double) * cnt,
+                                 cudaMemcpyDeviceToDevice, h->stream));
+    } else {
+      std::swap(h->x, h->xnew);
+    }
+    return OM_OK;
   }
   OM_TRY(om_fetch_scalars(h));
-  if (h->timing && h->method != OM_CPT_LINEAR_SOLVE) {
-    float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]) == cudaSuccess) {
-      h->t_step_ms += ms;
-      h->n_step++;
-    }
-  }
   OM_TRY(om_check_dev_err(h));
   if (!target_only) {
     if (h->own_hi >= 0 && h->method != OM_CPT_LINEAR_SOLVE) {
@@ -753,19 +780,12 @@ int om_update_points_impl(om_handle* h, double tol, om_step_stats* out, bool tar
       if (cnt)
         CUDA_TRY(cudaMemcpyAsync(h->x + off, h->xnew + off, sizeof(double) * cnt,
                                  cudaMemcpyDeviceToDevice, h->stream));
-      h->limited_frac =
-          (double)h->hs->n_limited / (double)std::max<int64_t>(h->own_hi - h->own_lo, 1);
     } else {
       std::swap(h->x, h->xnew);
-      h->limited_frac = (double)h->hs->n_limited / (double)h->N;
     }
   }
-  if (out) {
-    out->max_diff2 = bits_to_double(h->hs->max_diff2_bits);
-    out->n_limited = (int64_t)h->hs->n_limited;
-    out->is_final = out->max_diff2 < tol * tol ? 1 : 0;
-    out->solver_iters = iters;
-  }
+  if (!target_only) om_step_stats_from_scalars(h, tol, out);
+  if (out) out->solver_iters = iters;
   return OM_OK;
 }
 
