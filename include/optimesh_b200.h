@@ -179,6 +179,10 @@ int om_set_timing(om_handle* h, int on);
 int om_get_timing(om_handle* h, double* step_kernel_ms, int64_t* step_kernel_launches,
                   double* flip_pass_ms, int64_t* flip_passes);
 
+/* Device memory of destroyed handles stays in the device's stream-ordered pool so that the
+ * next om_create is cheap; this returns it to the driver. */
+int om_release_cached_memory(int device);
+
 /* kernels launched by this handle so far (bench.py's gpu_launches) */
 int om_launch_count(om_handle* h, int64_t* n);
 int om_synchronize(om_handle* h);

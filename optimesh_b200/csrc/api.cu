@@ -3,7 +3,9 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -57,6 +59,127 @@ struct DeviceGuard {
     if (prev >= 0 && cur != prev) cudaSetDevice(prev);
   }
 };
+
+// ---- host <-> device transfers through pinned staging chunks.
+// Pageable user memory is the slow side of the reference-facing API (640 MB of points and
+// int64 cells at 10M vertices): a plain cudaMemcpy is bounded by one thread touching fresh
+// pages.  Here PCIe moves pinned chunks while a few host threads copy the previous chunk
+// to/from the user's array, converting int64 <-> int32 cell indices on the fly so that only
+// 4 bytes per index cross the bus.
+constexpr size_t STAGE_BYTES = 16u << 20;
+constexpr int STAGE_THREADS = 6;
+
+struct Stage {
+  void* pin[2] = {nullptr, nullptr};
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  bool ok = false;
+  Stage() {
+    ok = cudaMallocHost(&pin[0], STAGE_BYTES) == cudaSuccess &&
+         cudaMallocHost(&pin[1], STAGE_BYTES) == cudaSuccess &&
+         cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming) == cudaSuccess;
+  }
+  ~Stage() {
+    for (int i = 0; i < 2; i++) {
+      if (pin[i]) cudaFreeHost(pin[i]);
+      if (ev[i]) cudaEventDestroy(ev[i]);
+    }
+  }
+};
+
+template <typename F>
+void parallel_chunks(size_t n, F f) {  // f(begin, end) on STAGE_THREADS host threads
+  const int T = n < (1u << 16) ? 1 : STAGE_THREADS;
+  if (T == 1) {
+    f((size_t)0, n);
+    return;
+  }
+  std::vector<std::thread> th;
+  const size_t per = (n + T - 1) / T;
+  for (int t = 0; t < T; t++) {
+    const size_t b = std::min(n, t * per), e = std::min(n, b + per);
+    if (b < e) th.emplace_back([=] { f(b, e); });
+  }
+  for (auto& x : th) x.join();
+}
+
+// device (elements of DEV_T) -> user memory (elements of HOST_T)
+// the handle keeps its staging buffers (pinned allocation costs about a millisecond each)
+Stage& stage_of(om_handle* h) {
+  if (!h->stage) h->stage = new Stage();
+  return *(Stage*)h->stage;
+}
+
+template <typename DEV_T, typename HOST_T>
+int staged_d2h(om_handle* h, const DEV_T* src_dev, HOST_T* dst_host, size_t n) {
+  Stage& st = stage_of(h);
+  if (!st.ok) {
+    om_set_error("pinned staging allocation failed");
+    return OM_ERR_CUDA;
+  }
+  const size_t per = STAGE_BYTES / sizeof(DEV_T);
+  const size_t nchunks = (n + per - 1) / per;
+  auto issue = [&](size_t k) {
+    const size_t b = k * per, cnt = std::min(per, n - b);
+    cudaMemcpyAsync(st.pin[k & 1], src_dev + b, cnt * sizeof(DEV_T), cudaMemcpyDeviceToHost,
+                    h->stream);
+    cudaEventRecord(st.ev[k & 1], h->stream);
+  };
+  if (nchunks) issue(0);
+  for (size_t k = 0; k < nchunks; k++) {
+    CUDA_TRY(cudaEventSynchronize(st.ev[k & 1]));
+    if (k + 1 < nchunks) issue(k + 1);  // PCIe fills the other buffer while we copy this one
+    const size_t b = k * per, cnt = std::min(per, n - b);
+    const DEV_T* pin = (const DEV_T*)st.pin[k & 1];
+    HOST_T* out = dst_host + b;
+    parallel_chunks(cnt, [=](size_t lo, size_t hi) {
+      if (sizeof(DEV_T) == sizeof(HOST_T))
+        memcpy((void*)(out + lo), (const void*)(pin + lo), (hi - lo) * sizeof(DEV_T));
+      else
+        for (size_t i = lo; i < hi; i++) out[i] = (HOST_T)pin[i];
+    });
+  }
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return OM_OK;
+}
+
+// user memory (HOST_T) -> device (DEV_T); *bad is set if a narrowed index does not fit
+template <typename HOST_T, typename DEV_T>
+int staged_h2d(om_handle* h, const HOST_T* src_host, DEV_T* dst_dev, size_t n, bool* bad) {
+  Stage& st = stage_of(h);
+  cudaStream_t stream = h->stream;
+  if (!st.ok) {
+    om_set_error("pinned staging allocation failed");
+    return OM_ERR_CUDA;
+  }
+  const size_t per = STAGE_BYTES / sizeof(DEV_T);
+  const size_t nchunks = (n + per - 1) / per;
+  std::atomic<bool> overflow(false);
+  for (size_t k = 0; k < nchunks; k++) {
+    const size_t b = k * per, cnt = std::min(per, n - b);
+    if (k >= 2) CUDA_TRY(cudaEventSynchronize(st.ev[k & 1]));  // buffer free again?
+    DEV_T* pin = (DEV_T*)st.pin[k & 1];
+    const HOST_T* in = src_host + b;
+    parallel_chunks(cnt, [&, pin, in](size_t lo, size_t hi) {
+      if (sizeof(DEV_T) == sizeof(HOST_T)) {
+        memcpy((void*)(pin + lo), (const void*)(in + lo), (hi - lo) * sizeof(DEV_T));
+      } else {
+        bool o = false;
+        for (size_t i = lo; i < hi; i++) {
+          const HOST_T v = in[i];
+          o |= (v < 0) || ((long long)v > 0x7fffffffll);
+          pin[i] = (DEV_T)v;
+        }
+        if (o) overflow = true;
+      }
+    });
+    cudaMemcpyAsync(dst_dev + b, pin, cnt * sizeof(DEV_T), cudaMemcpyHostToDevice, stream);
+    cudaEventRecord(st.ev[k & 1], stream);
+  }
+  CUDA_TRY(cudaStreamSynchronize(stream));
+  if (bad) *bad = overflow.load();
+  return OM_OK;
+}
 
 #define OM_ENTER(h)                              \
   if (!(h)) {                                    \
@@ -175,6 +298,14 @@ int create_common(om_handle** out, int device, void* stream, int64_t N, int dim,
     return OM_ERR_ARG;
   }
   DeviceGuard guard(device);
+  {
+    // keep released blocks in the device's stream-ordered pool (see om_malloc)
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      uint64_t keep = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   om_handle* h = new om_handle();
   h->device = device;
   h->N = N;
@@ -202,22 +333,38 @@ int create_common(om_handle** out, int device, void* stream, int64_t N, int dim,
   double* pup = nullptr;
   void* cup = nullptr;
   if (!inputs_on_device) {
-    const size_t pb = sizeof(double) * (size_t)N * dim, cb = (size_t)itemsize * 3 * (size_t)C;
-    if (cudaMalloc(&pup, std::max<size_t>(pb, 8)) != cudaSuccess ||
-        cudaMalloc(&cup, std::max<size_t>(cb, 8)) != cudaSuccess) {
+    // cells always reach the device as int32 (narrowed by the host threads if needed)
+    const size_t pb = sizeof(double) * (size_t)N * dim, cb = sizeof(int) * 3 * (size_t)C;
+    if (om_malloc(h, &pup, std::max<size_t>(pb, 8)) != cudaSuccess ||
+        om_malloc(h, &cup, std::max<size_t>(cb, 8)) != cudaSuccess) {
       om_set_error("device allocation failed");
-      cudaFree(pup);
+      om_free(h, pup);
       return fail(OM_ERR_CUDA);
     }
-    cudaMemcpyAsync(pup, points, pb, cudaMemcpyHostToDevice, h->stream);
-    cudaMemcpyAsync(cup, cells, cb, cudaMemcpyHostToDevice, h->stream);
+    bool bad = false;
+    rc = staged_h2d<double, double>(h, points, pup, (size_t)N * dim, nullptr);
+    if (rc == OM_OK)
+      rc = itemsize == 4
+               ? staged_h2d<int, int>(h, (const int*)cells, (int*)cup, (size_t)3 * C, nullptr)
+               : staged_h2d<long long, int>(h, (const long long*)cells, (int*)cup,
+                                            (size_t)3 * C, &bad);
+    if (rc == OM_OK && bad) {
+      om_set_error("cells refer to vertices outside [0, N)");
+      rc = OM_ERR_INDEX;
+    }
+    if (rc != OM_OK) {
+      om_free(h, pup);
+      om_free(h, cup);
+      return fail(rc);
+    }
+    h->cells_itemsize = 4;
     pdev = pup;
     cdev = cup;
   }
   rc = om_setup_mesh(h, pdev, cdev, flags);
   cudaStreamSynchronize(h->stream);
-  cudaFree(pup);
-  cudaFree(cup);
+  om_free(h, pup);
+  om_free(h, cup);
   if (rc != OM_OK) return fail(rc);
   *out = h;
   return OM_OK;
@@ -253,37 +400,38 @@ int om_destroy(om_handle* h) {
   if (!h) return OM_OK;
   DeviceGuard guard(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  cudaFree(h->x);
-  cudaFree(h->xnew);
-  cudaFree(h->cells);
-  cudaFree(h->adj);
-  cudaFree(h->adj_tmp);
-  cudaFree(h->v2c);
-  cudaFree(h->bflag);
-  cudaFree(h->ring);
-  cudaFree(h->dirty);
-  cudaFree(h->dirty_epoch);
-  cudaFree(h->over);
-  cudaFree(h->perm);
-  cudaFree(h->inv_perm);
-  cudaFree(h->cand);
-  cudaFree(h->work);
-  cudaFree(h->work_epoch);
-  cudaFree(h->cand_epoch);
-  cudaFree(h->sarr);
-  cudaFree(h->recs);
-  cudaFree(h->best);
-  cudaFree(h->flip_epoch);
-  cudaFree(h->reloc);
-  cudaFree(h->nbr_ptr);
-  cudaFree(h->nbr_idx);
-  cudaFree(h->nbr_w);
-  cudaFree(h->pcg_buf);
-  cudaFree(h->ds);
-  cudaFree(h->partials);
+  om_free(h, h->x);
+  om_free(h, h->xnew);
+  om_free(h, h->cells);
+  om_free(h, h->adj);
+  om_free(h, h->adj_tmp);
+  om_free(h, h->v2c);
+  om_free(h, h->bflag);
+  om_free(h, h->ring);
+  om_free(h, h->dirty);
+  om_free(h, h->dirty_epoch);
+  om_free(h, h->over);
+  om_free(h, h->perm);
+  om_free(h, h->inv_perm);
+  om_free(h, h->cand);
+  om_free(h, h->work);
+  om_free(h, h->work_epoch);
+  om_free(h, h->cand_epoch);
+  om_free(h, h->sarr);
+  om_free(h, h->recs);
+  om_free(h, h->best);
+  om_free(h, h->flip_epoch);
+  om_free(h, h->reloc);
+  om_free(h, h->nbr_ptr);
+  om_free(h, h->nbr_idx);
+  om_free(h, h->nbr_w);
+  om_free(h, h->pcg_buf);
+  om_free(h, h->ds);
+  om_free(h, h->partials);
   if (h->hs) cudaFreeHost(h->hs);
   for (int i = 0; i < 4; i++)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  delete (Stage*)h->stage;
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return OM_OK;
@@ -384,8 +532,8 @@ int om_new_points(om_handle* h, double* out_host) {
   OM_ENTER(h);
   if (h->N == 0) return OM_OK;
   double *target = nullptr, *flat = nullptr;
-  CUDA_TRY(cudaMalloc(&target, sizeof(double) * h->N * h->PD));
-  CUDA_TRY(cudaMalloc(&flat, sizeof(double) * h->N * h->D));
+  CUDA_TRY(om_malloc(h, &target, sizeof(double) * h->N * h->PD));
+  CUDA_TRY(om_malloc(h, &flat, sizeof(double) * h->N * h->D));
   int rc = om_update_points_impl(h, 0.0, nullptr, true, target);
   if (rc == OM_OK) {
     const int B = 256, G = om_grid(h->N, B);
@@ -400,8 +548,8 @@ int om_new_points(om_handle* h, double* out_host) {
       rc = OM_ERR_CUDA;
     }
   }
-  cudaFree(target);
-  cudaFree(flat);
+  om_free(h, target);
+  om_free(h, flat);
   return rc;
 }
 
@@ -422,32 +570,36 @@ int om_get_points(om_handle* h, double* out_host) {
   OM_ENTER(h);
   if (h->N == 0) return OM_OK;
   double* flat = nullptr;
-  CUDA_TRY(cudaMalloc(&flat, sizeof(double) * h->N * h->D));
+  CUDA_TRY(om_malloc(h, &flat, sizeof(double) * h->N * h->D));
   const int B = 256, G = om_grid(h->N, B);
   if (h->D == 2)
     OM_LAUNCH(h, k_export_points<2>, G, B, h->x, h->perm, (int)h->N, flat);
   else
     OM_LAUNCH(h, k_export_points<3>, G, B, h->x, h->perm, (int)h->N, flat);
-  cudaMemcpyAsync(out_host, flat, sizeof(double) * h->N * h->D, cudaMemcpyDeviceToHost, h->stream);
-  cudaError_t e = cudaStreamSynchronize(h->stream);
-  cudaFree(flat);
-  CUDA_TRY(e);
-  return OM_OK;
+  int rc = staged_d2h<double, double>(h, flat, out_host, (size_t)h->N * h->D);
+  om_free(h, flat);
+  return rc;
 }
 
 int om_set_points(om_handle* h, const double* in_host) {
   OM_ENTER(h);
   if (h->N == 0) return OM_OK;
   double* flat = nullptr;
-  CUDA_TRY(cudaMalloc(&flat, sizeof(double) * h->N * h->D));
-  cudaMemcpyAsync(flat, in_host, sizeof(double) * h->N * h->D, cudaMemcpyHostToDevice, h->stream);
+  CUDA_TRY(om_malloc(h, &flat, sizeof(double) * h->N * h->D));
+  {
+    int rc = staged_h2d<double, double>(h, in_host, flat, (size_t)h->N * h->D, nullptr);
+    if (rc != OM_OK) {
+      om_free(h, flat);
+      return rc;
+    }
+  }
   const int B = 256, G = om_grid(h->N, B);
   if (h->D == 2)
     OM_LAUNCH(h, k_import_points<2>, G, B, flat, h->perm, (int)h->N, h->x);
   else
     OM_LAUNCH(h, k_import_points<3>, G, B, flat, h->perm, (int)h->N, h->x);
   cudaError_t e = cudaStreamSynchronize(h->stream);
-  cudaFree(flat);
+  om_free(h, flat);
   CUDA_TRY(e);
   return OM_OK;
 }
@@ -459,30 +611,27 @@ int om_get_cells(om_handle* h, void* out_host, int itemsize) {
     return OM_ERR_ARG;
   }
   if (h->C == 0) return OM_OK;
-  void* flat = nullptr;
-  const size_t bytes = (size_t)itemsize * 3 * h->C;
-  CUDA_TRY(cudaMalloc(&flat, bytes));
+  int* flat = nullptr;
+  const size_t n = (size_t)3 * h->C;
+  CUDA_TRY(om_malloc(h, &flat, sizeof(int) * n));
   const int B = 256, G = om_grid(h->C, B);
-  if (itemsize == 4)
-    OM_LAUNCH(h, k_export_cells<int>, G, B, h->cells, h->perm, (int)h->C, (int*)flat);
-  else
-    OM_LAUNCH(h, k_export_cells<long long>, G, B, h->cells, h->perm, (int)h->C, (long long*)flat);
-  cudaMemcpyAsync(out_host, flat, bytes, cudaMemcpyDeviceToHost, h->stream);
-  cudaError_t e = cudaStreamSynchronize(h->stream);
-  cudaFree(flat);
-  CUDA_TRY(e);
-  return OM_OK;
+  OM_LAUNCH(h, k_export_cells<int>, G, B, h->cells, h->perm, (int)h->C, flat);
+  // 4 bytes per index cross the bus; 64-bit output is widened by the host threads
+  int rc = itemsize == 4 ? staged_d2h<int, int>(h, flat, (int*)out_host, n)
+                         : staged_d2h<int, long long>(h, flat, (long long*)out_host, n);
+  om_free(h, flat);
+  return rc;
 }
 
 int om_get_boundary_flags(om_handle* h, uint8_t* out_host) {
   OM_ENTER(h);
   if (h->N == 0) return OM_OK;
   uint8_t* flat = nullptr;
-  CUDA_TRY(cudaMalloc(&flat, h->N));
+  CUDA_TRY(om_malloc(h, &flat, h->N));
   OM_LAUNCH(h, k_export_flags, om_grid(h->N, 256), 256, h->bflag, h->perm, (int)h->N, flat);
   cudaMemcpyAsync(out_host, flat, h->N, cudaMemcpyDeviceToHost, h->stream);
   cudaError_t e = cudaStreamSynchronize(h->stream);
-  cudaFree(flat);
+  om_free(h, flat);
   CUDA_TRY(e);
   return OM_OK;
 }
@@ -523,11 +672,11 @@ int om_pin_vertices(om_handle* h, const int32_t* idx_host, int64_t n) {
   OM_ENTER(h);
   if (n == 0) return OM_OK;
   int* d = nullptr;
-  CUDA_TRY(cudaMalloc(&d, sizeof(int) * n));
+  CUDA_TRY(om_malloc(h, &d, sizeof(int) * n));
   cudaMemcpyAsync(d, idx_host, sizeof(int) * n, cudaMemcpyHostToDevice, h->stream);
   OM_LAUNCH(h, k_pin, om_grid(n, 256), 256, h->bflag, h->inv_perm, d, n);
   cudaError_t e = cudaStreamSynchronize(h->stream);
-  cudaFree(d);
+  om_free(h, d);
   CUDA_TRY(e);
   h->nbr_valid = false;
   OM_TRY(om_rebuild_rings(h, true));  // pinned vertices have no ring row
@@ -595,6 +744,14 @@ int om_get_timing(om_handle* h, double* step_kernel_ms, int64_t* step_kernel_lau
   if (step_kernel_launches) *step_kernel_launches = h->n_step;
   if (flip_pass_ms) *flip_pass_ms = h->t_flip_ms;
   if (flip_passes) *flip_passes = h->n_flip;
+  return OM_OK;
+}
+
+int om_release_cached_memory(int device) {
+  cudaMemPool_t pool;
+  CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemPoolTrimTo(pool, 0));
   return OM_OK;
 }
 

@@ -119,6 +119,7 @@ struct om_handle {
   int64_t own_lo = 0, own_hi = -1;  // hi < 0: whole mesh
   double limited_frac = 1.0;  // share of vertices limited in the previous step
   // optional event timing (om_set_timing)
+  void* stage = nullptr;  // pinned staging buffers of the host transfers (api.cu)
   bool timing = false;
   bool ev_pending = false;  // ev[0..1] recorded, elapsed time not read yet
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -135,6 +136,18 @@ struct om_handle {
   } while (0)
 
 static inline int om_grid(int64_t n, int block) { return (int)((n + block - 1) / block); }
+
+// Device memory comes from the device's stream-ordered pool (kept across handles: the
+// release threshold is raised at the first om_create): allocation and release are ordered on
+// the handle's stream, cost microseconds once the pool is warm and never synchronise the
+// device the way cudaMalloc/cudaFree do.
+template <typename T>
+static inline cudaError_t om_malloc(om_handle* h, T** p, size_t bytes) {
+  return cudaMallocAsync((void**)p, bytes ? bytes : 1, h->stream);
+}
+static inline cudaError_t om_free(om_handle* h, void* p) {
+  return p ? cudaFreeAsync(p, h->stream) : cudaSuccess;
+}
 
 // fetch DevScalars to host (synchronises the stream)
 int om_fetch_scalars(om_handle* h);

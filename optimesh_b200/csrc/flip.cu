@@ -416,7 +416,7 @@ int flip_rounds(om_handle* h, double tol, int max_rounds, int64_t* n_flips, int3
 int om_flip_check_range_impl(om_handle* h, double tol, int64_t clo, int64_t chi,
                              int64_t* n_records) {
   const int B = 256;
-  if (!h->recs) CUDA_TRY(cudaMalloc(&h->recs, sizeof(FlipRec) * std::max<int64_t>(h->C, 1)));
+  if (!h->recs) CUDA_TRY(om_malloc(h, &h->recs, sizeof(FlipRec) * std::max<int64_t>(h->C, 1)));
   h->dirty_pass++;  // a new flip pass starts here
   CUDA_TRY(cudaMemsetAsync(&h->ds->n_dirty, 0, sizeof(int), h->stream));
   OM_LAUNCH(h, k_reset_flip_scalars, 1, 1, h->ds, 1);

@@ -265,25 +265,25 @@ int build_neighbours(om_handle* h) {
   if (h->nbr_valid) return OM_OK;
   const int N = (int)h->N;
   const int G = om_grid(N, 256);
-  if (!h->nbr_ptr) CUDA_TRY(cudaMalloc(&h->nbr_ptr, sizeof(int) * (N + 1)));
+  if (!h->nbr_ptr) CUDA_TRY(om_malloc(h, &h->nbr_ptr, sizeof(int) * (N + 1)));
   int* cnt = nullptr;
-  CUDA_TRY(cudaMalloc(&cnt, sizeof(int) * N));
+  CUDA_TRY(om_malloc(h, &cnt, sizeof(int) * N));
   OM_LAUNCH(h, (k_ring<false>), G, 256, h->cells, (const int*)h->adj, h->v2c, h->bflag, N, cnt,
             (int*)nullptr, h->ds);
   size_t bytes = 0;
   CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, bytes, cnt, h->nbr_ptr, N, h->stream));
   void* tmp = nullptr;
-  CUDA_TRY(cudaMalloc(&tmp, bytes ? bytes : 1));
+  CUDA_TRY(om_malloc(h, &tmp, bytes ? bytes : 1));
   CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp, bytes, cnt, h->nbr_ptr, N, h->stream));
   OM_LAUNCH(h, k_set_last, 1, 1, h->nbr_ptr, cnt, N);
   int nnz = 0;
   CUDA_TRY(cudaMemcpyAsync(&nnz, h->nbr_ptr + N, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
-  cudaFree(tmp);
-  cudaFree(cnt);
-  if (h->nbr_idx) cudaFree(h->nbr_idx);
+  om_free(h, tmp);
+  om_free(h, cnt);
+  if (h->nbr_idx) om_free(h, h->nbr_idx);
   h->nbr_idx = nullptr;
-  CUDA_TRY(cudaMalloc(&h->nbr_idx, sizeof(int) * std::max(nnz, 1)));
+  CUDA_TRY(om_malloc(h, &h->nbr_idx, sizeof(int) * std::max(nnz, 1)));
   h->nnz = nnz;
   OM_LAUNCH(h, (k_ring<true>), G, 256, h->cells, (const int*)h->adj, h->v2c, h->bflag, N,
             h->nbr_ptr, h->nbr_idx, h->ds);
@@ -298,13 +298,13 @@ int pcg(om_handle* h, double rtol, int max_iter, int32_t* iters, double* relres,
   const int N = (int)h->N;
   const size_t vec = sizeof(double) * (size_t)N * h->PD;
   OM_TRY(build_neighbours(h));
-  if (!h->pcg_buf) CUDA_TRY(cudaMalloc(&h->pcg_buf, 3 * vec + sizeof(double) * 8 * MAXG + 256));
+  if (!h->pcg_buf) CUDA_TRY(om_malloc(h, &h->pcg_buf, 3 * vec + sizeof(double) * 8 * MAXG + 256));
   double* r = h->pcg_buf;
   double* p = r + (size_t)N * h->PD;
   double* q = p + (size_t)N * h->PD;
   double* partials = q + (size_t)N * h->PD;
   PcgScal* sc = nullptr;
-  CUDA_TRY(cudaMalloc(&sc, sizeof(PcgScal)));
+  CUDA_TRY(om_malloc(h, &sc, sizeof(PcgScal)));
   CUDA_TRY(cudaMemsetAsync(sc, 0, sizeof(PcgScal), h->stream));
   // the iterate lives in `out`; fixed vertices keep their coordinates
   if (out != h->x) CUDA_TRY(cudaMemcpyAsync(out, h->x, vec, cudaMemcpyDeviceToDevice, h->stream));
@@ -337,7 +337,7 @@ int pcg(om_handle* h, double rtol, int max_iter, int32_t* iters, double* relres,
     }
     if (!(worst > rtol)) break;
   }
-  cudaFree(sc);
+  om_free(h, sc);
   if (iters) *iters = it;
   if (relres) *relres = worst;
   CUDA_TRY(cudaGetLastError());

@@ -213,11 +213,11 @@ int sort_pairs(om_handle* h, const K* kin, K* kout, const V* vin, V* vout, int64
   CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, n, 0, end_bit,
                                            h->stream));
   void* tmp = nullptr;
-  CUDA_TRY(cudaMalloc(&tmp, bytes ? bytes : 1));
+  CUDA_TRY(om_malloc(h, &tmp, bytes ? bytes : 1));
   cudaError_t e =
       cub::DeviceRadixSort::SortPairs(tmp, bytes, kin, kout, vin, vout, n, 0, end_bit, h->stream);
   cudaError_t e2 = cudaStreamSynchronize(h->stream);
-  cudaFree(tmp);
+  om_free(h, tmp);
   CUDA_TRY(e);
   CUDA_TRY(e2);
   return OM_OK;
@@ -235,7 +235,7 @@ int setup_points(om_handle* h, const double* raw, bool renumber) {
   const int B = 256;
   if (renumber && N > 1) {
     unsigned long long* bbox = nullptr;
-    CUDA_TRY(cudaMalloc(&bbox, 6 * sizeof(unsigned long long)));
+    CUDA_TRY(om_malloc(h, &bbox, 6 * sizeof(unsigned long long)));
     unsigned long long init[6];
     for (int k = 0; k < 3; k++) {
       init[k] = ~0ull;
@@ -246,18 +246,18 @@ int setup_points(om_handle* h, const double* raw, bool renumber) {
     OM_LAUNCH(h, k_bbox<D>, g, B, raw, N, bbox);
     unsigned long long *keys = nullptr, *keys2 = nullptr;
     int *vals = nullptr;
-    CUDA_TRY(cudaMalloc(&keys, N * 8));
-    CUDA_TRY(cudaMalloc(&keys2, N * 8));
-    CUDA_TRY(cudaMalloc(&vals, N * 4));
-    CUDA_TRY(cudaMalloc(&h->perm, N * 4));
-    CUDA_TRY(cudaMalloc(&h->inv_perm, N * 4));
+    CUDA_TRY(om_malloc(h, &keys, N * 8));
+    CUDA_TRY(om_malloc(h, &keys2, N * 8));
+    CUDA_TRY(om_malloc(h, &vals, N * 4));
+    CUDA_TRY(om_malloc(h, &h->perm, N * 4));
+    CUDA_TRY(om_malloc(h, &h->inv_perm, N * 4));
     OM_LAUNCH(h, k_morton<D>, om_grid(N, B), B, raw, N, bbox, keys, vals);
     OM_TRY(sort_pairs(h, keys, keys2, vals, h->perm, N, D == 2 ? 64 : 63));
     OM_LAUNCH(h, k_invert_perm, om_grid(N, B), B, h->perm, N, h->inv_perm);
-    cudaFree(keys);
-    cudaFree(keys2);
-    cudaFree(vals);
-    cudaFree(bbox);
+    om_free(h, keys);
+    om_free(h, keys2);
+    om_free(h, vals);
+    om_free(h, bbox);
   }
   OM_LAUNCH(h, k_gather_points<D>, om_grid(N, B), B, raw, h->perm, N, h->x);
   CUDA_TRY(cudaMemsetAsync(h->xnew, 0, sizeof(double) * (N + OM_POINT_PAD) * h->PD, h->stream));
@@ -271,25 +271,25 @@ int om_setup_mesh(om_handle* h, const double* points_dev, const void* cells_dev,
   const int B = 256;
   const bool renumber = (flags & OM_RENUMBER) != 0;
   // OM_POINT_PAD extra vertices: lets a caller all-gather equal-sized chunks in place
-  CUDA_TRY(cudaMalloc(&h->x, sizeof(double) * (N + OM_POINT_PAD) * h->PD));
-  CUDA_TRY(cudaMalloc(&h->xnew, sizeof(double) * (N + OM_POINT_PAD) * h->PD));
+  CUDA_TRY(om_malloc(h, &h->x, sizeof(double) * (N + OM_POINT_PAD) * h->PD));
+  CUDA_TRY(om_malloc(h, &h->xnew, sizeof(double) * (N + OM_POINT_PAD) * h->PD));
   CUDA_TRY(cudaMemsetAsync(h->x, 0, sizeof(double) * (N + OM_POINT_PAD) * h->PD, h->stream));
-  CUDA_TRY(cudaMalloc(&h->cells, sizeof(int4) * std::max<int64_t>(C, 1)));
-  CUDA_TRY(cudaMalloc(&h->adj, sizeof(int4) * std::max<int64_t>(C, 1)));
-  CUDA_TRY(cudaMalloc(&h->adj_tmp, sizeof(int4) * std::max<int64_t>(C, 1)));
-  CUDA_TRY(cudaMalloc(&h->v2c, sizeof(int) * N));
-  CUDA_TRY(cudaMalloc(&h->bflag, N));
-  CUDA_TRY(cudaMalloc(&h->cand, sizeof(int) * std::max<int64_t>(C, 1)));
-  CUDA_TRY(cudaMalloc(&h->work, sizeof(int) * std::max<int64_t>(C, 1)));
-  CUDA_TRY(cudaMalloc(&h->work_epoch, sizeof(int) * std::max<int64_t>(C, 1)));
-  CUDA_TRY(cudaMalloc(&h->best, std::max<int64_t>(C, 1)));
-  CUDA_TRY(cudaMalloc(&h->cand_epoch, sizeof(int) * std::max<int64_t>(C, 1)));
-  CUDA_TRY(cudaMalloc(&h->sarr, sizeof(double) * 4 * std::max<int64_t>(C, 1)));
-  CUDA_TRY(cudaMalloc(&h->flip_epoch, sizeof(int) * std::max<int64_t>(C, 1)));
-  CUDA_TRY(cudaMalloc(&h->reloc, sizeof(int) * 4 * std::max<int64_t>(C, 1)));
-  CUDA_TRY(cudaMalloc(&h->ds, sizeof(DevScalars)));
+  CUDA_TRY(om_malloc(h, &h->cells, sizeof(int4) * std::max<int64_t>(C, 1)));
+  CUDA_TRY(om_malloc(h, &h->adj, sizeof(int4) * std::max<int64_t>(C, 1)));
+  CUDA_TRY(om_malloc(h, &h->adj_tmp, sizeof(int4) * std::max<int64_t>(C, 1)));
+  CUDA_TRY(om_malloc(h, &h->v2c, sizeof(int) * N));
+  CUDA_TRY(om_malloc(h, &h->bflag, N));
+  CUDA_TRY(om_malloc(h, &h->cand, sizeof(int) * std::max<int64_t>(C, 1)));
+  CUDA_TRY(om_malloc(h, &h->work, sizeof(int) * std::max<int64_t>(C, 1)));
+  CUDA_TRY(om_malloc(h, &h->work_epoch, sizeof(int) * std::max<int64_t>(C, 1)));
+  CUDA_TRY(om_malloc(h, &h->best, std::max<int64_t>(C, 1)));
+  CUDA_TRY(om_malloc(h, &h->cand_epoch, sizeof(int) * std::max<int64_t>(C, 1)));
+  CUDA_TRY(om_malloc(h, &h->sarr, sizeof(double) * 4 * std::max<int64_t>(C, 1)));
+  CUDA_TRY(om_malloc(h, &h->flip_epoch, sizeof(int) * std::max<int64_t>(C, 1)));
+  CUDA_TRY(om_malloc(h, &h->reloc, sizeof(int) * 4 * std::max<int64_t>(C, 1)));
+  CUDA_TRY(om_malloc(h, &h->ds, sizeof(DevScalars)));
   CUDA_TRY(cudaMallocHost(&h->hs, sizeof(DevScalars)));
-  CUDA_TRY(cudaMalloc(&h->partials, sizeof(double) * 8 * 2048));
+  CUDA_TRY(om_malloc(h, &h->partials, sizeof(double) * 8 * 2048));
   CUDA_TRY(cudaMemsetAsync(h->ds, 0, sizeof(DevScalars), h->stream));
   CUDA_TRY(cudaMemsetAsync(h->flip_epoch, 0, sizeof(int) * std::max<int64_t>(C, 1), h->stream));
   CUDA_TRY(cudaMemsetAsync(h->work_epoch, 0, sizeof(int) * std::max<int64_t>(C, 1), h->stream));
@@ -309,13 +309,13 @@ int om_setup_mesh(om_handle* h, const double* points_dev, const void* cells_dev,
   int* tmp3 = nullptr;
   unsigned int *ckeys = nullptr, *ckeys2 = nullptr;
   int *cvals = nullptr, *cperm = nullptr;
-  CUDA_TRY(cudaMalloc(&tmp3, sizeof(int) * 3 * std::max<int64_t>(C, 1)));
+  CUDA_TRY(om_malloc(h, &tmp3, sizeof(int) * 3 * std::max<int64_t>(C, 1)));
   const bool sort_cells = renumber && C > 1;
   if (sort_cells) {
-    CUDA_TRY(cudaMalloc(&ckeys, 4 * C));
-    CUDA_TRY(cudaMalloc(&ckeys2, 4 * C));
-    CUDA_TRY(cudaMalloc(&cvals, 4 * C));
-    CUDA_TRY(cudaMalloc(&cperm, 4 * C));
+    CUDA_TRY(om_malloc(h, &ckeys, 4 * C));
+    CUDA_TRY(om_malloc(h, &ckeys2, 4 * C));
+    CUDA_TRY(om_malloc(h, &cvals, 4 * C));
+    CUDA_TRY(om_malloc(h, &cperm, 4 * C));
   }
   if (C > 0) {
     if (h->cells_itemsize == 4)
@@ -328,11 +328,11 @@ int om_setup_mesh(om_handle* h, const double* points_dev, const void* cells_dev,
     OM_LAUNCH(h, k_build_cells4, om_grid(C, B), B, tmp3, cperm, C, h->cells);
   }
   CUDA_TRY(cudaStreamSynchronize(h->stream));
-  cudaFree(tmp3);
-  cudaFree(ckeys);
-  cudaFree(ckeys2);
-  cudaFree(cvals);
-  cudaFree(cperm);
+  om_free(h, tmp3);
+  om_free(h, ckeys);
+  om_free(h, ckeys2);
+  om_free(h, cvals);
+  om_free(h, cperm);
   OM_TRY(om_fetch_scalars(h));
   OM_TRY(om_check_dev_err(h));
 
@@ -342,27 +342,27 @@ int om_setup_mesh(om_handle* h, const double* points_dev, const void* cells_dev,
     const int bits = bits_for(N);
     unsigned long long *ek = nullptr, *ek2 = nullptr;
     int *ev = nullptr, *ev2 = nullptr;
-    CUDA_TRY(cudaMalloc(&ek, 8 * M));
-    CUDA_TRY(cudaMalloc(&ek2, 8 * M));
-    CUDA_TRY(cudaMalloc(&ev, 4 * M));
-    CUDA_TRY(cudaMalloc(&ev2, 4 * M));
+    CUDA_TRY(om_malloc(h, &ek, 8 * M));
+    CUDA_TRY(om_malloc(h, &ek2, 8 * M));
+    CUDA_TRY(om_malloc(h, &ev, 4 * M));
+    CUDA_TRY(om_malloc(h, &ev2, 4 * M));
     OM_LAUNCH(h, k_edge_keys, om_grid(C, B), B, h->cells, C, bits, ek, ev);
     OM_TRY(sort_pairs(h, ek, ek2, ev, ev2, M, 2 * bits));
     OM_LAUNCH(h, k_pair_twins, om_grid(M, B), B, ek2, ev2, M, bits, (int*)h->adj, h->bflag,
               &h->ds->err);
     CUDA_TRY(cudaStreamSynchronize(h->stream));
-    cudaFree(ek);
-    cudaFree(ek2);
-    cudaFree(ev);
-    cudaFree(ev2);
+    om_free(h, ek);
+    om_free(h, ek2);
+    om_free(h, ev);
+    om_free(h, ev2);
   }
   OM_LAUNCH(h, k_fill_int, om_grid(N, B), B, h->v2c, N, OM_NONE_CELL);
   if (C > 0) OM_LAUNCH(h, k_v2c, om_grid(C, B), B, h->cells, C, h->v2c);
   if (N > 0) {
-    CUDA_TRY(cudaMalloc(&h->ring, sizeof(int) * OM_RING_W * N));
-    CUDA_TRY(cudaMalloc(&h->dirty, sizeof(int) * N));
-    CUDA_TRY(cudaMalloc(&h->dirty_epoch, sizeof(int) * N));
-    CUDA_TRY(cudaMalloc(&h->over, sizeof(int) * N));
+    CUDA_TRY(om_malloc(h, &h->ring, sizeof(int) * OM_RING_W * N));
+    CUDA_TRY(om_malloc(h, &h->dirty, sizeof(int) * N));
+    CUDA_TRY(om_malloc(h, &h->dirty_epoch, sizeof(int) * N));
+    CUDA_TRY(om_malloc(h, &h->over, sizeof(int) * N));
     CUDA_TRY(cudaMemsetAsync(h->dirty_epoch, 0, sizeof(int) * N, h->stream));
     OM_TRY(om_rebuild_rings(h, true));
   }

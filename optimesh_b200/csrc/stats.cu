@@ -106,7 +106,7 @@ int om_stats_impl(om_handle* h, int64_t* angle_hist72, int64_t* q_hist40, double
   const int B = 256;
   int G = std::min(om_grid(std::max<int64_t>(C, 1), B), MAX_BLOCKS);
   unsigned long long* hist = nullptr;
-  CUDA_TRY(cudaMalloc(&hist, sizeof(unsigned long long) * (NB_A + NB_Q)));
+  CUDA_TRY(om_malloc(h, &hist, sizeof(unsigned long long) * (NB_A + NB_Q)));
   CUDA_TRY(cudaMemsetAsync(hist, 0, sizeof(unsigned long long) * (NB_A + NB_Q), h->stream));
   if (h->D == 2)
     OM_LAUNCH(h, k_stats<2>, G, B, h->x, h->cells, C, hist, h->partials, h->ds);
@@ -120,7 +120,7 @@ int om_stats_impl(om_handle* h, int64_t* angle_hist72, int64_t* q_hist40, double
   CUDA_TRY(cudaMemcpyAsync(part.data(), h->partials, sizeof(double) * part.size(),
                            cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
-  cudaFree(hist);
+  om_free(h, hist);
   OM_TRY(om_fetch_scalars(h));
   OM_TRY(om_check_dev_err(h));
   for (int i = 0; i < NB_A; i++) angle_hist72[i] = (int64_t)hh[i];

@@ -717,7 +717,7 @@ int om_update_points_impl(om_handle* h, double tol, om_step_stats* out, bool tar
     if (!target_only) {
       // relax + limit from the solved target; result must not alias the target
       double* tmp = nullptr;
-      CUDA_TRY(cudaMalloc(&tmp, sizeof(double) * h->N * h->PD));
+      CUDA_TRY(om_malloc(h, &tmp, sizeof(double) * h->N * h->PD));
       StepParams p = make_params(h, tmp);
       const int B = 256, G = om_grid(h->N, B);
       if (h->D == 2)
@@ -728,7 +728,7 @@ int om_update_points_impl(om_handle* h, double tol, om_step_stats* out, bool tar
       CUDA_TRY(cudaMemcpyAsync(h->xnew, tmp, sizeof(double) * h->N * h->PD,
                                cudaMemcpyDeviceToDevice, h->stream));
       CUDA_TRY(cudaStreamSynchronize(h->stream));
-      cudaFree(tmp);
+      om_free(h, tmp);
     }
   } else {
     StepParams p = make_params(h, target_only ? target_out : h->xnew);
