@@ -225,49 +225,22 @@ def run_b200(args):
         del tp, tc
         torch.cuda.empty_cache()
     dm.set_method(method, omega)
-    dm.flip_until_delaunay()  # the loop's initial flip pass (setup, untimed)
+    band = None
     if world > 1:
-        from optimesh_b200.dist import chunk_of, device_points_tensor, owned_range, sharded_flip
+        from optimesh_b200.dist import owned_range, partitioned_begin, partitioned_step
 
         lo, hi = owned_range(n, rank, world)
-        chunk = chunk_of(n, world)
-        dm.set_owned_range(lo, hi)
-
-    breakdown = [0.0, 0.0, 0.0, 0.0] if os.environ.get("OM_BENCH_BREAKDOWN") else None
+        band = partitioned_begin(dm)  # own ranges + the loop's initial flip pass (untimed)
+    else:
+        dm.flip_until_delaunay()  # the loop's initial flip pass (setup, untimed)
 
     def one_step():
-        """One loop iteration; at world > 1 the update is sharded, coordinates all-gathered
-        in place over NCCL, statistics all-reduced, flips replicated (dist.run_sharded)."""
+        """One loop iteration; at world > 1 (dist.run_partitioned): own vertex range updated,
+        statistics all-reduced, band of coordinates exchanged over NCCL, every flip-check
+        round split by cell range with its flagged-edge records all-gathered."""
         if world == 1:
             return dm.step(0.0)
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if breakdown is not None \
-            else None
-        if ev:
-            ev[0].record()
-        st = dm.update_points(0.0)
-        if ev:
-            ev[1].record()
-        red = torch.tensor([st["max_diff2"], float(st["n_limited"])], dtype=torch.float64,
-                           device="cuda")
-        dist.all_reduce(red[:1], op=dist.ReduceOp.MAX)
-        dist.all_reduce(red[1:], op=dist.ReduceOp.SUM)
-        if ev:
-            ev[2].record()
-        x = device_points_tensor(dm)
-        out = x[: world * chunk]
-        send = out[rank * chunk:(rank + 1) * chunk].clone()
-        dist.all_gather_into_tensor(out, send)
-        if ev:
-            ev[3].record()
-        nf, nr = sharded_flip(dm)
-        if ev:
-            ev[4].record()
-            torch.cuda.synchronize()
-            for q in range(4):
-                breakdown[q] += ev[q].elapsed_time(ev[q + 1])
-        st["n_flips"], st["n_flip_rounds"] = nf, nr
-        st["max_diff2"], st["n_limited"] = float(red[0].item()), int(red[1].item())
-        return st
+        return partitioned_step(dm, band, 0.0)
 
     def barrier():
         torch.cuda.synchronize()
@@ -296,21 +269,13 @@ def run_b200(args):
     barrier()
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
-    if breakdown is not None:
-        print(f"[rank {rank}] ms per step: update {breakdown[0] / (args.steps + args.warmup):.3f} "
-              f"reduce {breakdown[1] / (args.steps + args.warmup):.3f} "
-              f"gather {breakdown[2] / (args.steps + args.warmup):.3f} "
-              f"flip {breakdown[3] / (args.steps + args.warmup):.3f}", file=sys.stderr)
-        from optimesh_b200 import dist as _d
-
-        if _d.PROFILE:
-            calls = max(_d.PROFILE.get("calls", 1), 1)
-            print(f"[rank {rank}] sharded_flip ms/call: " + " ".join(
-                f"{k}={1e3 * v / calls:.3f}" if k not in ("calls", "records_n") else f"{k}={v}"
-                for k, v in _d.PROFILE.items()), file=sys.stderr)
     launches = dm.launch_count - l0
     tim = dm.timing()
     dm.set_timing(False)
+    if band is not None:
+        line_band = {"band_vertices_all_ranks": int(sum(band.counts or [0])),
+                     "fallback_full_gathers": band.full_gathers,
+                     "slow_flip_rounds": band.slow_rounds}
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -353,9 +318,9 @@ def run_b200(args):
                         f"limiter + flip-until-Delaunay",
             "method": method, "omega": omega, "n_vertices": n, "n_cells": c,
             "parallelism": "1 GPU" if world == 1 else
-            f"{world} GPUs: vertex ranges of one mesh, update sharded, coordinates all-gathered "
-            f"over NCCL each step, first flip round sharded by cell range (records all-gathered), "
-            f"later rounds replicated",
+            f"{world} GPUs: vertex ranges of one mesh (topology replicated), update and every "
+            f"flip-check round sharded, band of coordinates + flagged-edge records exchanged "
+            f"over NCCL each step",
             "l2": "inputs (points+cells+twins = %.0f MB) larger than the 126 MB L2"
                   % ((16 * n + 32 * c) / 1e6),
         },
@@ -366,6 +331,8 @@ def run_b200(args):
         "clocks": clocks,
         "gpu_launches": launches,
     }
+    if band is not None:
+        line["exchange"] = line_band
 
     dm.close()  # its device memory returns to the pool before the end-to-end calls
     if rank == 0 and world == 1 and not args.no_e2e:

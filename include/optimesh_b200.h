@@ -172,6 +172,57 @@ int om_flip_finish(om_handle* h, double tol, int max_rounds, int64_t* n_flips,
                    int32_t* n_rounds, int32_t* cap_hit);
 int om_points_device(om_handle* h, double** points, int64_t* n_alloc, int32_t* stride);
 
+/* Partitioned coordinates (one process per GPU, identical topology on every rank, each rank
+ * only keeps CURRENT coordinates for its own vertex range plus a band around it):
+ *   om_coords_invalidate  foreign coordinates are stale from now on (call after the update)
+ *   om_band_build         internal ids of the own vertices within `depth` edges of a foreign
+ *                         vertex (pinned vertices excluded: they never move); device list
+ *   om_band_pack/unpack   gather own band coordinates into a buffer (stride = point stride) /
+ *                         scatter a received band (internal ids) and mark it current
+ *   om_coords_all_valid   every coordinate is current again (after a full all-gather)
+ * and the flip pass round by round, so that flagged-edge records can be exchanged in every
+ * round (only the check reads coordinates; select/flip/patch are integer work every rank
+ * repeats on the identical topology):
+ *   om_flip_pass_begin
+ *   om_flip_round_check   first != 0: cells [cell_lo, cell_hi); else the work-list cells in that
+ *                         range.  *stale = 1: a coordinate outside own range + band would have
+ *                         been read -- refresh (full all-gather) and call again
+ *   om_flip_add_records   the records of ALL ranks (declared above)
+ *   om_flip_round_apply   select + flip + patch; *n_candidates is the same on every rank,
+ *                         0 ends the pass
+ *   om_flip_pass_end      ring rows of touched vertices; totals of the pass              */
+/* Cells whose smallest vertex lies in the internal vertex range [vertex_lo, vertex_hi): a
+ * contiguous cell range right after om_create (cells are sorted by their smallest vertex);
+ * call it before any flip.  Gives each rank the cells that sit on its own vertices. */
+int om_cell_range_of_vertices(om_handle* h, int64_t vertex_lo, int64_t vertex_hi,
+                              int64_t* cell_lo, int64_t* cell_hi);
+/* With deferred commit om_update_points leaves the updated own range aside and reports in
+ * om_step_stats.reserved whether it met a stale coordinate; the caller either commits (every
+ * rank clean) or refreshes the coordinates and repeats the update. */
+int om_set_deferred_commit(om_handle* h, int on);
+int om_commit_points(om_handle* h);
+int om_coords_invalidate(om_handle* h);
+int om_coords_all_valid(om_handle* h);
+int om_band_build(om_handle* h, int depth, int64_t* n, int32_t** idx_dev);
+int om_band_pack(om_handle* h, const int32_t* idx_dev, int64_t n, double* buf_dev);
+int om_band_unpack(om_handle* h, const int32_t* idx_dev, int64_t n, const double* buf_dev);
+int om_flip_pass_begin(om_handle* h);
+int om_flip_round_check(om_handle* h, double tol, int first, int64_t cell_lo, int64_t cell_hi,
+                        int64_t* n_records, void** records_dev, int32_t* stale);
+int om_flip_round_apply(om_handle* h, int64_t total_records, int64_t* n_candidates,
+                        int64_t* n_flips_total);
+/* Same round without a host readback between check and flips: call om_flip_round_check with
+ * n_records == NULL, then om_flip_round_pack writes this rank's slot of (1 + capacity) 16-byte
+ * records (slot[0] = {count, stale}), the caller all-gathers the slots, and
+ * om_flip_round_apply_gathered applies all of them and flips.  *abort_bits != 0 (1: a rank was
+ * stale, 2: a slot overflowed) means nothing was applied: repeat the round with
+ * om_flip_round_check(n_records != NULL) / om_flip_add_records / om_flip_round_apply. */
+int om_flip_round_pack(om_handle* h, int32_t capacity, void* slot_dev);
+int om_flip_round_apply_gathered(om_handle* h, const void* gathered_dev, int32_t n_ranks,
+                                 int32_t capacity, int64_t* n_candidates, int64_t* n_flips_total,
+                                 int32_t* abort_bits, int64_t* max_records_of_any_rank);
+int om_flip_pass_end(om_handle* h, int64_t* n_flips, int32_t* n_rounds);
+
 /* Per-kernel timing with CUDA events on the handle's stream (bench.py's roofline line):
  * when on, the fused step kernel (K1) and each flip-until-Delaunay pass are bracketed by
  * events; om_get_timing returns the accumulated device times and counts. */

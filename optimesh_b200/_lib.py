@@ -31,7 +31,9 @@ class StepStats(C.Structure):
     ]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        d = {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        d["stale"] = self.reserved  # partitioned runs only (om_set_deferred_commit)
+        return d
 
 
 _H = C.c_void_p
@@ -75,6 +77,23 @@ SIGNATURES = {
     "om_flip_finish": (C.c_int, [_H, C.c_double, C.c_int, _P(C.c_int64), _P(C.c_int32),
                                  _P(C.c_int32)]),
     "om_points_device": (C.c_int, [_H, _P(C.c_void_p), _P(C.c_int64), _P(C.c_int32)]),
+    "om_cell_range_of_vertices": (C.c_int, [_H, C.c_int64, C.c_int64, _P(C.c_int64),
+                                            _P(C.c_int64)]),
+    "om_set_deferred_commit": (C.c_int, [_H, C.c_int]),
+    "om_commit_points": (C.c_int, [_H]),
+    "om_coords_invalidate": (C.c_int, [_H]),
+    "om_coords_all_valid": (C.c_int, [_H]),
+    "om_band_build": (C.c_int, [_H, C.c_int, _P(C.c_int64), _P(C.c_void_p)]),
+    "om_band_pack": (C.c_int, [_H, C.c_void_p, C.c_int64, C.c_void_p]),
+    "om_band_unpack": (C.c_int, [_H, C.c_void_p, C.c_int64, C.c_void_p]),
+    "om_flip_pass_begin": (C.c_int, [_H]),
+    "om_flip_round_check": (C.c_int, [_H, C.c_double, C.c_int, C.c_int64, C.c_int64,
+                                      _P(C.c_int64), _P(C.c_void_p), _P(C.c_int32)]),
+    "om_flip_round_apply": (C.c_int, [_H, C.c_int64, _P(C.c_int64), _P(C.c_int64)]),
+    "om_flip_pass_end": (C.c_int, [_H, _P(C.c_int64), _P(C.c_int32)]),
+    "om_flip_round_pack": (C.c_int, [_H, C.c_int32, C.c_void_p]),
+    "om_flip_round_apply_gathered": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_int32, _P(C.c_int64),
+                                               _P(C.c_int64), _P(C.c_int32), _P(C.c_int64)]),
     "om_set_timing": (C.c_int, [_H, C.c_int]),
     "om_get_timing": (C.c_int, [_H, _P(C.c_double), _P(C.c_int64), _P(C.c_double),
                                 _P(C.c_int64)]),

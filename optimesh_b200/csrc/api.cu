@@ -411,6 +411,9 @@ int om_destroy(om_handle* h) {
   om_free(h, h->dirty);
   om_free(h, h->dirty_epoch);
   om_free(h, h->over);
+  om_free(h, h->valid_epoch);
+  om_free(h, h->band);
+  om_free(h, h->band_mark);
   om_free(h, h->perm);
   om_free(h, h->inv_perm);
   om_free(h, h->cand);
@@ -705,6 +708,130 @@ int om_flip_finish(om_handle* h, double tol, int max_rounds, int64_t* n_flips, i
                    int32_t* cap_hit) {
   OM_ENTER(h);
   return om_flip_impl(h, tol, max_rounds, n_flips, n_rounds, cap_hit, true);
+}
+
+__global__ void k_lower_bound_cells(const int4* __restrict__ cells, int C, int key, int* out) {
+  // first cell whose smallest vertex is >= key (cells are sorted by it after setup)
+  int lo = 0, hi = C;
+  while (lo < hi) {
+    const int mid = lo + (hi - lo) / 2;
+    const int4 c = cells[mid];
+    if (min(c.x, min(c.y, c.z)) < key)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  *out = lo;
+}
+
+int om_cell_range_of_vertices(om_handle* h, int64_t vertex_lo, int64_t vertex_hi, int64_t* cell_lo,
+                              int64_t* cell_hi) {
+  OM_ENTER(h);
+  int* d = nullptr;
+  CUDA_TRY(om_malloc(h, &d, 2 * sizeof(int)));
+  k_lower_bound_cells<<<1, 1, 0, h->stream>>>(h->cells, (int)h->C, (int)vertex_lo, d);
+  k_lower_bound_cells<<<1, 1, 0, h->stream>>>(h->cells, (int)h->C, (int)vertex_hi, d + 1);
+  int r[2] = {0, 0};
+  CUDA_TRY(cudaMemcpyAsync(r, d, sizeof(r), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  om_free(h, d);
+  if (cell_lo) *cell_lo = r[0];
+  if (cell_hi) *cell_hi = r[1];
+  return OM_OK;
+}
+
+int om_flip_pass_begin(om_handle* h) {
+  OM_ENTER(h);
+  return om_flip_pass_begin_impl(h);
+}
+
+int om_flip_round_check(om_handle* h, double tol, int first, int64_t cell_lo, int64_t cell_hi,
+                        int64_t* n_records, void** records_dev, int32_t* stale) {
+  OM_ENTER(h);
+  if (cell_lo < 0 || cell_hi < cell_lo || cell_hi > h->C) {
+    om_set_error("cell range [%lld, %lld) outside [0, %lld]", (long long)cell_lo,
+                 (long long)cell_hi, (long long)h->C);
+    return OM_ERR_ARG;
+  }
+  // n_records == NULL: leave the counts on the device (fixed-capacity exchange follows)
+  OM_TRY(om_flip_round_check_impl(h, tol, first, cell_lo, cell_hi, n_records, stale,
+                                  n_records != nullptr));
+  if (records_dev) *records_dev = (void*)h->recs;
+  return OM_OK;
+}
+
+int om_flip_round_pack(om_handle* h, int32_t capacity, void* slot_dev) {
+  OM_ENTER(h);
+  if (capacity < 1 || !slot_dev) {
+    om_set_error("om_flip_round_pack: bad capacity or buffer");
+    return OM_ERR_ARG;
+  }
+  return om_flip_round_pack_impl(h, capacity, slot_dev);
+}
+
+int om_flip_round_apply_gathered(om_handle* h, const void* gathered_dev, int32_t n_ranks,
+                                 int32_t capacity, int64_t* n_candidates, int64_t* n_flips_total,
+                                 int32_t* abort_bits, int64_t* own_records) {
+  OM_ENTER(h);
+  return om_flip_round_apply_gathered_impl(h, gathered_dev, n_ranks, capacity, n_candidates,
+                                           n_flips_total, abort_bits, own_records);
+}
+
+int om_flip_round_apply(om_handle* h, int64_t total_records, int64_t* n_candidates,
+                        int64_t* n_flips_total) {
+  OM_ENTER(h);
+  return om_flip_round_apply_impl(h, total_records, n_candidates, n_flips_total);
+}
+
+int om_flip_pass_end(om_handle* h, int64_t* n_flips, int32_t* n_rounds) {
+  OM_ENTER(h);
+  return om_flip_pass_end_impl(h, n_flips, n_rounds);
+}
+
+int om_band_build(om_handle* h, int depth, int64_t* n, int32_t** idx_dev) {
+  OM_ENTER(h);
+  if (depth < 1 || depth > 200) {
+    om_set_error("band depth %d out of range", depth);
+    return OM_ERR_ARG;
+  }
+  OM_TRY(om_band_build_impl(h, depth, n));
+  if (idx_dev) *idx_dev = (int32_t*)h->band;
+  return OM_OK;
+}
+
+int om_band_pack(om_handle* h, const int32_t* idx_dev, int64_t n, double* buf_dev) {
+  OM_ENTER(h);
+  return om_band_pack_impl(h, (const int*)idx_dev, n, buf_dev);
+}
+
+int om_band_unpack(om_handle* h, const int32_t* idx_dev, int64_t n, const double* buf_dev) {
+  OM_ENTER(h);
+  return om_band_unpack_impl(h, (const int*)idx_dev, n, buf_dev);
+}
+
+int om_coords_invalidate(om_handle* h) {
+  OM_ENTER(h);
+  OM_TRY(om_band_alloc(h));
+  h->valid_stamp++;
+  h->all_valid = false;
+  return OM_OK;
+}
+
+int om_set_deferred_commit(om_handle* h, int on) {
+  OM_ENTER(h);
+  h->defer_commit = on != 0;
+  return OM_OK;
+}
+
+int om_commit_points(om_handle* h) {
+  OM_ENTER(h);
+  return om_commit_points_impl(h);
+}
+
+int om_coords_all_valid(om_handle* h) {
+  OM_ENTER(h);
+  h->all_valid = true;
+  return OM_OK;
 }
 
 int om_set_owned_range(om_handle* h, int64_t lo, int64_t hi) {

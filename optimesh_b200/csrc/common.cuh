@@ -52,6 +52,10 @@ struct DevScalars {
   int n_dirty;     // vertices whose ring row must be rebuilt after the flip pass
   int n_over;      // vertices without a ring row met by the step kernel
   int n_rounds;    // rounds of the current flip pass that flipped at least one edge
+  int stale;       // sharded check met a coordinate this rank does not hold
+  int abort;       // gathered round rejected: 1 = some rank stale, 2 = some slot overflowed
+  int max_count;   // largest record count among the gathered slots
+  int pad5;
   int flips_prev;  // n_flips at the last round boundary
   int pad3;
   int err;         // OM_DEV_* bits
@@ -117,6 +121,14 @@ struct om_handle {
   int64_t launches = 0;
   // owned vertex range (internal numbering) when the step is sharded across handles
   int64_t own_lo = 0, own_hi = -1;  // hi < 0: whole mesh
+  // partitioned coordinates (dist.py): which foreign vertices hold current coordinates
+  int* valid_epoch = nullptr;  // N: stamp of the last band exchange that refreshed the vertex
+  int valid_stamp = 1;
+  bool all_valid = true;       // right after a full all-gather (or single GPU)
+  bool defer_commit = false;   // om_update_points leaves the own range in xnew (om_commit_points)
+  int* band = nullptr;         // N: own vertices other ranks may need (internal ids)
+  uint8_t* band_mark = nullptr;  // N: hop distance to a foreign vertex (0: far)
+  int64_t pass_work_bound = 0; // upper bound of the work list length in a round-wise pass
   double limited_frac = 1.0;  // share of vertices limited in the previous step
   // optional event timing (om_set_timing)
   void* stage = nullptr;  // pinned staging buffers of the host transfers (api.cu)
@@ -161,11 +173,26 @@ int om_flip_impl(om_handle* h, double tol, int max_rounds, int64_t* n_flips, int
 int om_flip_check_range_impl(om_handle* h, double tol, int64_t clo, int64_t chi,
                              int64_t* n_records);
 int om_flip_add_records_impl(om_handle* h, const void* recs, int64_t n);
+int om_flip_pass_begin_impl(om_handle* h);
+int om_flip_round_check_impl(om_handle* h, double tol, int first, int64_t clo, int64_t chi,
+                             int64_t* n_records, int32_t* stale, bool fetch = true);
+int om_flip_round_pack_impl(om_handle* h, int cap, void* slot_dev);
+int om_flip_round_apply_gathered_impl(om_handle* h, const void* gathered, int P, int cap,
+                                      int64_t* n_cand, int64_t* n_flips_total, int32_t* abort_bits,
+                                      int64_t* own_records);
+int om_flip_round_apply_impl(om_handle* h, int64_t total_records, int64_t* n_cand,
+                             int64_t* n_flips_total);
+int om_flip_pass_end_impl(om_handle* h, int64_t* n_flips, int32_t* n_rounds);
+int om_band_build_impl(om_handle* h, int depth, int64_t* n);
+int om_band_alloc(om_handle* h);
+int om_band_pack_impl(om_handle* h, const int* idx_dev, int64_t n, double* buf_dev);
+int om_band_unpack_impl(om_handle* h, const int* idx_dev, int64_t n, const double* buf_dev);
 // step.cu
 int om_update_points_impl(om_handle* h, double tol, om_step_stats* out, bool target_only,
                           double* target_out, bool defer_fetch = false);
 void om_step_stats_from_scalars(om_handle* h, double tol, om_step_stats* out);
 int om_project_impl(om_handle* h, int32_t* sweeps);
+int om_commit_points_impl(om_handle* h);
 int om_rebuild_rings(om_handle* h, bool all);
 // pcg.cu
 int om_pcg_impl(om_handle* h, double rtol, int max_iter, int32_t* iters, double* relres,

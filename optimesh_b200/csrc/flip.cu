@@ -65,13 +65,30 @@ __device__ __forceinline__ int sel3i(const int (&a)[3], int k) {
 // MODE 0: cells [off, off+n); MODE 1: cells list[0..n); MODE 2: cells [off, off+n), flagged
 // edges are appended to `recs` instead of being applied (sharded check: the records of all
 // ranks are exchanged and applied by k_apply_records).
+// Which coordinates a rank may trust when the coordinates are partitioned (dist.py): its own
+// vertex range, pinned vertices (they never move) and the vertices refreshed by the last
+// band exchange.  valid_epoch == nullptr: everything is valid (single GPU, or right after a
+// full all-gather).
+struct ShardInfo {
+  int vlo, vhi;   // own vertex range
+  int clo, chi;   // cell range this rank examines (MODE 3 filters the work list with it)
+  const int* valid_epoch;
+  int valid_stamp;
+  const uint8_t* bflag;
+  __device__ __forceinline__ bool valid(int v) const {
+    return valid_epoch == nullptr || (v >= vlo && v < vhi) || bflag[v] != 0 ||
+           valid_epoch[v] == valid_stamp;
+  }
+};
+
+// MODE 3: like MODE 2 (records) but over the work list, restricted to cells in [clo, chi).
 template <int D, int MODE>
 __global__ void __launch_bounds__(256)
     k_suspect(const double* __restrict__ x, const int4* __restrict__ cells,
               const int* __restrict__ adj, int off, int n, const int* __restrict__ list,
               double tol, double* __restrict__ sarr, int* __restrict__ cand,
               int* __restrict__ cand_epoch, int epoch, FlipRec* __restrict__ recs,
-              DevScalars* ds, const int* __restrict__ n_dev) {
+              DevScalars* ds, const int* __restrict__ n_dev, ShardInfo sh) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (n_dev) n = *n_dev;  // length known only on the device (chained rounds)
   bool flag = false;
@@ -79,8 +96,13 @@ __global__ void __launch_bounds__(256)
   double sval = 0.0;
   do {  // no early return: the list appends below are warp-collective
     if (i >= n) break;
-    c = MODE == 1 ? list[i] : off + i;
+    c = (MODE == 1 || MODE == 3) ? list[i] : off + i;
+    if (MODE == 3 && (c < sh.clo || c >= sh.chi)) break;  // another rank examines it
     const int4 cl = cells[c];
+    if ((MODE == 2 || MODE == 3) && !(sh.valid(cl.x) && sh.valid(cl.y) && sh.valid(cl.z))) {
+      ds->stale = 1;  // a coordinate this rank does not hold: the caller refreshes and repeats
+      break;
+    }
     // fetched up front (coalesced) so the slow path does not wait for it after the geometry
     const int4 tw = __ldg(reinterpret_cast<const int4*>(adj) + c);
     Vec<D> P[3] = {ld_point<D>(x, cl.x), ld_point<D>(x, cl.y), ld_point<D>(x, cl.z)};
@@ -99,6 +121,10 @@ __global__ void __launch_bounds__(256)
     const int kn = t & 3;
     const int4 cln = __ldg(cells + cn);
     const int nid[3] = {cln.x, cln.y, cln.z};
+    if ((MODE == 2 || MODE == 3) && !sh.valid(sel3i(nid, kn))) {
+      ds->stale = 1;
+      break;
+    }
     // neighbour's vertices in ITS slot order: slot kn is the opposite vertex, the other
     // two are shared with this cell (slots (k+1)%3 and (k+2)%3 here)
     const Vec<D> O = ld_point<D>(x, sel3i(nid, kn));
@@ -129,13 +155,13 @@ __global__ void __launch_bounds__(256)
       tt = t;
       sval = s;
       flag = true;
-      if (MODE != 2) {
+      if (MODE != 2 && MODE != 3) {
         sarr[he] = s;
         sarr[t] = s;
       }
     }
   } while (false);
-  if (MODE == 2) {
+  if (MODE == 2 || MODE == 3) {
     // records: reserve one slot per flagged thread (block-aggregated), then write
     __shared__ int r_warp[8];
     __shared__ int r_base;
@@ -189,11 +215,68 @@ __global__ void __launch_bounds__(256)
   block_append<2>(&ds->n_cand, cand, vals, preds);
 }
 
+// ---- fixed-capacity record exchange (no host readback between check and flips).
+// Every rank publishes one slot of 1 + cap records: slot[0] = {count, stale flag}, then its
+// records.  After the all-gather k_round_scan looks at the P headers: a stale rank or a count
+// above cap sets ds->abort, which turns the rest of the round (apply, select, flips) into
+// no-ops; the host then repeats the round the slow way.
+__global__ void k_round_pack(const FlipRec* __restrict__ recs, const DevScalars* ds, int cap,
+                             FlipRec* __restrict__ slot) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = ds->n_rec;
+  if (i == 0) {
+    FlipRec hd;
+    hd.he = n;
+    hd.twin = ds->stale;
+    hd.s = 0.0;
+    slot[0] = hd;
+  }
+  if (i < n && i < cap) slot[1 + i] = recs[i];
+}
+
+__global__ void k_round_scan(const FlipRec* __restrict__ gathered, int P, int cap,
+                             DevScalars* ds) {
+  int ab = 0, mx = 0;
+  for (int r = 0; r < P; r++) {
+    const FlipRec hd = gathered[(size_t)r * (cap + 1)];
+    if (hd.twin) ab |= 1;
+    if (hd.he > cap) ab |= 2;
+    mx = max(mx, hd.he);
+  }
+  ds->abort = ab;
+  ds->max_count = mx;  // the same on every rank: lets them agree on the next capacity
+}
+
+__global__ void __launch_bounds__(256)
+    k_apply_gathered(const FlipRec* __restrict__ gathered, int P, int cap,
+                     double* __restrict__ sarr, int* __restrict__ cand,
+                     int* __restrict__ cand_epoch, int epoch, DevScalars* ds) {
+  if (ds->abort) return;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  int c = -1, cn = -1;
+  if (i < (long long)P * cap) {
+    const int r = (int)(i / cap), j = (int)(i % cap);
+    const FlipRec* slot = gathered + (size_t)r * (cap + 1);
+    if (j < slot[0].he) {
+      const FlipRec rec = slot[1 + j];
+      sarr[rec.he] = rec.s;
+      sarr[rec.twin] = rec.s;
+      c = rec.he >> 2;
+      cn = rec.twin >> 2;
+    }
+  }
+  const int vals[2] = {c, cn};
+  const bool preds[2] = {c >= 0 && atomicExch(&cand_epoch[c], epoch) != epoch,
+                         cn >= 0 && atomicExch(&cand_epoch[cn], epoch) != epoch};
+  block_append<2>(&ds->n_cand, cand, vals, preds);
+}
+
 // candidates: most negative flagged edge (ties: lowest local index); clears the s slots
 __global__ void __launch_bounds__(256)
     k_select(double* __restrict__ sarr, const int* __restrict__ cand, int n,
              int8_t* __restrict__ best, DevScalars* ds, const int* __restrict__ n_dev) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ds->abort) return;  // gathered round rejected (uniform over the grid)
   if (n_dev) n = *n_dev;
   if (i == 0) ds->n_work = 0;  // the work list was consumed by the check of this round
   if (i >= n) return;
@@ -221,6 +304,7 @@ __global__ void __launch_bounds__(256)
             int* __restrict__ dirty, int* __restrict__ dirty_epoch, int dirty_pass,
             DevScalars* ds, const int* __restrict__ n_dev) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ds->abort) return;
   if (n_dev) n = *n_dev;
   int nf = 0;
   int dv[4] = {0, 0, 0, 0};  // the four vertices of the flip this thread applied
@@ -289,6 +373,7 @@ __global__ void __launch_bounds__(256)
             int* __restrict__ work, int8_t* __restrict__ best, DevScalars* ds,
             const int* __restrict__ n_dev) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ds->abort) return;
   if (n_dev) n = *n_dev;
   // cells to enlist for the next round: self (flipped or lost), the two outer neighbours
   // and the flip partner
@@ -327,6 +412,8 @@ __global__ void __launch_bounds__(256)
 // new_pass: also clears the per-pass counters (flips are counted over the whole pass)
 __global__ void k_reset_flip_scalars(DevScalars* ds, int new_pass) {
   ds->n_flagged = 0;
+  ds->stale = 0;
+  ds->abort = 0;
   ds->n_cand = 0;
   ds->n_rec = 0;
   if (new_pass) {
@@ -367,7 +454,7 @@ int flip_rounds(om_handle* h, double tol, int max_rounds, int64_t* n_flips, int3
     h->epoch++;
     OM_LAUNCH(h, (k_suspect<D, 0>), om_grid(C, B), B, h->x, h->cells, (const int*)h->adj, 0, C,
               (const int*)nullptr, tol, h->sarr, h->cand, h->cand_epoch, h->epoch,
-              (FlipRec*)nullptr, h->ds, (const int*)nullptr);
+              (FlipRec*)nullptr, h->ds, (const int*)nullptr, ShardInfo{0, 0, 0, 0, nullptr, 0, nullptr});
   }
   OM_TRY(om_fetch_scalars(h));
   OM_TRY(om_check_dev_err(h));
@@ -386,7 +473,7 @@ int flip_rounds(om_handle* h, double tol, int max_rounds, int64_t* n_flips, int3
         h->epoch++;
         OM_LAUNCH(h, (k_suspect<D, 1>), om_grid(wb, B), B, h->x, h->cells, (const int*)h->adj, 0,
                   0, h->work, tol, h->sarr, h->cand, h->cand_epoch, h->epoch, (FlipRec*)nullptr,
-                  h->ds, (const int*)&h->ds->n_work);
+                  h->ds, (const int*)&h->ds->n_work, ShardInfo{0, 0, 0, 0, nullptr, 0, nullptr});
         const bool may_flip = r < max_rounds;
         if (may_flip) launch_flips(0, &h->ds->n_cand, (int)cb);
         OM_TRY(om_fetch_scalars(h));
@@ -412,6 +499,131 @@ int flip_rounds(om_handle* h, double tol, int max_rounds, int64_t* n_flips, int3
 
 }  // namespace
 
+static ShardInfo shard_info(om_handle* h, int64_t clo, int64_t chi) {
+  ShardInfo sh;
+  sh.vlo = (int)h->own_lo;
+  sh.vhi = (int)(h->own_hi >= 0 ? h->own_hi : h->N);
+  sh.clo = (int)clo;
+  sh.chi = (int)chi;
+  const bool partitioned = h->own_hi >= 0 && h->valid_epoch && !h->all_valid;
+  sh.valid_epoch = partitioned ? h->valid_epoch : nullptr;
+  sh.valid_stamp = h->valid_stamp;
+  sh.bflag = h->bflag;
+  return sh;
+}
+
+// ---- round-wise pass for partitioned coordinates (om_flip_pass_begin / om_flip_round_check /
+//      om_flip_add_records / om_flip_round_apply / om_flip_pass_end)
+int om_flip_pass_begin_impl(om_handle* h) {
+  if (!h->recs) CUDA_TRY(om_malloc(h, &h->recs, sizeof(FlipRec) * std::max<int64_t>(h->C, 1)));
+  h->dirty_pass++;
+  CUDA_TRY(cudaMemsetAsync(&h->ds->n_dirty, 0, sizeof(int), h->stream));
+  OM_LAUNCH(h, k_reset_flip_scalars, 1, 1, h->ds, 1);
+  h->pass_work_bound = 0;
+  return OM_OK;
+}
+
+int om_flip_round_check_impl(om_handle* h, double tol, int first, int64_t clo, int64_t chi,
+                             int64_t* n_records, int32_t* stale, bool fetch) {
+  const int B = 256;
+  // also right for a repeated call after a coordinate refresh (clears records and `stale`)
+  OM_LAUNCH(h, k_reset_flip_scalars, 1, 1, h->ds, 0);
+  h->epoch++;
+  const ShardInfo sh = shard_info(h, clo, chi);
+  if (first) {
+    const int n = (int)(chi - clo);
+    if (h->D == 2)
+      OM_LAUNCH(h, (k_suspect<2, 2>), om_grid(n, B), B, h->x, h->cells, (const int*)h->adj,
+                (int)clo, n, (const int*)nullptr, tol, h->sarr, h->cand, h->cand_epoch, h->epoch,
+                h->recs, h->ds, (const int*)nullptr, sh);
+    else
+      OM_LAUNCH(h, (k_suspect<3, 2>), om_grid(n, B), B, h->x, h->cells, (const int*)h->adj,
+                (int)clo, n, (const int*)nullptr, tol, h->sarr, h->cand, h->cand_epoch, h->epoch,
+                h->recs, h->ds, (const int*)nullptr, sh);
+  } else if (h->pass_work_bound > 0) {
+    const int nb = (int)std::min<int64_t>(h->pass_work_bound, h->C);
+    if (h->D == 2)
+      OM_LAUNCH(h, (k_suspect<2, 3>), om_grid(nb, B), B, h->x, h->cells, (const int*)h->adj, 0, 0,
+                h->work, tol, h->sarr, h->cand, h->cand_epoch, h->epoch, h->recs, h->ds,
+                (const int*)&h->ds->n_work, sh);
+    else
+      OM_LAUNCH(h, (k_suspect<3, 3>), om_grid(nb, B), B, h->x, h->cells, (const int*)h->adj, 0, 0,
+                h->work, tol, h->sarr, h->cand, h->cand_epoch, h->epoch, h->recs, h->ds,
+                (const int*)&h->ds->n_work, sh);
+  }
+  if (!fetch) return OM_OK;  // the counts stay on the device (om_flip_round_pack)
+  OM_TRY(om_fetch_scalars(h));
+  OM_TRY(om_check_dev_err(h));
+  if (n_records) *n_records = h->hs->n_rec;
+  if (stale) *stale = h->hs->stale;
+  return OM_OK;
+}
+
+int om_flip_round_pack_impl(om_handle* h, int cap, void* slot_dev) {
+  OM_LAUNCH(h, k_round_pack, om_grid(std::max(cap, 1), 256), 256, h->recs, h->ds, cap,
+            (FlipRec*)slot_dev);
+  CUDA_TRY(cudaGetLastError());
+  return OM_OK;
+}
+
+int om_flip_round_apply_gathered_impl(om_handle* h, const void* gathered, int P, int cap,
+                                      int64_t* n_cand, int64_t* n_flips_total, int32_t* abort_bits,
+                                      int64_t* own_records) {
+  const int B = 256;
+  const FlipRec* g = (const FlipRec*)gathered;
+  OM_LAUNCH(h, k_round_scan, 1, 1, g, P, cap, h->ds);
+  OM_LAUNCH(h, k_apply_gathered, om_grid((int64_t)P * cap, B), B, g, P, cap, h->sarr, h->cand,
+            h->cand_epoch, h->epoch, h->ds);
+  const int bound = (int)std::min<int64_t>(2ll * P * cap, h->C);
+  const int* nd = &h->ds->n_cand;
+  OM_LAUNCH(h, k_select, om_grid(bound, B), B, h->sarr, h->cand, 0, h->best, h->ds, nd);
+  OM_LAUNCH(h, k_flip1, om_grid(bound, B), B, h->cells, h->adj, h->best, h->cand, 0, h->epoch,
+            h->flip_epoch, h->reloc, h->adj_tmp, h->v2c, h->dirty, h->dirty_epoch, h->dirty_pass,
+            h->ds, nd);
+  OM_LAUNCH(h, k_flip2, om_grid(bound, B), B, (int*)h->adj, h->adj_tmp, h->flip_epoch, h->reloc,
+            h->cand, 0, h->epoch, h->work_epoch, h->work, h->best, h->ds, nd);
+  h->nbr_valid = false;
+  OM_TRY(om_fetch_scalars(h));
+  OM_TRY(om_check_dev_err(h));
+  if (abort_bits) *abort_bits = h->hs->abort;
+  if (own_records) *own_records = h->hs->max_count;
+  if (!h->hs->abort) h->pass_work_bound = h->hs->n_work;
+  if (n_cand) *n_cand = h->hs->n_cand;
+  if (n_flips_total) *n_flips_total = h->hs->n_flips;
+  return OM_OK;
+}
+
+// records of ALL ranks have been added: select, flip, patch twins, next work list
+int om_flip_round_apply_impl(om_handle* h, int64_t total_records, int64_t* n_cand,
+                             int64_t* n_flips_total) {
+  const int B = 256;
+  const int bound = (int)std::min<int64_t>(2 * total_records, h->C);
+  if (bound > 0) {
+    const int* nd = &h->ds->n_cand;
+    OM_LAUNCH(h, k_select, om_grid(bound, B), B, h->sarr, h->cand, 0, h->best, h->ds, nd);
+    OM_LAUNCH(h, k_flip1, om_grid(bound, B), B, h->cells, h->adj, h->best, h->cand, 0, h->epoch,
+              h->flip_epoch, h->reloc, h->adj_tmp, h->v2c, h->dirty, h->dirty_epoch,
+              h->dirty_pass, h->ds, nd);
+    OM_LAUNCH(h, k_flip2, om_grid(bound, B), B, (int*)h->adj, h->adj_tmp, h->flip_epoch, h->reloc,
+              h->cand, 0, h->epoch, h->work_epoch, h->work, h->best, h->ds, nd);
+    h->nbr_valid = false;
+  }
+  OM_TRY(om_fetch_scalars(h));
+  OM_TRY(om_check_dev_err(h));
+  h->pass_work_bound = h->hs->n_work;
+  if (n_cand) *n_cand = h->hs->n_cand;
+  if (n_flips_total) *n_flips_total = h->hs->n_flips;
+  return OM_OK;
+}
+
+int om_flip_pass_end_impl(om_handle* h, int64_t* n_flips, int32_t* n_rounds) {
+  // the last readback of the pass (a check round that found nothing) is current
+  if (n_flips) *n_flips = h->hs->n_flips;
+  if (n_rounds) *n_rounds = h->hs->n_rounds;
+  if (h->hs->n_flips > 0) OM_TRY(om_rebuild_rings(h, false));
+  return OM_OK;
+}
+
 // ---- sharded first round (om_flip_check_range / om_flip_add_records / om_flip_finish)
 int om_flip_check_range_impl(om_handle* h, double tol, int64_t clo, int64_t chi,
                              int64_t* n_records) {
@@ -426,11 +638,11 @@ int om_flip_check_range_impl(om_handle* h, double tol, int64_t clo, int64_t chi,
     if (h->D == 2)
       OM_LAUNCH(h, (k_suspect<2, 2>), om_grid(n, B), B, h->x, h->cells, (const int*)h->adj,
                 (int)clo, n, (const int*)nullptr, tol, h->sarr, h->cand, h->cand_epoch, h->epoch,
-                h->recs, h->ds, (const int*)nullptr);
+                h->recs, h->ds, (const int*)nullptr, shard_info(h, clo, chi));
     else
       OM_LAUNCH(h, (k_suspect<3, 2>), om_grid(n, B), B, h->x, h->cells, (const int*)h->adj,
                 (int)clo, n, (const int*)nullptr, tol, h->sarr, h->cand, h->cand_epoch, h->epoch,
-                h->recs, h->ds, (const int*)nullptr);
+                h->recs, h->ds, (const int*)nullptr, shard_info(h, clo, chi));
   }
   OM_TRY(om_fetch_scalars(h));
   OM_TRY(om_check_dev_err(h));

@@ -180,6 +180,14 @@ struct StepParams {
   const uint8_t* bflag;
   const int* ring;  // N x OM_RING_W ring rows, or nullptr
   int* over;        // vertices the main launch leaves to the list-driven (SRC 2) launch
+  // partitioned coordinates: foreign vertices are only current if pinned or stamped by the
+  // last band exchange (nullptr: everything is current)
+  const int* valid_epoch;
+  int valid_stamp;
+  __device__ __forceinline__ bool valid(int u) const {
+    return valid_epoch == nullptr || (u >= lo && u < hi) || bflag[u] != 0 ||
+           valid_epoch[u] == valid_stamp;
+  }
   int N;
   int lo, hi;  // vertices [lo, hi) are processed
   double omega;
@@ -226,6 +234,8 @@ constexpr int MAX_RING = 4096;
 template <int D, typename F>
 __device__ __forceinline__ void walk_star(const StepParams& p, int v, int c0, const int4& cell0,
                                           int j, int& err, F&& f) {
+  if (!(p.valid(cell_get(cell0, (j + 1) % 3)) && p.valid(cell_get(cell0, (j + 2) % 3))))
+    p.ds->stale = 1;
   f(ld_point<D>(p.x, cell_get(cell0, (j + 1) % 3)), ld_point<D>(p.x, cell_get(cell0, (j + 2) % 3)));
   bool closed = false;
   for (int dir = 0; dir < 2 && !closed; dir++) {
@@ -247,6 +257,8 @@ __device__ __forceinline__ void walk_star(const StepParams& p, int v, int c0, co
         closed = true;
         break;
       }
+      if (!(p.valid(cell_get(cl, (jn + 1) % 3)) && p.valid(cell_get(cl, (jn + 2) % 3))))
+        p.ds->stale = 1;
       f(ld_point<D>(p.x, cell_get(cl, (jn + 1) % 3)), ld_point<D>(p.x, cell_get(cl, (jn + 2) % 3)));
       cur = cn;
       kexit = 3 - jn - kn;
@@ -387,6 +399,7 @@ __global__ void __launch_bounds__(step_block<D>(), (D == 2 ? OM_K1_MINB : 3))
 #pragma unroll
           for (int q = 0; q < OM_RING_W; q++)
             if (e[q] >= 0) {
+              if (!p.valid(e[q] & RING_MASK)) p.ds->stale = 1;  // caller refreshes and repeats
               const double2* src =
                   reinterpret_cast<const double2*>(p.x) + (size_t)PER * (e[q] & RING_MASK);
 #pragma unroll
@@ -652,6 +665,7 @@ __global__ void k_sphere_sweep(double* x, int N, double cx, double cy, double cz
 
 __global__ void k_reset_step_scalars(DevScalars* ds) {
   ds->n_over = 0;
+  ds->stale = 0;
   ds->max_diff2_bits = 0ull;
   ds->n_limited = 0ull;
   ds->max_f_bits = 0ull;
@@ -668,6 +682,8 @@ StepParams make_params(om_handle* h, double* out) {
   p.bflag = h->bflag;
   p.ring = h->ring;
   p.over = h->over;
+  p.valid_epoch = (h->own_hi >= 0 && h->valid_epoch && !h->all_valid) ? h->valid_epoch : nullptr;
+  p.valid_stamp = h->valid_stamp;
   p.N = (int)h->N;
   p.lo = 0;
   p.hi = (int)h->N;
@@ -773,6 +789,15 @@ int om_update_points_impl(om_handle* h, double tol, om_step_stats* out, bool tar
   }
   OM_TRY(om_fetch_scalars(h));
   OM_TRY(om_check_dev_err(h));
+  if (!target_only && h->defer_commit && h->own_hi >= 0 && h->method != OM_CPT_LINEAR_SOLVE) {
+    // partitioned run: the caller commits once every rank reports "no stale coordinate"
+    om_step_stats_from_scalars(h, tol, out);
+    if (out) {
+      out->solver_iters = iters;
+      out->reserved = h->hs->stale;
+    }
+    return OM_OK;
+  }
   if (!target_only) {
     if (h->own_hi >= 0 && h->method != OM_CPT_LINEAR_SOLVE) {
       // sharded step: only [lo, hi) was written; fold it back, the rest of x stays
@@ -828,5 +853,171 @@ int om_rebuild_rings(om_handle* h, bool all) {
                 h->bflag, n, h->dirty, h->ring);
   }
   CUDA_TRY(cudaGetLastError());
+  return OM_OK;
+}
+
+// ---- band of a vertex range: own vertices within `depth` edges of a foreign vertex
+// (partitioned coordinates, dist.py).  Neighbours come from the ring row, or from a star walk
+// for vertices without one (boundary fans, valence > OM_RING_W).
+namespace {
+
+template <typename F>
+__device__ __forceinline__ void for_each_neighbour(const int4* __restrict__ cells,
+                                                   const int* __restrict__ adj,
+                                                   const int* __restrict__ v2c,
+                                                   const int* __restrict__ ring, int v, F&& f) {
+  const int4* rp = reinterpret_cast<const int4*>(ring + (size_t)OM_RING_W * v);
+  const int4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+  const int e[OM_RING_W] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+  if (e[0] != -2) {
+#pragma unroll
+    for (int q = 0; q < OM_RING_W; q++)
+      if (e[q] >= 0) f(e[q] & RING_MASK);
+    return;
+  }
+  const int c0 = v2c[v];
+  if (c0 == OM_NONE_CELL) return;
+  const int4 cell0 = __ldg(cells + c0);
+  const int j = slot_of(cell0, v);
+  if (j < 0) return;
+  f(cell_get(cell0, (j + 1) % 3));
+  f(cell_get(cell0, (j + 2) % 3));
+  bool closed = false;
+  for (int dir = 0; dir < 2 && !closed; dir++) {
+    int cur = c0, kexit = (j + 1 + dir) % 3, hops = 0;
+    while (true) {
+      const int t = __ldg(adj + 4 * (size_t)cur + kexit);
+      if (t < 0) break;
+      const int cn = t >> 2, kn = t & 3;
+      if (cn == c0) {
+        closed = true;
+        break;
+      }
+      const int4 cl = __ldg(cells + cn);
+      const int jn = slot_of(cl, v);
+      if (jn < 0 || jn == kn || ++hops > MAX_RING) {
+        closed = true;
+        break;
+      }
+      f(cell_get(cl, (jn + 1) % 3));
+      f(cell_get(cl, (jn + 2) % 3));
+      cur = cn;
+      kexit = 3 - jn - kn;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    k_band_mark(const int4* __restrict__ cells, const int* __restrict__ adj,
+                const int* __restrict__ v2c, const int* __restrict__ ring, int lo, int hi, int d,
+                uint8_t* __restrict__ mark) {
+  const int v = lo + blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= hi || mark[v] != 0) return;
+  bool hit = false;
+  for_each_neighbour(cells, adj, v2c, ring, v, [&](int u) {
+    if (d == 1)
+      hit |= (u < lo || u >= hi);
+    else if (u >= lo && u < hi) {
+      const int m = mark[u];
+      hit |= (m >= 1 && m < d);
+    }
+  });
+  if (hit) mark[v] = (uint8_t)d;
+}
+
+__global__ void __launch_bounds__(256)
+    k_band_collect(const uint8_t* __restrict__ mark, const uint8_t* __restrict__ bflag, int lo,
+                   int hi, int* __restrict__ band, DevScalars* ds) {
+  const int v = lo + blockIdx.x * blockDim.x + threadIdx.x;
+  const int vals[1] = {v};
+  const bool preds[1] = {v < hi && mark[v] != 0 && bflag[v] == 0};  // pinned ones never move
+  block_append<1>(&ds->n_over, band, vals, preds);
+}
+
+template <int PD>
+__global__ void k_band_pack(const double* __restrict__ x, const int* __restrict__ idx, int n,
+                            double* __restrict__ buf) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double2* src = reinterpret_cast<const double2*>(x) + (size_t)(PD / 2) * idx[i];
+  double2* dst = reinterpret_cast<double2*>(buf) + (size_t)(PD / 2) * i;
+#pragma unroll
+  for (int k = 0; k < PD / 2; k++) dst[k] = src[k];
+}
+
+template <int PD>
+__global__ void k_band_unpack(double* __restrict__ x, const int* __restrict__ idx, int n,
+                              const double* __restrict__ buf, int* __restrict__ valid_epoch,
+                              int stamp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int v = idx[i];
+  const double2* src = reinterpret_cast<const double2*>(buf) + (size_t)(PD / 2) * i;
+  double2* dst = reinterpret_cast<double2*>(x) + (size_t)(PD / 2) * v;
+#pragma unroll
+  for (int k = 0; k < PD / 2; k++) dst[k] = src[k];
+  valid_epoch[v] = stamp;
+}
+
+}  // namespace
+
+int om_band_alloc(om_handle* h) {
+  if (h->valid_epoch) return OM_OK;
+  const size_t N = (size_t)std::max<int64_t>(h->N, 1);
+  CUDA_TRY(om_malloc(h, &h->valid_epoch, sizeof(int) * N));
+  CUDA_TRY(om_malloc(h, &h->band, sizeof(int) * N));
+  CUDA_TRY(om_malloc(h, &h->band_mark, N));
+  CUDA_TRY(cudaMemsetAsync(h->valid_epoch, 0, sizeof(int) * N, h->stream));
+  return OM_OK;
+}
+
+int om_band_build_impl(om_handle* h, int depth, int64_t* n) {
+  if (n) *n = 0;
+  if (h->own_hi < 0 || h->N == 0) return OM_OK;
+  OM_TRY(om_band_alloc(h));
+  const int lo = (int)h->own_lo, hi = (int)h->own_hi;
+  const int B = 256, G = om_grid(hi - lo, B);
+  CUDA_TRY(cudaMemsetAsync(h->band_mark, 0, (size_t)h->N, h->stream));
+  CUDA_TRY(cudaMemsetAsync(&h->ds->n_over, 0, sizeof(int), h->stream));
+  for (int d = 1; d <= depth; d++)
+    OM_LAUNCH(h, k_band_mark, G, B, h->cells, (const int*)h->adj, h->v2c, h->ring, lo, hi, d,
+              h->band_mark);
+  OM_LAUNCH(h, k_band_collect, G, B, h->band_mark, h->bflag, lo, hi, h->band, h->ds);
+  OM_TRY(om_fetch_scalars(h));
+  OM_TRY(om_check_dev_err(h));
+  if (n) *n = h->hs->n_over;
+  return OM_OK;
+}
+
+int om_band_pack_impl(om_handle* h, const int* idx_dev, int64_t n, double* buf_dev) {
+  if (n <= 0) return OM_OK;
+  if (h->PD == 2)
+    OM_LAUNCH(h, k_band_pack<2>, om_grid(n, 256), 256, h->x, idx_dev, (int)n, buf_dev);
+  else
+    OM_LAUNCH(h, k_band_pack<4>, om_grid(n, 256), 256, h->x, idx_dev, (int)n, buf_dev);
+  CUDA_TRY(cudaGetLastError());
+  return OM_OK;
+}
+
+int om_band_unpack_impl(om_handle* h, const int* idx_dev, int64_t n, const double* buf_dev) {
+  if (n <= 0) return OM_OK;
+  OM_TRY(om_band_alloc(h));
+  if (h->PD == 2)
+    OM_LAUNCH(h, k_band_unpack<2>, om_grid(n, 256), 256, h->x, idx_dev, (int)n, buf_dev,
+              h->valid_epoch, h->valid_stamp);
+  else
+    OM_LAUNCH(h, k_band_unpack<4>, om_grid(n, 256), 256, h->x, idx_dev, (int)n, buf_dev,
+              h->valid_epoch, h->valid_stamp);
+  CUDA_TRY(cudaGetLastError());
+  return OM_OK;
+}
+
+// partitioned run: fold the freshly computed own range into the point array
+int om_commit_points_impl(om_handle* h) {
+  if (h->own_hi < 0) return OM_OK;
+  const size_t off = (size_t)h->own_lo * h->PD, cnt = (size_t)(h->own_hi - h->own_lo) * h->PD;
+  if (cnt)
+    CUDA_TRY(cudaMemcpyAsync(h->x + off, h->xnew + off, sizeof(double) * cnt,
+                             cudaMemcpyDeviceToDevice, h->stream));
   return OM_OK;
 }

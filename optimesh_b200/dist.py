@@ -25,6 +25,8 @@ import numpy as np
 
 # wall-clock breakdown of sharded_flip, filled when OM_DIST_PROFILE is set (diagnostics)
 PROFILE = {} if os.environ.get("OM_DIST_PROFILE") else None
+# diagnostics of the last run_partitioned call on this rank
+LAST_RUN = {}
 
 from .mesh import DeviceMesh
 
@@ -109,6 +111,253 @@ def sharded_flip(dm: DeviceMesh, group=None, tol: float = 0.0, max_steps: int = 
     PROFILE["records_n"] = PROFILE.get("records_n", 0) + sum(counts)
     return res
 
+
+class BandExchange:
+    """Keeps only a BAND of foreign coordinates current on every rank.
+
+    After the update of step k a rank needs, from the others, the vertices within a few edges
+    of its own vertex range: the rings of its own vertices (next update) and the cells it
+    examines in the flip check.  Every rank therefore publishes the part of ITS range that
+    lies within `depth` edges of a foreign vertex (`om_band_build`, recomputed only after
+    flips changed the topology); the index lists are all-gathered when they change, the
+    coordinates every step.  All ranks hold the same topology and numbering, so ids mean the
+    same thing everywhere.  A flip check that would read a coordinate outside own range +
+    band reports `stale`; the caller then falls back to one full all-gather."""
+
+    def __init__(self, dm: DeviceMesh, group=None, depth: int = 3):
+        import torch.distributed as dist
+
+        self.dm, self.group, self.depth = dm, group, depth
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.dirty = True
+        self.counts = None
+        self.idx_all = None
+        self.full_gathers = 0
+        self.band_bytes = 0
+        self.slow_rounds = 0
+        self.age, self.force, self.refresh = 0, False, 8
+        self.caps = [65536, 4096]  # record-slot capacities: round 0 / later rounds
+        self.buffers = {}
+        # the cells that sit on this rank's vertices (must be asked before any flip)
+        lo, hi = owned_range(dm.n, self.rank, self.world)
+        if self.rank == self.world - 1:
+            hi = dm.n + 1  # the last range also takes what is left
+        self.cell_range = dm.cell_range_of_vertices(lo, hi)
+
+    def full_gather(self):
+        import torch.distributed as dist
+
+        n = self.dm.n
+        chunk = chunk_of(n, self.world)
+        x = device_points_tensor(self.dm)
+        out = x[: self.world * chunk]
+        send = out[self.rank * chunk:(self.rank + 1) * chunk].clone()
+        dist.all_gather_into_tensor(out, send, group=self.group)
+        self.dm.coords_all_valid()
+        self.full_gathers += 1
+
+    def _rebuild(self):
+        import torch
+        import torch.distributed as dist
+
+        ptr, n = self.dm.band_build(self.depth)
+        cnt = torch.zeros(self.world, dtype=torch.int64, device="cuda")
+        cnt[self.rank] = n
+        dist.all_reduce(cnt, group=self.group)
+        self.counts = cnt.tolist()
+        maxn = max(max(self.counts), 1)
+        send = torch.zeros(maxn, dtype=torch.int32, device="cuda")
+        if n > 0:
+            send[:n] = torch.as_tensor(_DevPtr(ptr, (n,), "<i4"), device="cuda")
+        self.idx_all = torch.empty(self.world * maxn, dtype=torch.int32, device="cuda")
+        dist.all_gather_into_tensor(self.idx_all, send, group=self.group)
+        self.idx_all = self.idx_all.view(self.world, maxn)
+        self.maxn = maxn
+        self.dirty = False
+
+    def exchange(self):
+        """Call after the update: foreign coordinates become stale, bands are refreshed."""
+        import torch
+        import torch.distributed as dist
+
+        dm = self.dm
+        dm.coords_invalidate()
+        # The band only has to be a superset of what the others read; every read is
+        # validated (stale -> full gather), so after flips it is rebuilt lazily: at once
+        # after a fallback, otherwise every `refresh` steps.
+        self.age += 1
+        if self.counts is None or self.force or (self.dirty and self.age >= self.refresh):
+            self._rebuild()
+            self.age, self.force = 0, False
+        stride = dm.points_device()[2]
+        send = torch.zeros(self.maxn, stride, dtype=torch.float64, device="cuda")
+        n = self.counts[self.rank]
+        if n > 0:
+            dm.band_pack(self.idx_all[self.rank].data_ptr(), n, send.data_ptr())
+        recv = torch.empty(self.world * self.maxn, stride, dtype=torch.float64, device="cuda")
+        dist.all_gather_into_tensor(recv, send, group=self.group)
+        recv = recv.view(self.world, self.maxn, stride)
+        for r in range(self.world):
+            if r != self.rank and self.counts[r] > 0:
+                dm.band_unpack(self.idx_all[r].data_ptr(), self.counts[r], recv[r].data_ptr())
+        self.band_bytes += int(sum(self.counts)) * stride * 8
+        self._keep = (send, recv)  # alive until the stream has consumed them
+
+
+def _pow2_at_least(n: int) -> int:
+    p = 1
+    while p < n:
+        p *= 2
+    return p
+
+
+def partitioned_flip(dm: DeviceMesh, band: BandExchange, group=None, tol: float = 0.0,
+                     max_steps: int = 100):
+    """flip-until-Delaunay with every check round split over the ranks by cell range.  Per
+    round: each rank examines its cells (all of them in round 0, its share of the work list
+    later); the flagged-edge records travel in fixed-capacity slots (one all-gather, no host
+    readback between check and flips); every rank applies ALL records and runs select / flip /
+    twin patch itself (integer work on identical topology).  A stale coordinate or a slot
+    overflow rejects the round on every rank alike; it is then repeated the slow way."""
+    import torch
+    import torch.distributed as dist
+
+    world, rank = band.world, band.rank
+    clo, chi = band.cell_range
+    dm.flip_pass_begin()
+    first = True
+    for rnd in range(max_steps + 1):
+        cap = band.caps[0 if first else 1]
+        key = (cap,)
+        if key not in band.buffers:
+            band.buffers[key] = (torch.zeros(cap + 1, 2, dtype=torch.float64, device="cuda"),
+                                 torch.empty(world * (cap + 1), 2, dtype=torch.float64,
+                                             device="cuda"))
+        send, recv = band.buffers[key]
+        dm.flip_round_check_nofetch(first, clo, chi, tol)
+        dm.flip_round_pack(cap, send.data_ptr())
+        dist.all_gather_into_tensor(recv, send, group=group)
+        ncand, _, abort, maxc = dm.flip_round_apply_gathered(recv.data_ptr(), world, cap)
+        if abort:
+            band.slow_rounds += 1
+            ncand = _slow_round(dm, band, first, clo, chi, tol, group, abort)
+        # next capacity for this kind of round: twice the largest count seen (all ranks agree)
+        band.caps[0 if first else 1] = max(1024, _pow2_at_least(2 * max(maxc, 1)))
+        first = False
+        if ncand == 0:
+            break
+    nf, nr = dm.flip_pass_end()
+    if nf > 0:
+        band.dirty = True
+    return nf, nr
+
+
+def _slow_round(dm, band, first, clo, chi, tol, group, abort):
+    """One round with host-side counts (exact buffer sizes); used after a rejected round."""
+    import torch
+    import torch.distributed as dist
+
+    world, rank = band.world, band.rank
+    if abort & 1:
+        band.full_gather()  # a cell drifted outside own range + band
+        band.dirty, band.force = True, True
+    while True:
+        ptr, n, stale = dm.flip_round_check(first, clo, chi, tol)
+        info = torch.zeros(2 * world, dtype=torch.int64, device="cuda")
+        info[2 * rank] = n
+        info[2 * rank + 1] = int(stale)
+        dist.all_reduce(info, group=group)
+        info = info.tolist()
+        counts, stales = info[0::2], info[1::2]
+        if any(stales):
+            band.full_gather()
+            continue
+        break
+    total = sum(counts)
+    if total == 0:
+        return 0
+    maxc = max(counts)
+    send = torch.zeros(maxc, 2, dtype=torch.float64, device="cuda")
+    if n > 0:
+        send[:n] = torch.as_tensor(_DevPtr(ptr, (n, 2), "<f8"), device="cuda")
+    out = torch.empty(world * maxc, 2, dtype=torch.float64, device="cuda")
+    dist.all_gather_into_tensor(out, send, group=group)
+    for r in range(world):
+        if counts[r] > 0:
+            dm.flip_add_records(out[r * maxc:].data_ptr(), counts[r])
+    ncand, _ = dm.flip_round_apply(total)
+    return ncand
+
+
+def partitioned_step(dm: DeviceMesh, band: BandExchange, tol: float = 0.0, group=None):
+    """One loop iteration with partitioned coordinates: update of the own vertex range (kept
+    aside until every rank reports that it read no stale coordinate), statistics all-reduced,
+    band exchange, round-wise sharded flip pass."""
+    import torch
+    import torch.distributed as dist
+
+    while True:
+        st = dm.update_points(tol)
+        red = torch.tensor([st["max_diff2"], float(st["n_limited"]), float(st["stale"])],
+                           dtype=torch.float64, device="cuda")
+        dist.all_reduce(red[:1], op=dist.ReduceOp.MAX, group=group)
+        dist.all_reduce(red[1:], op=dist.ReduceOp.SUM, group=group)
+        red = red.tolist()
+        if red[2] > 0:  # a ring reached outside own range + band: refresh, repeat
+            band.full_gather()
+            band.dirty, band.force = True, True
+            continue
+        break
+    dm.commit_points()
+    band.exchange()
+    nf, nr = partitioned_flip(dm, band, group, 0.0)
+    return dict(max_diff2=red[0], n_limited=int(red[1]), n_flips=nf, n_flip_rounds=nr)
+
+
+def partitioned_begin(dm: DeviceMesh, group=None, band_depth: int = 3) -> BandExchange:
+    """Sets the handle up for partitioned stepping (call right after om_create, before any
+    flip) and runs the loop's initial flip pass."""
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    lo, hi = owned_range(dm.n, rank, world)
+    band = BandExchange(dm, group, band_depth)
+    dm.set_owned_range(lo, hi)
+    dm.coords_all_valid()
+    partitioned_flip(dm, band, group)
+    dm.set_deferred_commit(True)
+    return band
+
+
+def partitioned_end(dm: DeviceMesh, band: BandExchange):
+    dm.set_deferred_commit(False)
+    band.full_gather()  # every rank holds the complete point array again
+    dm.set_owned_range(0, -1)
+
+
+def run_partitioned(dm: DeviceMesh, method: str, tol: float, max_num_steps: int,
+                    omega: float = 1.0, group=None, log=None, band_depth: int = 3):
+    """optimize() loop with partitioned coordinates.  Bit-identical to one GPU."""
+    dm.set_method(method, omega)
+    band = partitioned_begin(dm, group, band_depth)
+    k = 0
+    try:
+        while True:
+            k += 1
+            st = partitioned_step(dm, band, tol, group)
+            is_final = (st["max_diff2"] < tol * tol) or k >= max_num_steps
+            if log is not None:
+                log.append(dict(step=k, **st))
+            if is_final:
+                break
+    finally:
+        LAST_RUN.update(steps=k, fallback_full_gathers=band.full_gathers,
+                        slow_rounds=band.slow_rounds,
+                        band_vertices=int(sum(band.counts or [0])), band_bytes=band.band_bytes)
+        partitioned_end(dm, band)
+    return k, band
 
 class GpuShard:
     """Adapter: the operations `run_sharded` needs, on a DeviceMesh."""
@@ -196,7 +445,7 @@ def run_sharded(shard, method: str, tol: float, max_num_steps: int, omega: float
 def optimize_points_cells_sharded(points, cells, method: str, tol: float, max_num_steps: int,
                                   omega: float = 1.0, implicit_surface=None,
                                   implicit_surface_tol: float = 1.0e-10, device=None, group=None,
-                                  log=None):
+                                  log=None, exchange: str = "band"):
     """`optimize_points_cells` for a process group: every rank passes the same arrays and
     gets the same result back (README.md:124-126 semantics)."""
     import torch
@@ -214,5 +463,13 @@ def optimize_points_cells_sharded(points, cells, method: str, tol: float, max_nu
             dm.set_sphere(implicit_surface.center, implicit_surface.radius, implicit_surface_tol)
         else:
             raise NotImplementedError("sharded runs support the built-in Sphere surface only")
-        run_sharded(GpuShard(dm, group), method, tol, max_num_steps, omega, group, log)
+        import torch.distributed as dist
+
+        partition = (exchange == "band" and implicit_surface is None
+                     and "linear-solve" not in method.lower().replace(" ", "-")
+                     and dist.get_world_size(group) > 1)
+        if partition:
+            run_partitioned(dm, method, tol, max_num_steps, omega, group, log)
+        else:
+            run_sharded(GpuShard(dm, group), method, tol, max_num_steps, omega, group, log)
         return dm.points, dm.cells(cells.dtype)

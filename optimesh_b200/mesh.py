@@ -227,6 +227,70 @@ class DeviceMesh:
             warnings.warn("Maximum number of edge flips reached.")
         return nf.value, nr.value
 
+    # -- partitioned coordinates (dist.py)
+    def cell_range_of_vertices(self, vlo: int, vhi: int):
+        a, b = C.c_int64(), C.c_int64()
+        check(self._lib.om_cell_range_of_vertices(self._h, int(vlo), int(vhi), C.byref(a),
+                                                  C.byref(b)))
+        return a.value, b.value
+
+    def set_deferred_commit(self, on: bool):
+        check(self._lib.om_set_deferred_commit(self._h, int(bool(on))))
+
+    def commit_points(self):
+        check(self._lib.om_commit_points(self._h))
+
+    def coords_invalidate(self):
+        check(self._lib.om_coords_invalidate(self._h))
+
+    def coords_all_valid(self):
+        check(self._lib.om_coords_all_valid(self._h))
+
+    def band_build(self, depth: int = 3):
+        n, p = C.c_int64(), C.c_void_p()
+        check(self._lib.om_band_build(self._h, int(depth), C.byref(n), C.byref(p)))
+        return p.value, n.value
+
+    def band_pack(self, idx_ptr: int, n: int, buf_ptr: int):
+        check(self._lib.om_band_pack(self._h, C.c_void_p(idx_ptr), int(n), C.c_void_p(buf_ptr)))
+
+    def band_unpack(self, idx_ptr: int, n: int, buf_ptr: int):
+        check(self._lib.om_band_unpack(self._h, C.c_void_p(idx_ptr), int(n), C.c_void_p(buf_ptr)))
+
+    def flip_pass_begin(self):
+        check(self._lib.om_flip_pass_begin(self._h))
+
+    def flip_round_check(self, first: bool, cell_lo: int, cell_hi: int, tol: float = 0.0):
+        n, p, st = C.c_int64(), C.c_void_p(), C.c_int32()
+        check(self._lib.om_flip_round_check(self._h, float(tol), int(bool(first)), int(cell_lo),
+                                            int(cell_hi), C.byref(n), C.byref(p), C.byref(st)))
+        return p.value, n.value, bool(st.value)
+
+    def flip_round_check_nofetch(self, first: bool, cell_lo: int, cell_hi: int, tol: float = 0.0):
+        check(self._lib.om_flip_round_check(self._h, float(tol), int(bool(first)), int(cell_lo),
+                                            int(cell_hi), None, None, None))
+
+    def flip_round_pack(self, capacity: int, slot_ptr: int):
+        check(self._lib.om_flip_round_pack(self._h, int(capacity), C.c_void_p(slot_ptr)))
+
+    def flip_round_apply_gathered(self, gathered_ptr: int, n_ranks: int, capacity: int):
+        nc, nf, ab, own = C.c_int64(), C.c_int64(), C.c_int32(), C.c_int64()
+        check(self._lib.om_flip_round_apply_gathered(self._h, C.c_void_p(gathered_ptr),
+                                                     int(n_ranks), int(capacity), C.byref(nc),
+                                                     C.byref(nf), C.byref(ab), C.byref(own)))
+        return nc.value, nf.value, ab.value, own.value
+
+    def flip_round_apply(self, total_records: int):
+        nc, nf = C.c_int64(), C.c_int64()
+        check(self._lib.om_flip_round_apply(self._h, int(total_records), C.byref(nc),
+                                            C.byref(nf)))
+        return nc.value, nf.value
+
+    def flip_pass_end(self):
+        nf, nr = C.c_int64(), C.c_int32()
+        check(self._lib.om_flip_pass_end(self._h, C.byref(nf), C.byref(nr)))
+        return nf.value, nr.value
+
     def set_owned_range(self, lo: int, hi: int):
         check(self._lib.om_set_owned_range(self._h, int(lo), int(hi)))
 

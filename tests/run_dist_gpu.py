@@ -33,6 +33,16 @@ def main():
         log = []
         p, c = optimize_points_cells_sharded(pts, cells, method, 1e-9, 8, omega=omega, log=log,
                                              device=local, **kw)
+        from optimesh_b200 import dist as _d
+
+        diag = dict(_d.LAST_RUN)
+        _d.LAST_RUN.clear()
+        # the same with the replicated-coordinates exchange
+        p2, c2 = optimize_points_cells_sharded(pts, cells, method, 1e-9, 8, omega=omega,
+                                               device=local, exchange="allgather", **kw)
+        if not (np.array_equal(p2, p) and np.array_equal(c2, c)):
+            print(f"[rank {rank}] {name}: band and all-gather exchanges differ", flush=True)
+            ok = False
         rlog = []
         rp, rc = ob.optimize_points_cells(pts, cells, method, 1e-9, 8, omega=omega, log=rlog,
                                           device=local, **kw)
@@ -43,7 +53,7 @@ def main():
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if rank == 0:
             print(f"{name:7s} {method:20s} world={world} N={len(pts)} flips={sum(l['n_flips'] for l in log)} "
-                  f"bit-identical={bool(flag.item())}", flush=True)
+                  f"bit-identical={bool(flag.item())} {diag}", flush=True)
         ok = ok and bool(flag.item())
     dist.destroy_process_group()
     if not ok:
