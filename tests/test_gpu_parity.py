@@ -578,3 +578,93 @@ def test_cli_end_to_end(ob, G, tmp_path):
     fmt = str(tmp_path / "s{:02d}.npz")
     assert cli.main([src, dst, "-m", "cpt-fixed-point", "-n", "2", "-t", "0", "-f", fmt]) == 0
     assert os.path.exists(fmt.format(1)) and os.path.exists(fmt.format(2))
+
+
+def test_partitioned_simulation(ob, G):
+    """The partitioned-coordinates path of dist.py (band exchange, validated reads, deferred
+    commit, round-wise flip pass with gathered record slots) emulated in one process with P
+    handles; what NCCL does between GPUs is done here with device copies.  Must be
+    bit-identical to the single-handle run."""
+    import torch
+
+    from optimesh_b200.dist import _DevPtr, owned_range
+
+    pts, cells = G.disk_mapped_grid(70, 0.25, 3, shuffle=True)
+    P, steps, cap = 3, 6, 1 << 14
+    method, omega = "cvt-block-diagonal", 1.0
+    log = []
+    ref_p, ref_c = ob.optimize_points_cells(pts, cells, method, 0.0, steps, omega=omega, log=log)
+    hs = [ob.DeviceMesh(pts, cells) for _ in range(P)]
+
+    def flip_pass():
+        for h in hs:
+            h.flip_pass_begin()
+        first = True
+        while True:
+            slots = []
+            for r, h in enumerate(hs):
+                h.flip_round_check_nofetch(first, *cranges[r])
+                slot = torch.zeros(cap + 1, 2, dtype=torch.float64, device="cuda")
+                h.flip_round_pack(cap, slot.data_ptr())
+                slots.append(slot)
+            torch.cuda.synchronize()
+            gathered = torch.cat(slots).contiguous()
+            res = [h.flip_round_apply_gathered(gathered.data_ptr(), P, cap) for h in hs]
+            assert all(x == res[0] for x in res) and res[0][2] == 0  # same everywhere, no abort
+            first = False
+            if res[0][0] == 0:
+                break
+        ends = [h.flip_pass_end() for h in hs]
+        assert all(e == ends[0] for e in ends)
+        return ends[0]
+
+    try:
+        ranges = [owned_range(hs[0].n, r, P) for r in range(P)]
+        cranges = [hs[r].cell_range_of_vertices(ranges[r][0], ranges[r][1] if r < P - 1
+                                                else hs[r].n + 1) for r in range(P)]
+        assert cranges[0][0] == 0 and cranges[-1][1] == hs[0].c
+        for r, h in enumerate(hs):
+            h.set_method(method, omega)
+            h.set_owned_range(*ranges[r])
+            h.coords_all_valid()
+        flip_pass()
+        for h in hs:
+            h.set_deferred_commit(True)
+        for k in range(steps):
+            sts = [h.update_points(0.0) for h in hs]
+            assert all(st["stale"] == 0 for st in sts)
+            assert sum(st["n_limited"] for st in sts) == log[k]["n_limited"]
+            for h in hs:
+                h.commit_points()
+                h.coords_invalidate()
+            bands = [h.band_build(3) for h in hs]
+            stride = hs[0].points_device()[2]
+            for s_, (ptr, n) in enumerate(bands):
+                assert 0 < n < hs[0].n // 2  # a band, not the whole range
+                buf = torch.zeros(n, stride, dtype=torch.float64, device="cuda")
+                hs[s_].band_pack(ptr, n, buf.data_ptr())
+                torch.cuda.synchronize()
+                for r_, h in enumerate(hs):
+                    if r_ != s_:
+                        h.band_unpack(ptr, n, buf.data_ptr())
+                torch.cuda.synchronize()
+            nf, nr = flip_pass()
+            assert (nf, nr) == (log[k]["n_flips"], log[k]["n_flip_rounds"])
+        # own ranges are current everywhere they are owned: assemble and compare
+        xs = []
+        for r, h in enumerate(hs):
+            ptr, n_alloc, st = h.points_device()
+            xs.append(torch.as_tensor(_DevPtr(ptr, (n_alloc, st), "<f8"), device="cuda"))
+        for r in range(P):
+            lo, hi = ranges[r]
+            for s_ in range(P):
+                if s_ != r:
+                    xs[s_][lo:hi] = xs[r][lo:hi]
+        torch.cuda.synchronize()
+        for h in hs:
+            h.set_deferred_commit(False)
+            h.set_owned_range(0, -1)
+            assert np.array_equal(h.points, ref_p) and np.array_equal(h.cells(), ref_c)
+    finally:
+        for h in hs:
+            h.close()
