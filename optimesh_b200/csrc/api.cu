@@ -841,8 +841,11 @@ int om_set_owned_range(om_handle* h, int64_t lo, int64_t hi) {
                  (long long)h->N);
     return OM_ERR_ARG;
   }
+  const bool changed = (hi >= 0 ? lo : 0) != h->own_lo || hi != h->own_hi;
   h->own_lo = hi >= 0 ? lo : 0;
   h->own_hi = hi;
+  // rows outside the previous range were not maintained: make all of them current again
+  if (changed && h->rings_partial) OM_TRY(om_rebuild_rings(h, true));
   return OM_OK;
 }
 

@@ -125,6 +125,7 @@ struct om_handle {
   int* valid_epoch = nullptr;  // N: stamp of the last band exchange that refreshed the vertex
   int valid_stamp = 1;
   bool all_valid = true;       // right after a full all-gather (or single GPU)
+  bool rings_partial = false;  // ring rows outside the owned range may be out of date
   bool defer_commit = false;   // om_update_points leaves the own range in xnew (om_commit_points)
   int* band = nullptr;         // N: own vertices other ranks may need (internal ids)
   uint8_t* band_mark = nullptr;  // N: hop distance to a foreign vertex (0: far)

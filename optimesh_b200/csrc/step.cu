@@ -284,10 +284,11 @@ template <bool LIST>
 __global__ void __launch_bounds__(256)
     k_build_rings(const int4* __restrict__ cells, const int* __restrict__ adj,
                   const int* __restrict__ v2c, const uint8_t* __restrict__ bflag, int n,
-                  const int* __restrict__ list, int* __restrict__ ring) {
+                  const int* __restrict__ list, int* __restrict__ ring, int lo, int hi) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int v = LIST ? list[i] : i;
+  if (v < lo || v >= hi) return;  // partitioned run: only the own range's rows are read
   int e[OM_RING_W];
 #pragma unroll
   for (int q = 0; q < OM_RING_W; q++) e[q] = -1;
@@ -845,12 +846,18 @@ int om_rebuild_rings(om_handle* h, bool all) {
   const int B = 256;
   if (all) {
     OM_LAUNCH(h, (k_build_rings<false>), om_grid(h->N, B), B, h->cells, (const int*)h->adj, h->v2c,
-              h->bflag, (int)h->N, (const int*)nullptr, h->ring);
+              h->bflag, (int)h->N, (const int*)nullptr, h->ring, 0, (int)h->N);
+    h->rings_partial = false;
   } else {
     const int n = h->hs->n_dirty;  // fetched by the flip pass
+    // with an owned range only its rows are kept current (nothing else reads ring rows);
+    // om_set_owned_range(whole mesh) rebuilds all of them
+    const bool ranged = h->own_hi >= 0;
+    if (ranged) h->rings_partial = true;
     if (n > 0)
       OM_LAUNCH(h, (k_build_rings<true>), om_grid(n, B), B, h->cells, (const int*)h->adj, h->v2c,
-                h->bflag, n, h->dirty, h->ring);
+                h->bflag, n, h->dirty, h->ring, ranged ? (int)h->own_lo : 0,
+                ranged ? (int)h->own_hi : (int)h->N);
   }
   CUDA_TRY(cudaGetLastError());
   return OM_OK;
