@@ -273,6 +273,13 @@ def run_b200(args):
     tim = dm.timing()
     dm.set_timing(False)
     if band is not None:
+        from optimesh_b200 import dist as _d
+
+        if _d.PROFILE:
+            steps_p = max(_d.PROFILE.get("steps", 1), 1)
+            print(f"[rank {rank}] ms/step: " + " ".join(
+                f"{k}={1e3 * v / steps_p:.3f}" if isinstance(v, float) else f"{k}={v}"
+                for k, v in _d.PROFILE.items()), file=sys.stderr)
         line_band = {"band_vertices_all_ranks": int(sum(band.counts or [0])),
                      "fallback_full_gathers": band.full_gathers,
                      "slow_flip_rounds": band.slow_rounds}

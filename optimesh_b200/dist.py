@@ -112,6 +112,16 @@ def sharded_flip(dm: DeviceMesh, group=None, tol: float = 0.0, max_steps: int = 
     return res
 
 
+def _tick():
+    """Wall clock after a device sync -- only when OM_DIST_PROFILE is set (diagnostics)."""
+    if PROFILE is None:
+        return 0.0
+    import torch
+
+    torch.cuda.synchronize()
+    return time.perf_counter()
+
+
 class BandExchange:
     """Keeps only a BAND of foreign coordinates current on every rank.
 
@@ -187,22 +197,34 @@ class BandExchange:
         # validated (stale -> full gather), so after flips it is rebuilt lazily: at once
         # after a fallback, otherwise every `refresh` steps.
         self.age += 1
+        b0 = _tick()
         if self.counts is None or self.force or (self.dirty and self.age >= self.refresh):
             self._rebuild()
             self.age, self.force = 0, False
+            if PROFILE is not None:
+                PROFILE["band_rebuilds"] = PROFILE.get("band_rebuilds", 0) + 1
+        b1 = _tick()
         stride = dm.points_device()[2]
-        send = torch.zeros(self.maxn, stride, dtype=torch.float64, device="cuda")
+        key = ("band", self.maxn, stride)
+        if key not in self.buffers:
+            self.buffers = {k: v for k, v in self.buffers.items() if k[0] != "band"}
+            self.buffers[key] = (
+                torch.zeros(self.maxn, stride, dtype=torch.float64, device="cuda"),
+                torch.empty(self.world * self.maxn, stride, dtype=torch.float64, device="cuda"))
+        send, recv = self.buffers[key]
         n = self.counts[self.rank]
         if n > 0:
             dm.band_pack(self.idx_all[self.rank].data_ptr(), n, send.data_ptr())
-        recv = torch.empty(self.world * self.maxn, stride, dtype=torch.float64, device="cuda")
         dist.all_gather_into_tensor(recv, send, group=self.group)
         recv = recv.view(self.world, self.maxn, stride)
         for r in range(self.world):
             if r != self.rank and self.counts[r] > 0:
                 dm.band_unpack(self.idx_all[r].data_ptr(), self.counts[r], recv[r].data_ptr())
         self.band_bytes += int(sum(self.counts)) * stride * 8
-        self._keep = (send, recv)  # alive until the stream has consumed them
+        b2 = _tick()
+        if PROFILE is not None:
+            PROFILE["band_rebuild"] = PROFILE.get("band_rebuild", 0.0) + (b1 - b0)
+            PROFILE["band_xchg"] = PROFILE.get("band_xchg", 0.0) + (b2 - b1)
 
 
 def _pow2_at_least(n: int) -> int:
@@ -235,10 +257,21 @@ def partitioned_flip(dm: DeviceMesh, band: BandExchange, group=None, tol: float 
                                  torch.empty(world * (cap + 1), 2, dtype=torch.float64,
                                              device="cuda"))
         send, recv = band.buffers[key]
+        r0 = _tick()
         dm.flip_round_check_nofetch(first, clo, chi, tol)
         dm.flip_round_pack(cap, send.data_ptr())
+        r1 = _tick()
         dist.all_gather_into_tensor(recv, send, group=group)
+        r2 = _tick()
         ncand, _, abort, maxc = dm.flip_round_apply_gathered(recv.data_ptr(), world, cap)
+        r3 = _tick()
+        if PROFILE is not None:
+            tag = "r0" if first else "rN"
+            for key2, dt in ((tag + "_check", r1 - r0), (tag + "_gather", r2 - r1),
+                             (tag + "_apply", r3 - r2)):
+                PROFILE[key2] = PROFILE.get(key2, 0.0) + dt
+            PROFILE[tag + "_n"] = PROFILE.get(tag + "_n", 0) + 1
+            PROFILE[tag + "_cap"] = cap
         if abort:
             band.slow_rounds += 1
             ncand = _slow_round(dm, band, first, clo, chi, tol, group, abort)
@@ -297,21 +330,33 @@ def partitioned_step(dm: DeviceMesh, band: BandExchange, tol: float = 0.0, group
     import torch
     import torch.distributed as dist
 
+    t0 = _tick()
     while True:
         st = dm.update_points(tol)
-        red = torch.tensor([st["max_diff2"], float(st["n_limited"]), float(st["stale"])],
-                           dtype=torch.float64, device="cuda")
-        dist.all_reduce(red[:1], op=dist.ReduceOp.MAX, group=group)
-        dist.all_reduce(red[1:], op=dist.ReduceOp.SUM, group=group)
-        red = red.tolist()
+        t1 = _tick()
+        # one collective for max |diff|^2 (max), #limited and "stale" (sums)
+        mine = torch.tensor([st["max_diff2"], float(st["n_limited"]), float(st["stale"])],
+                            dtype=torch.float64, device="cuda")
+        allr = torch.empty(band.world * 3, dtype=torch.float64, device="cuda")
+        dist.all_gather_into_tensor(allr, mine, group=group)
+        allr = allr.view(band.world, 3).tolist()
+        red = [max(a[0] for a in allr), sum(a[1] for a in allr), sum(a[2] for a in allr)]
         if red[2] > 0:  # a ring reached outside own range + band: refresh, repeat
             band.full_gather()
             band.dirty, band.force = True, True
             continue
         break
     dm.commit_points()
+    t2 = _tick()
     band.exchange()
+    t3 = _tick()
     nf, nr = partitioned_flip(dm, band, group, 0.0)
+    t4 = _tick()
+    if PROFILE is not None:
+        for key, dt in (("update", t1 - t0), ("reduce+commit", t2 - t1), ("band", t3 - t2),
+                        ("flips", t4 - t3)):
+            PROFILE[key] = PROFILE.get(key, 0.0) + dt
+        PROFILE["steps"] = PROFILE.get("steps", 0) + 1
     return dict(max_diff2=red[0], n_limited=int(red[1]), n_flips=nf, n_flip_rounds=nr)
 
 
