@@ -273,9 +273,12 @@ __device__ __forceinline__ void walk_star(const StepParams& p, int v, int c0, co
 // fan, or more than OM_RING_W cells).  The order is the walk order, so the sums are
 // bit-identical to the walk; the rows only remove the dependent adj -> cell -> point chains.
 // threads per block of the step kernels (3D: smaller, its ring staging is twice as wide)
+#ifndef OM_K1_BLOCK
+#define OM_K1_BLOCK 256
+#endif
 template <int D>
 __host__ __device__ constexpr int step_block() {
-  return D == 2 ? 256 : 128;
+  return D == 2 ? OM_K1_BLOCK : 128;
 }
 constexpr int RING_FLAG = 1 << 30;
 constexpr int RING_MASK = RING_FLAG - 1;
@@ -407,8 +410,13 @@ __global__ void __launch_bounds__(step_block<D>(), (D == 2 ? OM_K1_MINB : 3))
               for (int h2 = 0; h2 < PER; h2++) {
                 const unsigned dst = (unsigned)__cvta_generic_to_shared(
                     &ring_sm[(q * PER + h2) * step_block<D>() + threadIdx.x]);
+                #ifdef OM_K1_CPASYNC_CG
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst),
+                             "l"(src + h2));
+#else
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst),
                              "l"(src + h2));
+#endif
               }
               nring = q + 1;
               rflags |= (e[q] & RING_FLAG) ? (1u << q) : 0u;
