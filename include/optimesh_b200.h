@@ -35,7 +35,8 @@ enum {
   OM_CVT_BLOCK_DIAGONAL = 1, /* --method cvt-block-diagonal    README.md:80  */
   OM_CPT_FIXED_POINT = 2,    /* --method cpt-fixed-point       README.md:90  */
   OM_ODT_FIXED_POINT = 3,    /* --method odt-fixed-point       README.md:104 */
-  OM_CPT_LINEAR_SOLVE = 4    /* --method cpt-linear-solve      README.md:90  */
+  OM_CPT_LINEAR_SOLVE = 4,   /* --method cpt-linear-solve      README.md:90  */
+  OM_ODT_DP_FP = 5           /* --method odt-dp-fp             README.md:104 */
 };
 
 /* error codes */
@@ -92,6 +93,10 @@ int om_destroy(om_handle* h);
 int om_set_method(om_handle* h, int method, double omega);
 /* step limiter of the driver loop on/off (default on) */
 int om_set_limiter(om_handle* h, int on);
+/* ODT methods (odt-fixed-point, odt-dp-fp; README.md:104-113): cells with a boundary edge
+ * contribute their barycenter instead of their circumcenter, which can lie outside the
+ * domain there (default on; 0 = circumcenters everywhere, SURVEY.md A.8 as written) */
+int om_set_odt_boundary_barycenters(om_handle* h, int on);
 /* implicit surface, README.md:146-176.  kind 0: none; kind 1: sphere
  * f(x) = R^2 - |x - c|^2, params = {cx, cy, cz, R} (the README's Sphere is {0,0,0,1}) */
 int om_set_surface(om_handle* h, int kind, double tol, const double* params, int max_sweeps);

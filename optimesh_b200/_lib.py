@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(HERE, "liboptimesh_b200.so")
 
 OM_RENUMBER = 1
 (OM_LLOYD, OM_CVT_BLOCK_DIAGONAL, OM_CPT_FIXED_POINT, OM_ODT_FIXED_POINT,
- OM_CPT_LINEAR_SOLVE) = range(5)
+ OM_CPT_LINEAR_SOLVE, OM_ODT_DP_FP) = range(6)
 (OM_OK, OM_ERR_CUDA, OM_ERR_ARG, OM_ERR_DEGENERATE, OM_ERR_NONMANIFOLD, OM_ERR_INDEX,
  OM_ERR_NOT_CONVERGED) = range(7)
 
@@ -49,6 +49,7 @@ SIGNATURES = {
     "om_destroy": (C.c_int, [_H]),
     "om_set_method": (C.c_int, [_H, C.c_int, C.c_double]),
     "om_set_limiter": (C.c_int, [_H, C.c_int]),
+    "om_set_odt_boundary_barycenters": (C.c_int, [_H, C.c_int]),
     "om_set_surface": (C.c_int, [_H, C.c_int, C.c_double, _P(C.c_double), C.c_int]),
     "om_set_solver": (C.c_int, [_H, C.c_double, C.c_int]),
     "om_flip_until_delaunay": (C.c_int, [_H, C.c_double, C.c_int, _P(C.c_int64), _P(C.c_int32),

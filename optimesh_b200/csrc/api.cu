@@ -278,7 +278,7 @@ int create_common(om_handle** out, int device, void* stream, int64_t N, int dim,
     om_set_error("cells itemsize must be 4 or 8, got %d", itemsize);
     return OM_ERR_ARG;
   }
-  if (N < 0 || C < 0 || N >= (1ll << 31) - 1 || C >= (1ll << 29)) {
+  if (N < 0 || C < 0 || N >= (1ll << 29) || C >= (1ll << 29)) {
     om_set_error("mesh size out of range (N=%lld, C=%lld)", (long long)N, (long long)C);
     return OM_ERR_ARG;
   }
@@ -442,7 +442,7 @@ int om_destroy(om_handle* h) {
 
 int om_set_method(om_handle* h, int method, double omega) {
   OM_ENTER(h);
-  if (method < OM_LLOYD || method > OM_CPT_LINEAR_SOLVE) {
+  if (method < OM_LLOYD || method > OM_ODT_DP_FP) {
     om_set_error("unknown method id %d", method);
     return OM_ERR_ARG;
   }
@@ -454,6 +454,12 @@ int om_set_method(om_handle* h, int method, double omega) {
 int om_set_limiter(om_handle* h, int on) {
   OM_ENTER(h);
   h->limiter = on ? 1 : 0;
+  return OM_OK;
+}
+
+int om_set_odt_boundary_barycenters(om_handle* h, int on) {
+  OM_ENTER(h);
+  h->odt_bary = on ? 1 : 0;
   return OM_OK;
 }
 

@@ -130,6 +130,7 @@ struct om_handle {
   int* band = nullptr;         // N: own vertices other ranks may need (internal ids)
   uint8_t* band_mark = nullptr;  // N: hop distance to a foreign vertex (0: far)
   int64_t pass_work_bound = 0; // upper bound of the work list length in a round-wise pass
+  int odt_bary = 1;            // ODT: barycenters for cells with a boundary edge
   int flip_spec = 0;           // flip rounds to enqueue before the first readback (flip.cu)
   double limited_frac = 1.0;  // share of vertices limited in the previous step
   // optional event timing (om_set_timing)

@@ -74,9 +74,12 @@ __device__ __forceinline__ double inradius(const CellGeo<D>& g) {
 // Only the two edges at the vertex are formed (e1 = P0 - P2, e2 = P1 - P0); since
 // e0 + e1 + e2 = 0 every other product follows from ee1, ee2 and ed0 = e1.e2:
 //   ed1 = -(ed0 + ee2), ed2 = -(ed0 + ee1), ee0 = ee1 + ee2 + 2 ed0, A^2 = (ee1 ee2 - ed0^2)/4.
+// bary: ODT methods only -- the cell has a boundary edge and contributes its barycenter
+// instead of its circumcenter (which may lie outside the domain there).
 template <int D, int METHOD, bool EXACT>
 __device__ __forceinline__ void accumulate_cell(const Vec<D>& P0, const Vec<D>& P1,
-                                                const Vec<D>& P2, Acc<D>& a, int& err) {
+                                                const Vec<D>& P2, Acc<D>& a, int& err,
+                                                bool bary) {
   const Vec<D> e1 = vsub<D>(P0, P2), e2 = vsub<D>(P1, P0);
   const double ee1 = vdot<D>(e1, e1), ee2 = vdot<D>(e2, e2), ed0 = vdot<D>(e1, e2);
   const double vol2 = 0.25 * fma(ee1, ee2, -ed0 * ed0);
@@ -102,11 +105,15 @@ __device__ __forceinline__ void accumulate_cell(const Vec<D>& P0, const Vec<D>& 
     for (int k = 0; k < D; k++) a.num.v[k] += A * (e2.v[k] - e1.v[k]);
     return;
   }
-  if (METHOD == OM_ODT_FIXED_POINT) {
-    // 3 A (circumcenter - P0) = 3 A (al1 e2 - al2 e1), al_k = ee_k ed_k / (-8 A^2), A = vol2 r
-    a.w += vol2 * r;
-    const double f = -0.375 * r;
-    const double s2 = ee1 * ed1 * f, s1 = ee2 * ed2 * f;
+  if (METHOD == OM_ODT_FIXED_POINT || METHOD == OM_ODT_DP_FP) {
+    // volume averaged: weight A = vol2 r; count averaged (density preserving): weight 1
+    // 3 (circumcenter - P0) = 3 (al1 e2 - al2 e1), al_k = ee_k ed_k / (-8 A^2)
+    const bool dp = METHOD == OM_ODT_DP_FP;
+    const double A = vol2 * r;
+    a.w += dp ? 1.0 : A;
+    const double f = -0.375 * r * (dp ? r : 1.0);
+    const double wb = dp ? 1.0 : A;  // barycenter: 3 (b - P0) = e2 - e1
+    const double s2 = bary ? wb : ee1 * ed1 * f, s1 = bary ? wb : ee2 * ed2 * f;
 #pragma unroll
     for (int k = 0; k < D; k++) a.num.v[k] += s2 * e2.v[k] - s1 * e1.v[k];
     return;
@@ -192,6 +199,7 @@ struct StepParams {
   int lo, hi;  // vertices [lo, hi) are processed
   double omega;
   int limiter;
+  int odt_bary;  // ODT: cells with a boundary edge contribute their barycenter
   DevScalars* ds;
 };
 
@@ -231,12 +239,19 @@ constexpr int MAX_RING = 4096;
 // leaving through local edge (j+1)%3; an open fan (boundary vertex) is completed from the
 // start cell in the other direction.  f(P1, P2) receives the other two vertices of each
 // cell in slot order.  The visiting order depends only on the mesh, never on scheduling.
-template <int D, typename F>
+// BC: f also receives "this cell has a boundary edge" (read from the cell's twin row).
+template <int D, bool BC = false, typename F>
 __device__ __forceinline__ void walk_star(const StepParams& p, int v, int c0, const int4& cell0,
                                           int j, int& err, F&& f) {
+  auto has_boundary_edge = [&](int c) {
+    if (!BC) return false;
+    const int4 ta = __ldg(reinterpret_cast<const int4*>(p.adj) + c);
+    return ta.x < 0 || ta.y < 0 || ta.z < 0;
+  };
   if (!(p.valid(cell_get(cell0, (j + 1) % 3)) && p.valid(cell_get(cell0, (j + 2) % 3))))
     p.ds->stale = 1;
-  f(ld_point<D>(p.x, cell_get(cell0, (j + 1) % 3)), ld_point<D>(p.x, cell_get(cell0, (j + 2) % 3)));
+  f(ld_point<D>(p.x, cell_get(cell0, (j + 1) % 3)), ld_point<D>(p.x, cell_get(cell0, (j + 2) % 3)),
+    has_boundary_edge(c0));
   bool closed = false;
   for (int dir = 0; dir < 2 && !closed; dir++) {
     int cur = c0;
@@ -259,7 +274,8 @@ __device__ __forceinline__ void walk_star(const StepParams& p, int v, int c0, co
       }
       if (!(p.valid(cell_get(cl, (jn + 1) % 3)) && p.valid(cell_get(cl, (jn + 2) % 3))))
         p.ds->stale = 1;
-      f(ld_point<D>(p.x, cell_get(cl, (jn + 1) % 3)), ld_point<D>(p.x, cell_get(cl, (jn + 2) % 3)));
+      f(ld_point<D>(p.x, cell_get(cl, (jn + 1) % 3)), ld_point<D>(p.x, cell_get(cl, (jn + 2) % 3)),
+        has_boundary_edge(cn));
       cur = cn;
       kexit = 3 - jn - kn;
     }
@@ -280,8 +296,9 @@ template <int D>
 __host__ __device__ constexpr int step_block() {
   return D == 2 ? OM_K1_BLOCK : 128;
 }
-constexpr int RING_FLAG = 1 << 30;
-constexpr int RING_MASK = RING_FLAG - 1;
+constexpr int RING_FLAG = 1 << 30;   // cell q has slot order (v, n_{q+1}, n_q)
+constexpr int RING_BCELL = 1 << 29;  // cell q has a boundary edge (ODT uses its barycenter)
+constexpr int RING_MASK = RING_BCELL - 1;
 
 template <bool LIST>
 __global__ void __launch_bounds__(256)
@@ -307,8 +324,15 @@ __global__ void __launch_bounds__(256)
       int cur = c0, kexit = (j + 1) % 3;
       ok = true;
       while (true) {
+        // twin row of cell k (`cur`): the exit edge, and whether the cell has a boundary edge
+        const int4 ta = __ldg(reinterpret_cast<const int4*>(adj) + cur);
+        if (ta.x < 0 || ta.y < 0 || ta.z < 0) {
+#pragma unroll
+          for (int q = 0; q < OM_RING_W; q++)
+            if (q == k) e[q] |= RING_BCELL;
+        }
         k++;
-        const int t = __ldg(adj + 4 * (size_t)cur + kexit);
+        const int t = cell_get(ta, kexit);
         if (t < 0) {  // open fan
           ok = false;
           break;
@@ -387,6 +411,8 @@ __global__ void __launch_bounds__(step_block<D>(), (D == 2 ? OM_K1_MINB : 3))
     __shared__ double2 ring_sm[SRC == 0 ? OM_RING_W * (D == 2 ? 1 : 2) * step_block<D>() : 1];
     int nring = 0;         // cells (= ring vertices) in the row
     unsigned rflags = 0u;  // bit q: cell q has slot order (v, n_{q+1}, n_q)
+    unsigned bcells = 0u;  // bit q: cell q has a boundary edge (ODT methods only)
+    constexpr bool ODT = METHOD == OM_ODT_FIXED_POINT || METHOD == OM_ODT_DP_FP;
     int4 cell = make_int4(0, 0, 0, 0);
     int j = 0;
     if (walk) {
@@ -420,6 +446,7 @@ __global__ void __launch_bounds__(step_block<D>(), (D == 2 ? OM_K1_MINB : 3))
               }
               nring = q + 1;
               rflags |= (e[q] & RING_FLAG) ? (1u << q) : 0u;
+              if (ODT) bcells |= (e[q] & RING_BCELL) ? (1u << q) : 0u;
             }
           asm volatile("cp.async.commit_group;");
           asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -468,16 +495,17 @@ __global__ void __launch_bounds__(step_block<D>(), (D == 2 ? OM_K1_MINB : 3))
               X1.v[k] = sw ? B.v[k] : A.v[k];
               X2.v[k] = sw ? A.v[k] : B.v[k];
             }
-            f(X1, X2);
+            f(X1, X2, ODT && ((bcells >> q) & 1u));
             A = B;
           }
         } else {
-          walk_star<D>(p, v, c0, cell, j, err, f);
+          walk_star<D, ODT>(p, v, c0, cell, j, err, f);
         }
       };
 
-      for_each_cell([&](const Vec<D>& P1, const Vec<D>& P2) {
-        accumulate_cell<D, METHOD, EXACT>(P0, P1, P2, acc, err);
+      const bool odt_bary = ODT && p.odt_bary != 0;
+      for_each_cell([&](const Vec<D>& P1, const Vec<D>& P2, bool bcell) {
+        accumulate_cell<D, METHOD, EXACT>(P0, P1, P2, acc, err, odt_bary && bcell);
       });
       // method formula -> offset of the target from the vertex.  The reference divides by
       // the control volume whatever its sign; only 0/0 (every adjacent cell masked) leaves
@@ -561,6 +589,9 @@ int launch_step(om_handle* h, const StepParams& p) {
     case OM_ODT_FIXED_POINT:
       OM_LAUNCH(h, (k_step<D, OM_ODT_FIXED_POINT, MODE, SRC>), G, B, p);
       break;
+    case OM_ODT_DP_FP:
+      OM_LAUNCH(h, (k_step<D, OM_ODT_DP_FP, MODE, SRC>), G, B, p);
+      break;
     default:
       om_set_error("method %d has no fixed-point kernel", h->method);
       return OM_ERR_ARG;
@@ -607,7 +638,7 @@ __global__ void __launch_bounds__(256) k_relax_from_target(StepParams p, const d
         if (j < 0) {
           err |= OM_DEV_WALK;
         } else {
-          walk_star<D>(p, v, c0, cell, j, err, [&](const Vec<D>& P1, const Vec<D>& P2) {
+          walk_star<D>(p, v, c0, cell, j, err, [&](const Vec<D>& P1, const Vec<D>& P2, bool) {
             const CellGeo<D> g = cell_geo<D>(P0, P1, P2);
             if (g.vol2 > 0.0)
               rmin = fmin(rmin, inradius<D>(g));
@@ -698,6 +729,7 @@ StepParams make_params(om_handle* h, double* out) {
   p.hi = (int)h->N;
   p.omega = h->omega;
   p.limiter = h->limiter;
+  p.odt_bary = h->odt_bary;
   p.ds = h->ds;
   return p;
 }

@@ -39,12 +39,13 @@ def _project_host(dm: DeviceMesh, surface, tol: float, max_iter: int = 100):
 def _run_loop(dm: DeviceMesh, method: str, tol: float, max_num_steps: int, omega: float = 1.0,
               verbose: bool = False, callback=None, step_filename_format=None,
               implicit_surface=None, implicit_surface_tol: float = 1.0e-10, boundary_step=None,
-              cells_dtype=None, log=None):
+              cells_dtype=None, log=None, odt_boundary_barycenters: bool = True):
     if boundary_step is not None:
         raise NotImplementedError("boundary_step callbacks are outside this build")
     if max_num_steps < 1:
         raise ValueError("max_num_steps must be >= 1")
     dm.set_method(method, omega)
+    dm.set_odt_boundary_barycenters(odt_boundary_barycenters)
     host_surface = None
     if implicit_surface is None:
         dm.clear_surface()
@@ -103,13 +104,19 @@ def optimize_points_cells(points, cells, method: str, tol: float, max_num_steps:
                           omega: float = 1.0, verbose: bool = False, callback=None,
                           step_filename_format=None, implicit_surface=None,
                           implicit_surface_tol: float = 1.0e-10, boundary_step=None,
-                          method_name=None, device: int = 0, log=None):
-    """Returns ``(points, cells)``; the inputs are not modified (README.md:124-126)."""
+                          method_name=None, device: int = 0, log=None,
+                          odt_boundary_barycenters: bool = True):
+    """Returns ``(points, cells)``; the inputs are not modified (README.md:124-126).
+
+    ``device``, ``log`` (per-step statistics are appended to the list) and
+    ``odt_boundary_barycenters`` (see ``DeviceMesh.set_odt_boundary_barycenters``) are
+    additions of this build."""
     method_id(method)  # validate before touching the device
     cells = np.asarray(cells)
     with DeviceMesh(points, cells, device=device) as dm:
         _run_loop(dm, method, tol, max_num_steps, omega, verbose, callback, step_filename_format,
-                  implicit_surface, implicit_surface_tol, boundary_step, cells.dtype, log)
+                  implicit_surface, implicit_surface_tol, boundary_step, cells.dtype, log,
+                  odt_boundary_barycenters)
         return dm.points, dm.cells(cells.dtype)
 
 
@@ -123,11 +130,13 @@ def optimize(mesh, method: str, tol: float, max_num_steps: int, **kwargs):
     return mesh
 
 
-def get_new_points(mesh, method: str, device: int = 0) -> np.ndarray:
+def get_new_points(mesh, method: str, device: int = 0,
+                   odt_boundary_barycenters: bool = True) -> np.ndarray:
     """One un-relaxed update, ``(N, d)`` array (README.md:141)."""
     method_id(method)
     with DeviceMesh(mesh.points, _mesh_cells(mesh), device=device) as dm:
         dm.set_method(method, 1.0)
+        dm.set_odt_boundary_barycenters(odt_boundary_barycenters)
         return dm.new_points()
 
 

@@ -21,9 +21,10 @@ METHOD_IDS = {
     "cpt-fixed-point": _lib.OM_CPT_FIXED_POINT,
     "odt-fixed-point": _lib.OM_ODT_FIXED_POINT,
     "cpt-linear-solve": _lib.OM_CPT_LINEAR_SOLVE,
+    "odt-dp-fp": _lib.OM_ODT_DP_FP,
 }
 # names the reference knows (README.md:80, :90, :104, :194) that are outside this build
-NOT_IMPLEMENTED = ("cvt-full", "cvt-uniform-qnf", "cpt-quasi-newton", "odt-dp-fp", "odt-bfgs")
+NOT_IMPLEMENTED = ("cvt-full", "cvt-uniform-qnf", "cpt-quasi-newton", "odt-bfgs")
 
 
 def normalize_method_name(name: str) -> str:
@@ -112,6 +113,11 @@ class DeviceMesh:
 
     def set_limiter(self, on: bool):
         check(self._lib.om_set_limiter(self._h, int(bool(on))))
+
+    def set_odt_boundary_barycenters(self, on: bool):
+        """ODT methods: cells with a boundary edge contribute their barycenter (default) or,
+        if off, their circumcenter like every other cell."""
+        check(self._lib.om_set_odt_boundary_barycenters(self._h, int(bool(on))))
 
     def set_sphere(self, center=(0.0, 0.0, 0.0), radius=1.0, tol=1.0e-10, max_sweeps=100):
         params = (C.c_double * 4)(center[0], center[1], center[2], radius)

@@ -230,6 +230,11 @@ class MeshTri:
         return flag
 
     @property
+    def is_boundary_cell(self):
+        """Cells with at least one boundary edge (meshplex: ``is_boundary_cell``)."""
+        return np.any(self.twins.reshape(-1, 3) < 0, axis=1)
+
+    @property
     def is_interior_point(self):
         # vertices that belong to at least one cell and are not on the boundary
         used = np.zeros(self.n, dtype=bool)

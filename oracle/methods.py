@@ -18,9 +18,15 @@ NOT_IMPLEMENTED = (
     "cvt-full",
     "cvt-uniform-qnf",
     "cpt-quasi-newton",
-    "odt-dp-fp",
     "odt-bfgs",
 )
+
+# ODT: cells with a boundary edge contribute their barycenter instead of their circumcenter
+# (the circumcenter of such a cell may lie outside the domain).  This is how the upstream
+# package's ODT fixed-point update treats them as far as it could be recollected; SURVEY.md
+# A.8 as written uses circumcenters everywhere -- set False for that variant.  The GPU library
+# has the same switch (om_set_odt_boundary_barycenters) and the tests cover both settings.
+ODT_BOUNDARY_BARYCENTERS = True
 
 
 def normalize_method_name(name: str) -> str:
@@ -56,8 +62,35 @@ def cpt_fixed_point(mesh: MeshTri) -> np.ndarray:
     return _volume_averaged(mesh, mesh.cell_barycenters)
 
 
+def _count_averaged(mesh: MeshTri, reference_points: np.ndarray) -> np.ndarray:
+    """Density-preserving variant: density ~ 1/|c| makes every adjacent cell count the same,
+    x_i = mean_c r_c over adjacent cells; boundary pinned."""
+    num = np.zeros(mesh.points.shape)
+    den = np.zeros(mesh.n)
+    for i in mesh.cells("points").T:
+        np.add.at(num, i, reference_points)
+        np.add.at(den, i, 1.0)
+    idx = mesh.is_interior_point
+    new = mesh.points.copy()
+    new[idx] = num[idx] / den[idx][:, None]
+    return new
+
+
+def _odt_reference_points(mesh: MeshTri) -> np.ndarray:
+    ref = mesh.cell_circumcenters.copy()
+    if ODT_BOUNDARY_BARYCENTERS:
+        bc = mesh.is_boundary_cell
+        ref[bc] = mesh.cell_barycenters[bc]
+    return ref
+
+
 def odt_fixed_point(mesh: MeshTri) -> np.ndarray:
-    return _volume_averaged(mesh, mesh.cell_circumcenters)
+    return _volume_averaged(mesh, _odt_reference_points(mesh))
+
+
+def odt_dp_fp(mesh: MeshTri) -> np.ndarray:
+    """README.md:104: density-preserving ODT fixed-point iteration (count averaged)."""
+    return _count_averaged(mesh, _odt_reference_points(mesh))
 
 
 def cvt_block_diagonal(mesh: MeshTri) -> np.ndarray:
@@ -122,6 +155,7 @@ METHODS = {
     "cpt-fixed-point": cpt_fixed_point,
     "cpt-linear-solve": cpt_linear_solve,
     "odt-fixed-point": odt_fixed_point,
+    "odt-dp-fp": odt_dp_fp,
 }
 
 

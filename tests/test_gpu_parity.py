@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 STEP_TOL = 1.0e-10  # relative to max |x|, per step
-METHODS = ["lloyd", "cvt-block-diagonal", "cpt-fixed-point", "odt-fixed-point"]
+METHODS = ["lloyd", "cvt-block-diagonal", "cpt-fixed-point", "odt-fixed-point", "odt-dp-fp"]
 
 
 @pytest.fixture(scope="module")
@@ -99,6 +99,40 @@ def test_get_new_points_matches_oracle(ob, G, name, method, renumber):
         got = dm.new_points()
     tol = 1e-9 if method == "cpt-linear-solve" else STEP_TOL
     assert rel_err(got, ref) <= tol
+
+
+@pytest.mark.parametrize("name", ["disk40", "disk120", "square"])
+@pytest.mark.parametrize("method", ["odt-fixed-point", "odt-dp-fp"])
+def test_odt_circumcenters_everywhere_option(ob, G, name, method, monkeypatch):
+    """SURVEY.md A.8 as written: no barycenter substitution in cells with a boundary edge.
+    The default (substitution on) is covered by every other ODT test."""
+    import oracle.methods as om
+
+    pts, cells = _meshes(G)[name]
+    default = oracle.get_new_points(OMesh(pts, cells), method)
+    monkeypatch.setattr(om, "ODT_BOUNDARY_BARYCENTERS", False)
+    ref = oracle.get_new_points(OMesh(pts, cells), method)
+    assert rel_err(default, ref) > 1e-6  # the two variants really differ on these meshes
+    with ob.DeviceMesh(pts, cells) as dm:
+        dm.set_method(method)
+        dm.set_odt_boundary_barycenters(False)
+        got = dm.new_points()
+        dm.set_odt_boundary_barycenters(True)
+        got_default = dm.new_points()
+    assert rel_err(got, ref) <= STEP_TOL
+    assert rel_err(got_default, default) <= STEP_TOL
+    got2 = ob.get_new_points(ob.MeshTri(pts, cells), method, odt_boundary_barycenters=False)
+    assert np.array_equal(got2, got)
+
+
+def test_odt_boundary_cells_after_flips(ob, G):
+    """Flips change which cells carry a boundary edge: the ring rows must follow."""
+    pts, cells = G.disk(60, 4)
+    for method in ("odt-fixed-point", "odt-dp-fp"):
+        rp, rc = oracle.optimize_points_cells(pts, cells, method, 0.0, 12, omega=1.5)
+        p, c = ob.optimize_points_cells(pts, cells, method, 0.0, 12, omega=1.5)
+        assert np.array_equal(canonical_cells(c), canonical_cells(rc))
+        assert rel_err(p, rp) <= 1e-8
 
 
 def test_get_new_points_matches_golden_fixture(ob, G):

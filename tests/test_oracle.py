@@ -102,6 +102,41 @@ def test_hex_patch_is_fixed_point():
         assert np.allclose(new[0], 0.0, atol=1e-14), meth
 
 
+def test_odt_boundary_cells_use_barycenters(monkeypatch):
+    """Cells with a boundary edge contribute their barycenter to the ODT updates."""
+    import oracle.methods as om
+
+    pts, cells = G.disk(40, 3)
+    mesh = MeshTri(pts, cells)
+    bc = mesh.is_boundary_cell
+    # a cell is a boundary cell iff one of its edges has no twin
+    assert bc.sum() == (mesh.twins < 0).sum() == 40
+    ref = mesh.cell_circumcenters.copy()
+    ref[bc] = mesh.cell_barycenters[bc]
+    assert np.array_equal(om.odt_fixed_point(mesh), om._volume_averaged(mesh, ref))
+    assert np.array_equal(om.odt_dp_fp(mesh), om._count_averaged(mesh, ref))
+    with_sub = om.odt_fixed_point(mesh)
+    monkeypatch.setattr(om, "ODT_BOUNDARY_BARYCENTERS", False)
+    plain = om.odt_fixed_point(mesh)
+    assert np.array_equal(plain, om._volume_averaged(mesh, mesh.cell_circumcenters))
+    # only vertices of boundary cells are affected
+    touched = np.zeros(mesh.n, dtype=bool)
+    touched[cells[bc].reshape(-1)] = True
+    assert np.array_equal(with_sub[~touched], plain[~touched])
+    assert not np.allclose(with_sub[touched & mesh.is_interior_point],
+                           plain[touched & mesh.is_interior_point])
+
+
+def test_odt_dp_fp_simple1():
+    # every cell of simple1 is a boundary cell: the interior vertex moves to
+    # x/3 + 2/3 (0.5, 0.5) per step (mean of the four barycenters)
+    X, cells = G.SIMPLE1
+    new = oracle.get_new_points(MeshTri(X, cells), "odt-dp-fp")
+    assert np.allclose(new[4], X[4] / 3 + np.array([1.0, 1.0]) / 3, atol=1e-15)
+    p, _ = oracle.optimize_points_cells(X, cells, "odt-dp-fp", 1.0e-6, 100)
+    assert np.allclose(p[4], [0.5, 0.5], atol=1e-6)
+
+
 def test_degenerate_cell_raises():
     pts = np.array([[0.0, 0.0], [1.0, 0.0], [2.0, 0.0]])
     with pytest.raises(DegenerateCellsError):
