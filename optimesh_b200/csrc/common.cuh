@@ -131,6 +131,10 @@ struct om_handle {
   uint8_t* band_mark = nullptr;  // N: hop distance to a foreign vertex (0: far)
   int64_t pass_work_bound = 0; // upper bound of the work list length in a round-wise pass
   int odt_bary = 1;            // ODT: barycenters for cells with a boundary edge
+  // round-wise (partitioned) flip pass: only own vertices are enlisted for the ring rebuild and
+  // only cells of the own range for the next check (every rank applies all flips, but each
+  // examines and rebuilds only its part).  Full ranges outside such a pass.
+  int flt_vlo = 0, flt_vhi = 0x7fffffff, flt_clo = 0, flt_chi = 0x7fffffff;
   int flip_spec = 0;           // flip rounds to enqueue before the first readback (flip.cu)
   double limited_frac = 1.0;  // share of vertices limited in the previous step
   // optional event timing (om_set_timing)

@@ -22,6 +22,8 @@
 // products are explicit fma chains: both cells of an edge see bit-identical s.
 #include <algorithm>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "geom.cuh"
 
@@ -83,15 +85,19 @@ struct ShardInfo {
 
 // MODE 3: like MODE 2 (records) but over the work list, restricted to cells in [clo, chi).
 template <int D, int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (D == 2 ? 5 : 4))  // 2D: <= 51 registers, 5 blocks per SM
     k_suspect(const double* __restrict__ x, const int4* __restrict__ cells,
               const int* __restrict__ adj, int off, int n, const int* __restrict__ list,
               double tol, double* __restrict__ sarr, int* __restrict__ cand,
               int* __restrict__ cand_epoch, int epoch, FlipRec* __restrict__ recs,
               DevScalars* ds, const int* __restrict__ n_dev, ShardInfo sh) {
   if (n_dev) n = *n_dev;  // length known only on the device (chained rounds)
-  // block-stride loop: chained rounds run on a fixed grid whatever the list length is
-  for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+  // list modes: block-stride loop (chained rounds run on a fixed grid whatever the list length
+  // is); range modes: exactly one trip per block (the loop form cost the range check 0.1 ms)
+  constexpr bool LOOP = MODE == 1 || MODE == 3;
+  for (int base = blockIdx.x * blockDim.x;
+       LOOP ? base < n : base == (int)(blockIdx.x * blockDim.x);
+       base += gridDim.x * blockDim.x) {
   const int i = base + threadIdx.x;
   bool flag = false;
   int c = -1, cn = -1, he = -1, tt = -1;
@@ -189,6 +195,7 @@ __global__ void __launch_bounds__(256)
       r.s = sval;
       recs[r_base + r_warp[warp] + __popc(m & ((1u << lane) - 1u))] = r;
     }
+    if (!LOOP) return;
     __syncthreads();  // r_warp / r_base are reused by the next trip
     continue;
   }
@@ -308,7 +315,7 @@ __global__ void __launch_bounds__(256)
             const int* __restrict__ cand, int n, int epoch, int* __restrict__ flip_epoch,
             int* __restrict__ reloc, int4* __restrict__ adj_tmp, int* __restrict__ v2c,
             int* __restrict__ dirty, int* __restrict__ dirty_epoch, int dirty_pass,
-            DevScalars* ds, const int* __restrict__ n_dev) {
+            DevScalars* ds, const int* __restrict__ n_dev, int vlo, int vhi) {
   if (ds->abort) return;
   if (n_dev) n = *n_dev;
   for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
@@ -366,7 +373,8 @@ __global__ void __launch_bounds__(256)
     bool dp[4];
 #pragma unroll
     for (int q = 0; q < 4; q++)
-      dp[q] = nf && atomicExch(&dirty_epoch[dv[q]], dirty_pass) != dirty_pass;
+      dp[q] = nf && dv[q] >= vlo && dv[q] < vhi &&
+              atomicExch(&dirty_epoch[dv[q]], dirty_pass) != dirty_pass;
     block_append<4>(&ds->n_dirty, dirty, dv, dp);
   }
   for (int o = 16; o > 0; o >>= 1) nf += __shfl_xor_sync(0xffffffffu, nf, o);
@@ -379,7 +387,7 @@ __global__ void __launch_bounds__(256)
             const int* __restrict__ flip_epoch, const int* __restrict__ reloc,
             const int* __restrict__ cand, int n, int epoch, int* __restrict__ work_epoch,
             int* __restrict__ work, int8_t* __restrict__ best, DevScalars* ds,
-            const int* __restrict__ n_dev) {
+            const int* __restrict__ n_dev, int clo, int chi) {
   if (ds->abort) return;
   if (n_dev) n = *n_dev;
   for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
@@ -414,7 +422,8 @@ __global__ void __launch_bounds__(256)
   bool preds[4];
 #pragma unroll
   for (int q = 0; q < 4; q++)
-    preds[q] = add[q] >= 0 && atomicExch(&work_epoch[add[q]], epoch) != epoch;
+    preds[q] = add[q] >= clo && add[q] < chi &&
+               atomicExch(&work_epoch[add[q]], epoch) != epoch;
   block_append<4>(&ds->n_work, work, add, preds);
   }
 }
@@ -459,9 +468,9 @@ int flip_rounds(om_handle* h, double tol, int max_rounds, int64_t* n_flips, int3
     OM_LAUNCH(h, k_select, G, B, h->sarr, h->cand, n_host, h->best, h->ds, n_dev);
     OM_LAUNCH(h, k_flip1, G, B, h->cells, h->adj, h->best, h->cand, n_host, h->epoch,
               h->flip_epoch, h->reloc, h->adj_tmp, h->v2c, h->dirty, h->dirty_epoch,
-              h->dirty_pass, h->ds, n_dev);
+              h->dirty_pass, h->ds, n_dev, h->flt_vlo, h->flt_vhi);
     OM_LAUNCH(h, k_flip2, G, B, (int*)h->adj, h->adj_tmp, h->flip_epoch, h->reloc, h->cand,
-              n_host, h->epoch, h->work_epoch, h->work, h->best, h->ds, n_dev);
+              n_host, h->epoch, h->work_epoch, h->work, h->best, h->ds, n_dev, h->flt_clo, h->flt_chi);
     h->nbr_valid = false;
   };
   int rounds = 0, cap = 0;
@@ -567,6 +576,14 @@ int om_flip_round_check_impl(om_handle* h, double tol, int first, int64_t clo, i
   OM_LAUNCH(h, k_reset_flip_scalars, 1, 1, h->ds, 0);
   h->epoch++;
   const ShardInfo sh = shard_info(h, clo, chi);
+  // every rank applies all flips of the round, but enlists only what it will look at itself
+  static const bool no_filter = getenv("OM_NO_LIST_FILTER") != nullptr;  // diagnostics
+  if (!no_filter) {
+    h->flt_vlo = sh.vlo;
+    h->flt_vhi = sh.vhi;
+    h->flt_clo = sh.clo;
+    h->flt_chi = sh.chi;
+  }
   if (first) {
     const int n = (int)(chi - clo);
     if (h->D == 2)
@@ -616,9 +633,9 @@ int om_flip_round_apply_gathered_impl(om_handle* h, const void* gathered, int P,
   OM_LAUNCH(h, k_select, om_grid(bound, B), B, h->sarr, h->cand, 0, h->best, h->ds, nd);
   OM_LAUNCH(h, k_flip1, om_grid(bound, B), B, h->cells, h->adj, h->best, h->cand, 0, h->epoch,
             h->flip_epoch, h->reloc, h->adj_tmp, h->v2c, h->dirty, h->dirty_epoch, h->dirty_pass,
-            h->ds, nd);
+            h->ds, nd, h->flt_vlo, h->flt_vhi);
   OM_LAUNCH(h, k_flip2, om_grid(bound, B), B, (int*)h->adj, h->adj_tmp, h->flip_epoch, h->reloc,
-            h->cand, 0, h->epoch, h->work_epoch, h->work, h->best, h->ds, nd);
+            h->cand, 0, h->epoch, h->work_epoch, h->work, h->best, h->ds, nd, h->flt_clo, h->flt_chi);
   h->nbr_valid = false;
   OM_TRY(om_fetch_scalars(h));
   OM_TRY(om_check_dev_err(h));
@@ -640,9 +657,9 @@ int om_flip_round_apply_impl(om_handle* h, int64_t total_records, int64_t* n_can
     OM_LAUNCH(h, k_select, om_grid(bound, B), B, h->sarr, h->cand, 0, h->best, h->ds, nd);
     OM_LAUNCH(h, k_flip1, om_grid(bound, B), B, h->cells, h->adj, h->best, h->cand, 0, h->epoch,
               h->flip_epoch, h->reloc, h->adj_tmp, h->v2c, h->dirty, h->dirty_epoch,
-              h->dirty_pass, h->ds, nd);
+              h->dirty_pass, h->ds, nd, h->flt_vlo, h->flt_vhi);
     OM_LAUNCH(h, k_flip2, om_grid(bound, B), B, (int*)h->adj, h->adj_tmp, h->flip_epoch, h->reloc,
-              h->cand, 0, h->epoch, h->work_epoch, h->work, h->best, h->ds, nd);
+              h->cand, 0, h->epoch, h->work_epoch, h->work, h->best, h->ds, nd, h->flt_clo, h->flt_chi);
     h->nbr_valid = false;
   }
   OM_TRY(om_fetch_scalars(h));
@@ -703,6 +720,9 @@ int om_flip_impl(om_handle* h, double tol, int max_rounds, int64_t* n_flips, int
   if (n_rounds) *n_rounds = 0;
   if (cap_hit) *cap_hit = 0;
   if (h->C == 0) return OM_OK;
+  // whole-mesh pass: every list covers the whole mesh
+  h->flt_vlo = h->flt_clo = 0;
+  h->flt_vhi = h->flt_chi = 0x7fffffff;
   if (!first_round_given) {
     h->dirty_pass++;
     CUDA_TRY(cudaMemsetAsync(&h->ds->n_dirty, 0, sizeof(int), h->stream));
