@@ -344,12 +344,15 @@ def run_b200(args):
     dm.close()  # its device memory returns to the pool before the end-to-end calls
     if rank == 0 and world == 1 and not args.no_e2e:
         # end to end through the public API with HOST buffers: upload, setup, K steps,
-        # download -- all inside the timed region.  Three calls, the median is reported
-        # (a call that has to grow the driver's memory pool is several times slower).
+        # download -- all inside the timed region.  Five calls, the median is reported
+        # (a call that has to grow the driver's memory pool is several times slower, and
+        # host-side page faulting of the fresh 637 MB result arrays jitters).
         e2e_steps = args.steps
         cells64 = cells  # int64, as numpy produces it
         times = []
-        for _ in range(3):
+        p_out = c_out = None
+        for _ in range(5):
+            del p_out, c_out
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             p_out, c_out = ob.optimize_points_cells(pts, cells64, method, 0.0, e2e_steps,

@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstring>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -103,12 +104,43 @@ void parallel_chunks(size_t n, F f) {  // f(begin, end) on STAGE_THREADS host th
   for (auto& x : th) x.join();
 }
 
-// device (elements of DEV_T) -> user memory (elements of HOST_T)
-// the handle keeps its staging buffers (pinned allocation costs about a millisecond each)
+// Staging buffers are kept for the lifetime of the process and handed from handle to handle
+// (pinning and unpinning 2 x 16 MB costs several milliseconds per optimize_points_cells call
+// otherwise).  Entries left in the cache at exit are deliberately not freed: the CUDA context
+// may already be gone by then.
+std::mutex g_stage_mutex;
+std::vector<std::pair<int, Stage*>> g_stage_cache;  // (device, buffers)
+
 Stage& stage_of(om_handle* h) {
+  if (!h->stage) {
+    std::lock_guard<std::mutex> lock(g_stage_mutex);
+    for (size_t i = 0; i < g_stage_cache.size(); i++)
+      if (g_stage_cache[i].first == h->device) {
+        h->stage = g_stage_cache[i].second;
+        g_stage_cache.erase(g_stage_cache.begin() + i);
+        break;
+      }
+  }
   if (!h->stage) h->stage = new Stage();
   return *(Stage*)h->stage;
 }
+
+void stage_release(om_handle* h) {
+  Stage* st = (Stage*)h->stage;
+  h->stage = nullptr;
+  if (!st) return;
+  if (!st->ok) {
+    delete st;
+    return;
+  }
+  std::lock_guard<std::mutex> lock(g_stage_mutex);
+  if (g_stage_cache.size() < 4)
+    g_stage_cache.emplace_back(h->device, st);
+  else
+    delete st;
+}
+
+// device (elements of DEV_T) -> user memory (elements of HOST_T)
 
 template <typename DEV_T, typename HOST_T>
 int staged_d2h(om_handle* h, const DEV_T* src_dev, HOST_T* dst_host, size_t n) {
@@ -434,7 +466,7 @@ int om_destroy(om_handle* h) {
   if (h->hs) cudaFreeHost(h->hs);
   for (int i = 0; i < 4; i++)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
-  delete (Stage*)h->stage;
+  stage_release(h);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return OM_OK;
@@ -888,6 +920,17 @@ int om_release_cached_memory(int device) {
   CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
   CUDA_TRY(cudaDeviceSynchronize());
   CUDA_TRY(cudaMemPoolTrimTo(pool, 0));
+  {  // the cached pinned staging buffers of that device too
+    std::lock_guard<std::mutex> lock(g_stage_mutex);
+    for (size_t i = 0; i < g_stage_cache.size();) {
+      if (g_stage_cache[i].first == device) {
+        delete g_stage_cache[i].second;
+        g_stage_cache.erase(g_stage_cache.begin() + i);
+      } else {
+        i++;
+      }
+    }
+  }
   return OM_OK;
 }
 
