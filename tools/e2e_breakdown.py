@@ -6,7 +6,7 @@ from optimesh_b200 import generators as G
 pts, cells = G.disk_mapped_grid(3154, 0.25, 0)
 def T(label, f):
     t=time.perf_counter(); r=f(); dt=time.perf_counter()-t; print(f"{label:28s} {dt*1e3:8.1f} ms", flush=True); return r
-for rep in range(4):
+for rep in range(3):
     print("--- rep", rep)
     t0=time.perf_counter()
     dm = T("DeviceMesh (H2D+setup)", lambda: ob.DeviceMesh(pts, cells))
