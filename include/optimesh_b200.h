@@ -36,7 +36,8 @@ enum {
   OM_CPT_FIXED_POINT = 2,    /* --method cpt-fixed-point       README.md:90  */
   OM_ODT_FIXED_POINT = 3,    /* --method odt-fixed-point       README.md:104 */
   OM_CPT_LINEAR_SOLVE = 4,   /* --method cpt-linear-solve      README.md:90  */
-  OM_ODT_DP_FP = 5           /* --method odt-dp-fp             README.md:104 */
+  OM_ODT_DP_FP = 5,          /* --method odt-dp-fp             README.md:104 */
+  OM_CPT_QUASI_NEWTON = 6    /* --method cpt-quasi-newton      README.md:90  */
 };
 
 /* error codes */

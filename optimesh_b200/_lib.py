@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(HERE, "liboptimesh_b200.so")
 
 OM_RENUMBER = 1
 (OM_LLOYD, OM_CVT_BLOCK_DIAGONAL, OM_CPT_FIXED_POINT, OM_ODT_FIXED_POINT,
- OM_CPT_LINEAR_SOLVE, OM_ODT_DP_FP) = range(6)
+ OM_CPT_LINEAR_SOLVE, OM_ODT_DP_FP, OM_CPT_QUASI_NEWTON) = range(7)
 (OM_OK, OM_ERR_CUDA, OM_ERR_ARG, OM_ERR_DEGENERATE, OM_ERR_NONMANIFOLD, OM_ERR_INDEX,
  OM_ERR_NOT_CONVERGED) = range(7)
 

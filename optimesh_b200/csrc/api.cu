@@ -486,7 +486,7 @@ int om_destroy(om_handle* h) {
 
 int om_set_method(om_handle* h, int method, double omega) {
   OM_ENTER(h);
-  if (method < OM_LLOYD || method > OM_ODT_DP_FP) {
+  if (method < OM_LLOYD || method > OM_CPT_QUASI_NEWTON) {
     om_set_error("unknown method id %d", method);
     return OM_ERR_ARG;
   }
@@ -553,7 +553,7 @@ int om_step(om_handle* h, double tol, om_step_stats* out) {
   om_step_stats st;
   memset(&st, 0, sizeof(st));
   // the statistics of the point update ride on the first readback of the flip pass
-  const bool defer = h->surf_kind == 0 && h->C > 0 && h->method != OM_CPT_LINEAR_SOLVE;
+  const bool defer = h->surf_kind == 0 && h->C > 0 && !om_is_solve_method(h->method);
   OM_TRY(om_update_points_impl(h, tol, &st, false, nullptr, defer));
   OM_TRY(om_project_impl(h, &st.surface_sweeps));
   OM_TRY(om_flip_impl(h, 0.0, 100, &st.n_flips, &st.n_flip_rounds, &st.flip_cap_hit));

@@ -204,5 +204,11 @@ int om_rebuild_rings(om_handle* h, bool all);
 // pcg.cu
 int om_pcg_impl(om_handle* h, double rtol, int max_iter, int32_t* iters, double* relres,
                 double* out /* N*PD, may alias h->xnew */);
+int om_quasi_newton_impl(om_handle* h, double rtol, int max_iter, int32_t* iters, double* relres,
+                         double* out);
+// methods whose target comes from a linear solve instead of the fused step kernel
+inline bool om_is_solve_method(int m) {
+  return m == OM_CPT_LINEAR_SOLVE || m == OM_CPT_QUASI_NEWTON;
+}
 // stats.cu
 int om_stats_impl(om_handle* h, int64_t* angle_hist72, int64_t* q_hist40, double* summary8);

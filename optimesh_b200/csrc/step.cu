@@ -744,7 +744,7 @@ double bits_to_double(unsigned long long b) {
 
 // Fills the step statistics from the scalars of the last readback.
 void om_step_stats_from_scalars(om_handle* h, double tol, om_step_stats* out) {
-  if (h->timing && h->method != OM_CPT_LINEAR_SOLVE && h->ev_pending) {
+  if (h->timing && !om_is_solve_method(h->method) && h->ev_pending) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]) == cudaSuccess) {
       h->t_step_ms += ms;
@@ -767,10 +767,13 @@ int om_update_points_impl(om_handle* h, double tol, om_step_stats* out, bool tar
   if (h->N == 0) return OM_OK;
   OM_LAUNCH(h, k_reset_step_scalars, 1, 1, h->ds);
   int32_t iters = 0;
-  if (h->method == OM_CPT_LINEAR_SOLVE) {
+  if (om_is_solve_method(h->method)) {
     double relres = 0.0;
     double* sol = target_only ? target_out : h->xnew;
-    OM_TRY(om_pcg_impl(h, h->solver_rtol, h->solver_max_iter, &iters, &relres, sol));
+    if (h->method == OM_CPT_LINEAR_SOLVE)
+      OM_TRY(om_pcg_impl(h, h->solver_rtol, h->solver_max_iter, &iters, &relres, sol));
+    else
+      OM_TRY(om_quasi_newton_impl(h, h->solver_rtol, h->solver_max_iter, &iters, &relres, sol));
     if (!target_only) {
       // relax + limit from the solved target; result must not alias the target
       double* tmp = nullptr;
@@ -816,7 +819,7 @@ int om_update_points_impl(om_handle* h, double tol, om_step_stats* out, bool tar
         OM_TRY(launch_step_mode<3>(h, p, mode, 2));
     }
   }
-  if (defer_fetch && !target_only && h->method != OM_CPT_LINEAR_SOLVE) {
+  if (defer_fetch && !target_only && !om_is_solve_method(h->method)) {
     // om_step reads the statistics back together with the first flip-round readback
     if (h->own_hi >= 0) {
       const size_t off = (size_t)h->own_lo * h->PD, cnt = (size_t)(h->own_hi - h->own_lo) * h->PD;
@@ -830,7 +833,7 @@ int om_update_points_impl(om_handle* h, double tol, om_step_stats* out, bool tar
   }
   OM_TRY(om_fetch_scalars(h));
   OM_TRY(om_check_dev_err(h));
-  if (!target_only && h->defer_commit && h->own_hi >= 0 && h->method != OM_CPT_LINEAR_SOLVE) {
+  if (!target_only && h->defer_commit && h->own_hi >= 0 && !om_is_solve_method(h->method)) {
     // partitioned run: the caller commits once every rank reports "no stale coordinate"
     om_step_stats_from_scalars(h, tol, out);
     if (out) {
@@ -840,7 +843,7 @@ int om_update_points_impl(om_handle* h, double tol, om_step_stats* out, bool tar
     return OM_OK;
   }
   if (!target_only) {
-    if (h->own_hi >= 0 && h->method != OM_CPT_LINEAR_SOLVE) {
+    if (h->own_hi >= 0 && !om_is_solve_method(h->method)) {
       // sharded step: only [lo, hi) was written; fold it back, the rest of x stays
       const size_t off = (size_t)h->own_lo * h->PD, cnt = (size_t)(h->own_hi - h->own_lo) * h->PD;
       if (cnt)

@@ -31,6 +31,13 @@ LAST_RUN = {}
 from .mesh import DeviceMesh
 
 
+def _is_solve_method(method: str) -> bool:
+    """Methods whose update is a global solve: every rank runs them on the whole mesh."""
+    from .mesh import normalize_method_name
+
+    return normalize_method_name(method) in ("cpt-linear-solve", "cpt-quasi-newton")
+
+
 def chunk_of(n: int, world: int) -> int:
     return (n + world - 1) // world if n > 0 else 0
 
@@ -450,7 +457,7 @@ def run_sharded(shard, method: str, tol: float, max_num_steps: int, omega: float
     n = shard.n
     chunk = chunk_of(n, world)
     lo, hi = owned_range(n, rank, world)
-    replicated = "linear-solve" in method.lower().replace(" ", "-") or world == 1
+    replicated = _is_solve_method(method) or world == 1
     shard.set_method(method, omega)
     shard.flip_until_delaunay()
     if not replicated:
@@ -511,7 +518,7 @@ def optimize_points_cells_sharded(points, cells, method: str, tol: float, max_nu
         import torch.distributed as dist
 
         partition = (exchange == "band" and implicit_surface is None
-                     and "linear-solve" not in method.lower().replace(" ", "-")
+                     and not _is_solve_method(method)
                      and dist.get_world_size(group) > 1)
         if partition:
             run_partitioned(dm, method, tol, max_num_steps, omega, group, log)

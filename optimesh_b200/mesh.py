@@ -22,9 +22,10 @@ METHOD_IDS = {
     "odt-fixed-point": _lib.OM_ODT_FIXED_POINT,
     "cpt-linear-solve": _lib.OM_CPT_LINEAR_SOLVE,
     "odt-dp-fp": _lib.OM_ODT_DP_FP,
+    "cpt-quasi-newton": _lib.OM_CPT_QUASI_NEWTON,
 }
 # names the reference knows (README.md:80, :90, :104, :194) that are outside this build
-NOT_IMPLEMENTED = ("cvt-full", "cvt-uniform-qnf", "cpt-quasi-newton", "odt-bfgs")
+NOT_IMPLEMENTED = ("cvt-full", "cvt-uniform-qnf", "odt-bfgs")
 
 
 def normalize_method_name(name: str) -> str:

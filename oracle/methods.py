@@ -17,7 +17,6 @@ from .meshtri import MeshTri
 NOT_IMPLEMENTED = (
     "cvt-full",
     "cvt-uniform-qnf",
-    "cpt-quasi-newton",
     "odt-bfgs",
 )
 
@@ -149,6 +148,46 @@ def cpt_linear_solve(mesh: MeshTri) -> np.ndarray:
     return np.asarray(out).reshape(mesh.points.shape)
 
 
+def cpt_quasi_newton(mesh: MeshTri) -> np.ndarray:
+    """README.md:90, :97-98: uniform-density CPT, one quasi-Newton step x - H^-1 dE.
+
+    Chen-Holst: dE_i = 2/(d+1) sum_{t in star(i)} |t| (x_i - b_t).  Differentiating with the
+    cell areas held fixed gives  d_ii E = 2/(d+1) |w_i| - 2/(d+1)^2 |w_i|  and
+    d_ij E = -2/(d+1)^2 (sum of the areas of the cells on edge ij); the approximate Hessian
+    drops the negative part of the diagonal (it hurts convergence), keeping
+    H_ii = 2/(d+1) |w_i|.  d = 2 also on surfaces.  Boundary rows: identity, right-hand side 0.
+    The same scalar matrix is solved for every coordinate."""
+    X = mesh.points
+    n = mesh.n
+    cells = mesh.cells("points")
+    vol = mesh.cell_volumes
+    dim = 2
+    jac = np.zeros(X.shape)
+    bary = mesh.cell_barycenters
+    for k in range(3):
+        np.add.at(jac, cells[:, k], (X[cells[:, k]] - bary) * vol[:, None])
+    jac *= 2.0 / (dim + 1)
+    rows, cols, vals = [], [], []
+    for k in range(3):
+        rows.append(cells[:, k])
+        cols.append(cells[:, k])
+        vals.append(2.0 / (dim + 1) * vol)
+        for kk in ((k + 1) % 3, (k + 2) % 3):
+            rows.append(cells[:, k])
+            cols.append(cells[:, kk])
+            vals.append(-2.0 / (dim + 1) ** 2 * vol)
+    H = scipy.sparse.coo_matrix(
+        (np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n, n)
+    ).tocsr()
+    fixed = ~mesh.is_interior_point  # boundary + orphan vertices
+    keep = scipy.sparse.diags((~fixed).astype(float))
+    H = (keep @ H + scipy.sparse.diags(fixed.astype(float))).tocsc()
+    rhs = jac.copy()
+    rhs[fixed] = 0.0
+    step = np.asarray(scipy.sparse.linalg.spsolve(H, rhs)).reshape(X.shape)
+    return X - step
+
+
 METHODS = {
     "lloyd": lloyd,
     "cvt-block-diagonal": cvt_block_diagonal,
@@ -156,6 +195,7 @@ METHODS = {
     "cpt-linear-solve": cpt_linear_solve,
     "odt-fixed-point": odt_fixed_point,
     "odt-dp-fp": odt_dp_fp,
+    "cpt-quasi-newton": cpt_quasi_newton,
 }
 
 

@@ -62,7 +62,8 @@ def test_method_names():
     assert method_id("Lloyd") == 0 and method_id("CVT (block-diagonal)") == 1
     assert method_id("cpt-fixed-point") == 2 and method_id("ODT (fixed-point)") == 3
     assert method_id("cpt-linear-solve") == 4 and method_id("odt-dp-fp") == 5
-    for name in ("cvt-full", "cvt-uniform-qnf", "cpt-quasi-newton", "odt-bfgs"):
+    assert method_id("CPT (quasi-newton)") == 6
+    for name in ("cvt-full", "cvt-uniform-qnf", "odt-bfgs"):
         with pytest.raises(NotImplementedError):
             method_id(name)
     with pytest.raises(KeyError):

@@ -19,6 +19,7 @@ pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 STEP_TOL = 1.0e-10  # relative to max |x|, per step
 METHODS = ["lloyd", "cvt-block-diagonal", "cpt-fixed-point", "odt-fixed-point", "odt-dp-fp"]
+SOLVE_METHODS = ["cpt-linear-solve", "cpt-quasi-newton"]  # iterative solve: 1e-9 per step
 
 
 @pytest.fixture(scope="module")
@@ -87,7 +88,7 @@ def _meshes(G):
 
 
 @pytest.mark.parametrize("name", ["disk40", "disk120", "square", "sphere6", "sphere24"])
-@pytest.mark.parametrize("method", METHODS + ["cpt-linear-solve"])
+@pytest.mark.parametrize("method", METHODS + SOLVE_METHODS)
 @pytest.mark.parametrize("renumber", [True, False])
 def test_get_new_points_matches_oracle(ob, G, name, method, renumber):
     pts, cells = _meshes(G)[name]
@@ -97,7 +98,7 @@ def test_get_new_points_matches_oracle(ob, G, name, method, renumber):
     with ob.DeviceMesh(pts, cells, renumber=renumber) as dm:
         dm.set_method(method)
         got = dm.new_points()
-    tol = 1e-9 if method == "cpt-linear-solve" else STEP_TOL
+    tol = 1e-9 if method in SOLVE_METHODS else STEP_TOL
     assert rel_err(got, ref) <= tol
 
 
@@ -135,12 +136,43 @@ def test_odt_boundary_cells_after_flips(ob, G):
         assert rel_err(p, rp) <= 1e-8
 
 
+@pytest.mark.parametrize("name", ["disk120", "square", "sphere24"])
+@pytest.mark.parametrize("omega", [1.0, 1.5])
+def test_quasi_newton_step_and_trajectory(ob, G, name, omega):
+    """cpt-quasi-newton: one driver step (pin, omega, limiter) and a short run with flips."""
+    pts, cells = _meshes(G)[name]
+    om = OMesh(pts, cells)
+    max_diff2, n_limited = oracle.driver.step(om, "cpt-quasi-newton", omega=omega)
+    with ob.DeviceMesh(pts, cells) as dm:
+        dm.set_method("cpt-quasi-newton", omega)
+        st = dm.update_points(0.0)
+        got = dm.points
+    assert rel_err(got, om.points) <= 1e-9
+    assert st["n_limited"] == n_limited
+    assert abs(st["max_diff2"] - max_diff2) <= 1e-8 * max_diff2
+    assert 0 < st["solver_iters"] <= 100  # condition number <= 5: a few dozen iterations
+    rp, rc = oracle.optimize_points_cells(pts, cells, "cpt-quasi-newton", 0.0, 6, omega=omega)
+    p, c = ob.optimize_points_cells(pts, cells, "cpt-quasi-newton", 0.0, 6, omega=omega)
+    assert np.array_equal(canonical_cells(c), canonical_cells(rc))
+    assert rel_err(p, rp) <= 1e-8
+
+
+def test_quasi_newton_simple1_and_legacy_entry(ob, G):
+    # a single free vertex: one quasi-Newton step is the CPT fixed-point step
+    p, c = ob.cpt.quasi_newton(*G.SIMPLE1, 1.0e-2, 100)
+    n1, n2, ninf = norms(p)
+    assert abs(n1 - 5.0) < 1e-11 and abs(n2 - 2.1213203435596424) < 1e-11 and ninf == 1.0
+
+
 def test_get_new_points_matches_golden_fixture(ob, G):
     z = np.load(os.path.join(GOLDEN, "single_steps.npz"))
     pts, cells = G.disk(40, 3)
     for m in METHODS:
         got = ob.get_new_points(ob.MeshTri(pts, cells), m)
         assert rel_err(got, z[f"disk40_{m}"]) <= STEP_TOL
+    for m in SOLVE_METHODS:
+        got = ob.get_new_points(ob.MeshTri(pts, cells), m)
+        assert rel_err(got, z[f"disk40_{m}"]) <= 1e-9
     sp, sc = z["sphere6_points"], z["sphere6_cells"]
     for m in METHODS:
         got = ob.get_new_points(ob.MeshTri(sp, sc), m)

@@ -137,6 +137,36 @@ def test_odt_dp_fp_simple1():
     assert np.allclose(p[4], [0.5, 0.5], atol=1e-6)
 
 
+def test_cpt_quasi_newton_matrix_properties():
+    """The approximate Hessian is strictly diagonally dominant (off-diagonal row sum = 2/3 of
+    the diagonal), hence SPD and well conditioned; on a single free vertex the step equals
+    the CPT fixed-point step; it needs fewer steps than the fixed-point iteration."""
+    X, cells = G.SIMPLE1
+    qn = oracle.get_new_points(MeshTri(X, cells), "cpt-quasi-newton")
+    fp = oracle.get_new_points(MeshTri(X, cells), "cpt-fixed-point")
+    assert np.allclose(qn, fp, atol=1e-15)
+    pts, cells = G.disk(40, 3)
+    mesh = MeshTri(pts, cells)
+    new = oracle.get_new_points(mesh, "cpt-quasi-newton")
+    assert np.array_equal(new[mesh.is_boundary_point], pts[mesh.is_boundary_point])
+    # residual of the defining system on interior rows: H (x - new) = dE
+    vol, bary = mesh.cell_volumes, mesh.cell_barycenters
+    step = pts - new
+    res = np.zeros(pts.shape)
+    for k in range(3):
+        i = cells[:, k]
+        np.add.at(res, i, (2 / 3) * vol[:, None] * step[i])
+        for kk in ((k + 1) % 3, (k + 2) % 3):
+            np.add.at(res, i, -(2 / 9) * vol[:, None] * step[cells[:, kk]])
+        np.add.at(res, i, -(2 / 3) * vol[:, None] * (pts[i] - bary))
+    inner = mesh.is_interior_point
+    assert np.abs(res[inner]).max() < 1e-14
+    n_qn, n_fp = [], []
+    oracle.optimize_points_cells(pts, cells, "cpt-quasi-newton", 1.0e-6, 200, log=n_qn)
+    oracle.optimize_points_cells(pts, cells, "cpt-fixed-point", 1.0e-6, 200, log=n_fp)
+    assert len(n_qn) < len(n_fp)
+
+
 def test_degenerate_cell_raises():
     pts = np.array([[0.0, 0.0], [1.0, 0.0], [2.0, 0.0]])
     with pytest.raises(DegenerateCellsError):
