@@ -312,7 +312,7 @@ def run_b200(args):
         "algorithmic_bytes_per_launch": b_alg, "kernel_ms": k1_ms,
         "kernel_share_of_step": tim["step_kernel_ms"] / ms,
         "flip_pass_ms": tim["flip_pass_ms"] / max(tim["flip_passes"], 1),
-        "note": "fp64-pipe co-limited (SURVEY.md 7, hard part 1)",
+        "note": "bound by instruction issue (70 % of issue slots, fp64 pipe 47 %): DESIGN.md section 4",
     }
 
     line = {

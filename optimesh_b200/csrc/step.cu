@@ -9,7 +9,8 @@
 // (np.bincount / np.add.at / np.minimum.at) and the body of the optimize() loop
 // (README.md:131-132).  Arithmetic: SURVEY.md Appendix A.2-A.5, A.8, A.9.
 //
-// fp64 budget (the kernel is fp64-pipe/latency bound, not HBM bound): one rsqrt per cell
+// Instruction budget (ncu: the kernel is bound by instruction issue -- 70 % of the issue slots
+// busy, fp64 pipe 47 % -- not by HBM): one rsqrt per cell
 // visit and no division -- 1/(4A) = rsqrt(16 A^2), the circumcentre weights use
 // sum_k ee_k ed_k = -8 A^2, thirds are applied once per vertex.  The inradius (3 sqrt +
 // 1 div per cell) is only needed where the limiter bites, so the LAZY variant first tests
@@ -46,21 +47,33 @@ struct Acc {
   Vec<D> num;
   double H[D * (D + 1) / 2];  // upper triangle
   double rmin;                // EXACT: smallest incident inradius
-  double lb_num, lb_den;      // LAZY: cell minimising A^2 / sum(ee) (kept as a fraction)
+  double lb_num, lb_den;      // LAZY: cell minimising A^2 / (sum(ee)/2) (kept as a fraction)
 };
 
 // 1/sqrt(x) for positive, normal x (the caller has checked x > 0): hardware seed
-// (rsqrt.approx.f64, relative error < 2^-22) + two Newton steps, no special-case branch.
+// (rsqrt.approx.f64, relative error < 2^-22) + ONE third-order step
+//   e = 1 - x y^2,  y <- y (1 + e/2 + 3 e^2/8)        (remainder 5 e^3/16 < 2^-67)
+// -- five fp64 instructions instead of the seven of two Newton steps (the kernel is bound by
+// instruction issue: every instruction saved counts, whatever its pipe).
 __device__ __forceinline__ double fast_rsqrt(double x) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  const double hx = 0.5 * x;
-#pragma unroll
-  for (int it = 0; it < 2; it++) {
-    const double t = fma(-hx * y, y, 0.5);  // 0.5 - 0.5 x y^2
-    y = fma(y, t, y);
-  }
-  return y;
+  const double e = fma(-x * y, y, 1.0);
+  const double p = fma(0.375, e, 0.5);
+  return fma(y * e, p, y);
+}
+
+// t > 0.5 on the integer pipe (exact: compares the bit pattern with that of 0.5)
+__device__ __forceinline__ bool gt_half(double t) {
+  // as one 64-bit integer compare: t > 0.5  <=>  bits(t) > bits(0.5) for every non-NaN t
+  // (negative t have the sign bit set, i.e. are negative as signed integers)
+  return __double_as_longlong(t) > 0x3fe0000000000000ll;
+}
+
+// a < b for non-negative doubles (or +inf) on the integer pipe: their order is the order of
+// their bit patterns
+__device__ __forceinline__ bool lt_nonneg(double a, double b) {
+  return __double_as_longlong(a) < __double_as_longlong(b);
 }
 
 // exact inradius of one cell (A.3): 2A / (l0 + l1 + l2)
@@ -88,13 +101,15 @@ __device__ __forceinline__ void accumulate_cell(const Vec<D>& P0, const Vec<D>& 
     return;
   }
   const double ed1 = -(ed0 + ee2), ed2 = -(ed0 + ee1);
-  const double S = 2.0 * (ee1 + ee2 + ed0);  // ee0 + ee1 + ee2
   if (EXACT) {
     const double A = sqrt(vol2);
-    a.rmin = fmin(a.rmin, 2.0 * A / (sqrt(S - ee1 - ee2) + sqrt(ee1) + sqrt(ee2)));
-  } else if (vol2 * a.lb_den < a.lb_num * S) {
-    a.lb_num = vol2;
-    a.lb_den = S;
+    a.rmin = fmin(a.rmin, 2.0 * A / (sqrt(-(ed1 + ed2)) + sqrt(ee1) + sqrt(ee2)));  // ee0
+  } else {
+    const double Sh = ee2 - ed2;  // (ee0 + ee1 + ee2) / 2 = ee1 + ee2 + ed0
+    if (lt_nonneg(vol2 * a.lb_den, a.lb_num * Sh)) {
+      a.lb_num = vol2;
+      a.lb_den = Sh;
+    }
   }
   const double r = fast_rsqrt(vol2);  // 1/A
   if (METHOD == OM_CPT_FIXED_POINT) {
@@ -115,13 +130,13 @@ __device__ __forceinline__ void accumulate_cell(const Vec<D>& P0, const Vec<D>& 
     const double wb = dp ? 1.0 : A;  // barycenter: 3 (b - P0) = e2 - e1
     const double s2 = bary ? wb : ee1 * ed1 * f, s1 = bary ? wb : ee2 * ed2 * f;
 #pragma unroll
-    for (int k = 0; k < D; k++) a.num.v[k] += s2 * e2.v[k] - s1 * e1.v[k];
+    for (int k = 0; k < D; k++) a.num.v[k] = fma(s2, e2.v[k], fma(-s1, e1.v[k], a.num.v[k]));
     return;
   }
   // Lloyd / CVT block-diagonal (A.4, A.9), scaled as described at Acc
   const double q = 0.25 * r;
   const double t0 = ed0 * q, t1 = ed1 * q, t2 = ed2 * q;  // -ce_k
-  if (t0 > 0.5 || t1 > 0.5 || t2 > 0.5) return;  // cell masked (an angle > 135 deg)
+  if (gt_half(t0) | gt_half(t1) | gt_half(t2)) return;  // cell masked (an angle > 135 deg)
   const double w1 = ee1 * t1, w2 = ee2 * t2;  // -4 part_k
   const double ws = w1 + w2;
   a.w += ws;
@@ -129,8 +144,9 @@ __device__ __forceinline__ void accumulate_cell(const Vec<D>& P0, const Vec<D>& 
   //   = e2 (u w1 + w2/2 ... ) with u = -2 q ws:  s2' = u w1 - 0.5 w2 ... (signs folded below)
   const double u = -2.0 * q * ws;
   const double s2 = fma(u, w1, 0.5 * w2), s1 = fma(u, w2, 0.5 * w1);
+  // accumulated by fma chains: two fp64 instructions per component instead of three
 #pragma unroll
-  for (int k = 0; k < D; k++) a.num.v[k] += s2 * e2.v[k] - s1 * e1.v[k];
+  for (int k = 0; k < D; k++) a.num.v[k] = fma(s2, e2.v[k], fma(-s1, e1.v[k], a.num.v[k]));
   if (METHOD == OM_CVT_BLOCK_DIAGONAL) {
     Vec<D> a1, a2;
 #pragma unroll
@@ -143,7 +159,7 @@ __device__ __forceinline__ void accumulate_cell(const Vec<D>& P0, const Vec<D>& 
     for (int i = 0; i < D; i++)
 #pragma unroll
       for (int j = i; j < D; j++) {
-        a.H[qi] += a1.v[i] * e1.v[j] + a2.v[i] * e2.v[j];
+        a.H[qi] = fma(a1.v[i], e1.v[j], fma(a2.v[i], e2.v[j], a.H[qi]));
         qi++;
       }
   }
@@ -533,10 +549,10 @@ __global__ void __launch_bounds__(step_block<D>(), (D == 2 ? OM_K1_MINB : 3))
           diff2 = vdot<D>(d, d);
           if (p.limiter) {
             // limited iff |d| > r/2 with r the smallest incident inradius.  LAZY: every
-            // inradius satisfies r^2 >= 4 A^2 / (3 sum ee), so 3 |d|^2 sum_ee <= A^2 for
+            // inradius satisfies r^2 >= 4 A^2 / (3 sum ee), so 3 |d|^2 sum_ee <= A^2 (lb_den holds sum_ee / 2) for
             // the minimising cell proves "not limited" without a sqrt or a division.
             const bool check =
-                EXACT || !(3.0 * diff2 * acc.lb_den * (1.0 + 1e-12) <= acc.lb_num);
+                EXACT || !(6.0 * diff2 * acc.lb_den * (1.0 + 1e-12) <= acc.lb_num);
             if (check && !EXACT) {
               // rare (a few % of the vertices) and expensive: running it here would keep
               // whole warps busy for one lane.  The vertex goes to the list-driven exact
