@@ -21,20 +21,32 @@ def _have_meshio():
         return False
 
 
-def read(path: str):
-    """Returns (points (N,d) float64, triangle cells (C,3) int64)."""
+def read(path: str, with_cell_data: bool = False):
+    """Returns (points (N,d) float64, triangle cells (C,3) int64); with ``with_cell_data``
+    also a dict of per-triangle arrays (e.g. the subdomain field of ``optimesh -s NAME``)."""
+    points, cells, cell_data = _read(path)
+    return (points, cells, cell_data) if with_cell_data else (points, cells)
+
+
+def _read(path: str):
     ext = os.path.splitext(path)[1].lower()
     if ext == ".npz":
         with np.load(path) as z:
-            return np.asarray(z["points"], dtype=np.float64), np.asarray(z["cells"], dtype=np.int64)
+            cells = np.asarray(z["cells"], dtype=np.int64)
+            data = {k: np.asarray(z[k]) for k in z.files
+                    if k not in ("points", "cells") and z[k].shape[:1] == cells.shape[:1]}
+            return np.asarray(z["points"], dtype=np.float64), cells, data
     if _have_meshio():
         import meshio
 
         m = meshio.read(path)
-        tris = [c.data for c in m.cells if c.type == "triangle"]
-        if not tris:
+        blocks = [i for i, c in enumerate(m.cells) if c.type == "triangle"]
+        if not blocks:
             raise ValueError(f"{path}: no triangle cells")
-        return np.asarray(m.points, dtype=np.float64), np.concatenate(tris).astype(np.int64)
+        cells = np.concatenate([m.cells[i].data for i in blocks]).astype(np.int64)
+        data = {k: np.concatenate([np.asarray(v[i]) for i in blocks])
+                for k, v in (m.cell_data or {}).items()}
+        return np.asarray(m.points, dtype=np.float64), cells, data
     if ext == ".vtk":
         return _read_vtk(path)
     raise ValueError(
@@ -42,27 +54,32 @@ def read(path: str):
         "ASCII) and .npz")
 
 
-def write(path: str, points, cells):
+def write(path: str, points, cells, cell_data=None):
     points = np.asarray(points, dtype=np.float64)
     cells = np.asarray(cells)
+    cell_data = {k: np.asarray(v) for k, v in (cell_data or {}).items()}
+    for k, v in cell_data.items():
+        if v.shape[:1] != cells.shape[:1]:
+            raise ValueError(f"cell data {k!r} has {v.shape[0]} entries for {cells.shape[0]} cells")
     ext = os.path.splitext(path)[1].lower()
     if ext == ".npz":
-        np.savez(path, points=points, cells=cells)
+        np.savez(path, points=points, cells=cells, **cell_data)
         return
     if _have_meshio():
         import meshio
 
-        meshio.write_points_cells(path, points, [("triangle", cells)])
+        meshio.write_points_cells(path, points, [("triangle", cells)],
+                                  cell_data={k: [v] for k, v in cell_data.items()})
         return
     if ext == ".vtk":
-        _write_vtk(path, points, cells)
+        _write_vtk(path, points, cells, cell_data)
         return
     raise ValueError(
         f"cannot write {path!r}: meshio is not installed; built-in formats are .vtk (legacy "
         "ASCII) and .npz")
 
 
-def _write_vtk(path, points, cells):
+def _write_vtk(path, points, cells, cell_data=None):
     n, d = points.shape
     p3 = np.zeros((n, 3))
     p3[:, :d] = points
@@ -75,6 +92,20 @@ def _write_vtk(path, points, cells):
         np.savetxt(f, np.column_stack([np.full(c, 3), cells]), fmt="%d")
         f.write(f"CELL_TYPES {c}\n")
         np.savetxt(f, np.full(c, 5), fmt="%d")
+        if cell_data:
+            f.write(f"CELL_DATA {c}\n")
+            for name, v in cell_data.items():
+                if v.ndim != 1:
+                    raise ValueError("built-in VTK writer: scalar cell data only")
+                is_int = np.issubdtype(v.dtype, np.integer)
+                f.write(f"SCALARS {name.replace(' ', '_')} {'int' if is_int else 'double'} 1\n")
+                f.write("LOOKUP_TABLE default\n")
+                np.savetxt(f, v, fmt="%d" if is_int else "%.17g")
+
+
+_VTK_INT_TYPES = ("bit", "char", "unsigned_char", "short", "unsigned_short", "int",
+                  "unsigned_int", "long", "unsigned_long", "vtktypeint32", "vtktypeint64",
+                  "vtkidtype")
 
 
 def _read_vtk(path):
@@ -89,15 +120,52 @@ def _read_vtk(path):
     i = up.index("CELLS")
     c, total = int(tok[i + 1]), int(tok[i + 2])
     flat = np.array(tok[i + 3:i + 3 + total], dtype=np.int64)
-    cells = []
+    cells, is_tri = [], []
     k = 0
     while k < total:
         m = flat[k]
+        is_tri.append(m == 3)
         if m == 3:
             cells.append(flat[k + 1:k + 4])
         k += m + 1
     if not cells:
         raise ValueError(f"{path}: no triangle cells")
+    is_tri = np.array(is_tri)
+    data = {}
+    if "CELL_DATA" in up:
+        j = up.index("CELL_DATA")
+        nc = int(tok[j + 1])
+        j += 2
+        while j < len(tok) and up[j] not in ("POINT_DATA",):
+            if up[j] == "SCALARS":
+                name, typ = tok[j + 1], tok[j + 2].lower()
+                j += 3
+                ncomp = 1
+                if j < len(tok) and tok[j].isdigit():
+                    ncomp = int(tok[j])
+                    j += 1
+                if up[j] == "LOOKUP_TABLE":
+                    j += 2
+                vals = np.array(tok[j:j + nc * ncomp],
+                                dtype=np.int64 if typ in _VTK_INT_TYPES else np.float64)
+                j += nc * ncomp
+                vals = vals.reshape(nc, ncomp)[is_tri[:nc]] if nc == len(is_tri) else None
+                if vals is not None:
+                    data[name] = vals[:, 0] if ncomp == 1 else vals
+            elif up[j] == "FIELD":
+                narr = int(tok[j + 2])
+                j += 3
+                for _ in range(narr):
+                    name, ncomp, ntup, typ = tok[j], int(tok[j + 1]), int(tok[j + 2]), tok[j + 3].lower()
+                    j += 4
+                    vals = np.array(tok[j:j + ncomp * ntup],
+                                    dtype=np.int64 if typ in _VTK_INT_TYPES else np.float64)
+                    j += ncomp * ntup
+                    if ntup == len(is_tri):
+                        vals = vals.reshape(ntup, ncomp)[is_tri]
+                        data[name] = vals[:, 0] if ncomp == 1 else vals
+            else:
+                j += 1
     if np.all(pts[:, 2] == 0.0):
         pts = pts[:, :2]
-    return np.ascontiguousarray(pts), np.array(cells, dtype=np.int64)
+    return np.ascontiguousarray(pts), np.array(cells, dtype=np.int64), data

@@ -117,6 +117,73 @@ def test_cli_arguments():
     assert _parser().parse_args(["a", "b"]).method == "cvt-block-diagonal"
 
 
+def test_io_cell_data_roundtrip(tmp_path):
+    from optimesh_b200 import generators as G, io
+
+    pts, cells = G.square(6, 0.2, 0)
+    field = (pts[cells].mean(axis=1)[:, 0] > 0.5).astype(np.int64)
+    quality = np.linspace(0.0, 1.0, len(cells))
+    for ext in (".vtk", ".npz"):
+        path = str(tmp_path / ("m" + ext))
+        io.write(path, pts, cells, cell_data={"subdomain": field, "quality": quality})
+        p, c, data = io.read(path, with_cell_data=True)
+        assert np.allclose(p, pts) and np.array_equal(c, cells)
+        assert np.array_equal(data["subdomain"], field) and np.allclose(data["quality"], quality)
+        assert len(io.read(path)) == 2  # the two-value form is unchanged
+    with pytest.raises(ValueError):
+        io.write(str(tmp_path / "bad.npz"), pts, cells, cell_data={"f": field[:-1]})
+
+
+def test_cli_subdomains_preserve_interfaces(tmp_path, monkeypatch):
+    """`optimesh in out -s NAME` (README.md:17 "preserves submeshes"): every subdomain is
+    optimized on its own.  The device call is replaced by the CPU oracle here, so this checks
+    the splitting, the write-back and the cell data -- not the kernels."""
+    import oracle
+    from optimesh_b200 import cli, generators as G, io
+
+    pts, cells = G.square(12, 0.25, 3)
+    centroid_x = pts[cells].mean(axis=1)[:, 0]
+    field = np.where(centroid_x < 0.35, 3, np.where(centroid_x < 0.7, 5, 9)).astype(np.int64)
+    src, dst = str(tmp_path / "in.vtk"), str(tmp_path / "out.vtk")
+    io.write(src, pts, cells, cell_data={"gmsh:physical": field})
+
+    calls = []
+
+    def fake(points, cells_, method, tol, max_num_steps, **kwargs):
+        calls.append((points.shape[0], cells_.shape[0], method, kwargs.get("omega")))
+        assert cells_.min() == 0 and cells_.max() == points.shape[0] - 1  # compact submesh
+        kwargs.pop("device", None)
+        kwargs.pop("verbose", None)
+        return oracle.optimize_points_cells(points, cells_, method, tol, max_num_steps,
+                                            omega=kwargs.get("omega", 1.0))
+
+    monkeypatch.setattr(cli, "optimize_points_cells", fake)
+    assert cli.main([src, dst, "-m", "cpt-fixed-point", "-n", "5", "-t", "0", "-q",
+                     "-s", "gmsh:physical"]) == 0
+    assert len(calls) == 3 and sum(c[1] for c in calls) == len(cells)
+    p, c, data = io.read(dst, with_cell_data=True)
+    assert np.array_equal(data["gmsh:physical"], field)  # every cell kept its subdomain
+    # vertices used by more than one subdomain (the interfaces) and the outer boundary stay
+    owners = np.zeros((len(pts), 3), dtype=bool)
+    for k, v in enumerate((3, 5, 9)):
+        owners[c[field == v].reshape(-1), k] = True
+        # a subdomain never gains or loses vertices: flips stay inside it
+        assert set(c[field == v].reshape(-1)) == set(cells[field == v].reshape(-1))
+    shared = owners.sum(axis=1) > 1
+    assert shared.sum() > 10 and np.array_equal(p[shared], pts[shared])
+    bnd = oracle.MeshTri(pts, cells).is_boundary_point
+    assert np.array_equal(p[bnd], pts[bnd])
+    assert not np.allclose(p[~shared & ~bnd], pts[~shared & ~bnd])  # the interiors did move
+    # without -s the whole mesh is one set and interface vertices move too
+    calls.clear()
+    assert cli.main([src, dst, "-m", "cpt-fixed-point", "-n", "5", "-t", "0", "-q"]) == 0
+    assert len(calls) == 1 and calls[0][:2] == (len(pts), len(cells))
+    p2, _ = io.read(dst)
+    assert not np.array_equal(p2[shared & ~bnd], pts[shared & ~bnd])
+    with pytest.raises(SystemExit):
+        cli.main([src, dst, "-q", "-s", "no-such-field"])
+
+
 def test_print_stats_runs(capsys):
     from optimesh_b200.helpers import print_stats
     import oracle
