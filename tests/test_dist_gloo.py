@@ -87,7 +87,8 @@ def _worker(rank, world, port, pts, cells, method, omega, steps, out):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("method,omega", [("lloyd", 2.0), ("cvt-block-diagonal", 1.0)])
+@pytest.mark.parametrize("method,omega", [("lloyd", 2.0), ("cvt-block-diagonal", 1.0),
+                                          ("odt-dp-fp", 1.0), ("cpt-quasi-newton", 1.0)])
 def test_sharded_loop_matches_single_process(tmp_path, method, omega):
     import oracle
     from optimesh_b200 import generators as G
