@@ -134,6 +134,34 @@ def test_io_cell_data_roundtrip(tmp_path):
         io.write(str(tmp_path / "bad.npz"), pts, cells, cell_data={"f": field[:-1]})
 
 
+@pytest.mark.parametrize("ext", [".vtk", ".msh", ".off", ".obj", ".npz"])
+def test_builtin_formats_roundtrip(tmp_path, ext):
+    from optimesh_b200 import generators as G, io
+
+    for name, (pts, cells) in {"flat": G.square(6, 0.2, 0), "surface": G.tetra_sphere(3)}.items():
+        field = (pts[cells].mean(axis=1)[:, 0] > 0.5).astype(np.int64) + 1
+        path = str(tmp_path / (name + ext))
+        io.write(path, pts, cells, cell_data={"gmsh:physical": field})
+        p, c, data = io.read(path, with_cell_data=True)
+        assert np.array_equal(p, pts) and np.array_equal(c, cells)  # %.17g round-trips doubles
+        if ext in (".vtk", ".msh", ".npz"):
+            assert np.array_equal(data["gmsh:physical"], field)
+
+
+def test_msh_reader_skips_other_elements_and_sparse_node_ids(tmp_path):
+    from optimesh_b200 import io
+
+    path = tmp_path / "m.msh"
+    path.write_text(
+        "$MeshFormat\n2.2 0 8\n$EndMeshFormat\n$Nodes\n4\n"
+        "10 0 0 0\n20 1 0 0\n30 1 1 0\n40 0 1 0\n$EndNodes\n$Elements\n4\n"
+        "1 15 2 0 1 10\n2 1 2 7 1 10 20\n3 2 2 5 1 10 20 30\n4 2 2 6 2 10 30 40\n"
+        "$EndElements\n")
+    p, c, data = io.read(str(path), with_cell_data=True)
+    assert p.shape == (4, 2) and c.tolist() == [[0, 1, 2], [0, 2, 3]]
+    assert data["gmsh:physical"].tolist() == [5, 6] and data["gmsh:geometrical"].tolist() == [1, 2]
+
+
 def test_cli_subdomains_preserve_interfaces(tmp_path, monkeypatch):
     """`optimesh in out -s NAME` (README.md:17 "preserves submeshes"): every subdomain is
     optimized on its own.  The device call is replaced by the CPU oracle here, so this checks
