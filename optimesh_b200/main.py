@@ -36,12 +36,53 @@ def _project_host(dm: DeviceMesh, surface, tol: float, max_iter: int = 100):
         dm.points = x.T
 
 
+def _half_min_inradius(x: np.ndarray, cells: np.ndarray) -> np.ndarray:
+    """Per vertex: half of the smallest inradius over its cells (the loop's step limit)."""
+    p0, p1, p2 = x[cells[:, 0]], x[cells[:, 1]], x[cells[:, 2]]
+    e0, e1, e2 = p2 - p1, p0 - p2, p1 - p0
+    l0, l1, l2 = (np.sqrt(np.einsum("ij,ij->i", e, e)) for e in (e0, e1, e2))
+    # |e1 x e2|^2 = |e1|^2 |e2|^2 - (e1.e2)^2 in any embedding dimension
+    d12 = np.einsum("ij,ij->i", e1, e2)
+    area = 0.5 * np.sqrt(np.maximum(l1 * l1 * l2 * l2 - d12 * d12, 0.0))
+    r_in = 2.0 * area / (l0 + l1 + l2)
+    out = np.full(x.shape[0], np.inf)
+    np.minimum.at(out, cells.reshape(-1), np.repeat(r_in, 3))
+    return 0.5 * out
+
+
+def _host_update(dm: DeviceMesh, omega: float, tol: float, boundary_step) -> dict:
+    """One point update with a ``boundary_step`` callback: the targets come from the device,
+    the callback moves the boundary targets (e.g. back onto the domain boundary) on the
+    host, then relaxation and the step limiter are applied to every vertex as the reference's
+    loop does it.  This is the slow, hook-driven path; without the callback the whole update
+    is one kernel."""
+    x = dm.points
+    new = dm.new_points()
+    bnd = dm.is_boundary_point
+    if bnd.any():
+        moved = np.asarray(boundary_step(new[bnd].T), dtype=np.float64).T
+        if moved.shape != new[bnd].shape:
+            raise ValueError("boundary_step must return an array of the shape it was given")
+        new[bnd] = moved
+    diff = omega * (new - x)
+    len2 = np.einsum("ij,ij->i", diff, diff)
+    max_diff2 = float(len2.max()) if len2.size else 0.0
+    limit = _half_min_inradius(x, np.asarray(dm.cells(np.int64)))
+    length = np.sqrt(len2)
+    idx = length > limit
+    diff[idx] *= (limit[idx] / length[idx])[:, None]
+    dm.points = x + diff
+    return {"max_diff2": max_diff2, "n_limited": int(idx.sum()), "n_flips": 0, "n_flip_rounds": 0,
+            "flip_cap_hit": 0, "is_final": int(max_diff2 < tol * tol), "solver_iters": 0,
+            "surface_sweeps": 0, "stale": 0}
+
+
 def _run_loop(dm: DeviceMesh, method: str, tol: float, max_num_steps: int, omega: float = 1.0,
               verbose: bool = False, callback=None, step_filename_format=None,
               implicit_surface=None, implicit_surface_tol: float = 1.0e-10, boundary_step=None,
               cells_dtype=None, log=None, odt_boundary_barycenters: bool = True):
-    if boundary_step is not None:
-        raise NotImplementedError("boundary_step callbacks are outside this build")
+    if boundary_step is not None and not callable(boundary_step):
+        raise TypeError("boundary_step must be callable: (d, n) array -> (d, n) array")
     if max_num_steps < 1:
         raise ValueError("max_num_steps must be >= 1")
     dm.set_method(method, omega)
@@ -62,7 +103,7 @@ def _run_loop(dm: DeviceMesh, method: str, tol: float, max_num_steps: int, omega
         print_stats(*dm.stats())
 
     hooks = callback is not None or step_filename_format is not None or host_surface is not None \
-        or log is not None
+        or log is not None or boundary_step is not None
     if not hooks:
         steps, last = dm.run(tol, max_num_steps)
     else:
@@ -72,11 +113,17 @@ def _run_loop(dm: DeviceMesh, method: str, tol: float, max_num_steps: int, omega
             callback(0, _snapshot(dm, cells_dtype))
         while True:
             steps += 1
-            if host_surface is None:
+            if host_surface is None and boundary_step is None:
                 st = dm.step(tol)
             else:
-                st = dm.update_points(tol)
-                _project_host(dm, host_surface, implicit_surface_tol)
+                if boundary_step is None:
+                    st = dm.update_points(tol)
+                else:
+                    st = _host_update(dm, omega, tol, boundary_step)
+                if host_surface is not None:
+                    _project_host(dm, host_surface, implicit_surface_tol)
+                elif boundary_step is not None:
+                    dm.project()  # the built-in surface, if one is set
                 nf, nr = dm.flip_until_delaunay()
                 st["n_flips"], st["n_flip_rounds"] = nf, nr
             is_final = bool(st["is_final"]) or steps >= max_num_steps

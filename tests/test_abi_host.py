@@ -212,6 +212,97 @@ def test_cli_subdomains_preserve_interfaces(tmp_path, monkeypatch):
         cli.main([src, dst, "-q", "-s", "no-such-field"])
 
 
+class _OracleMesh:
+    """Stands in for DeviceMesh in host-logic tests: same methods, CPU oracle inside."""
+
+    def __init__(self, points, cells):
+        import oracle
+
+        self._o = oracle
+        self.mesh = oracle.MeshTri(np.array(points, dtype=float), np.array(cells))
+        self.n, self.dim = self.mesh.points.shape
+        self.method, self.omega = None, 1.0
+
+    def set_method(self, method, omega=1.0):
+        self.method, self.omega = method, omega
+
+    def set_odt_boundary_barycenters(self, on):
+        pass
+
+    def clear_surface(self):
+        pass
+
+    def flip_until_delaunay(self):
+        return self.mesh.flip_until_delaunay(), 0
+
+    def new_points(self):
+        return self._o.get_new_points(self.mesh, self.method)
+
+    def project(self):
+        return 0
+
+    @property
+    def points(self):
+        return self.mesh.points.copy()
+
+    @points.setter
+    def points(self, new):
+        self.mesh.points = new
+
+    def cells(self, dtype=None):
+        return self.mesh.cells("points").astype(dtype or np.int64)
+
+    @property
+    def is_boundary_point(self):
+        return self.mesh.is_boundary_point
+
+
+def test_boundary_step_host_path():
+    """`boundary_step` (hook of the reference's loop): targets from the mesh object, the
+    callback moves the boundary targets, relaxation + limiter on every vertex."""
+    import oracle
+    from optimesh_b200 import generators as G
+    from optimesh_b200.main import _half_min_inradius, _run_loop
+
+    pts, cells = G.disk(40, 3)
+    om = oracle.MeshTri(pts, cells)
+    want = np.full(len(pts), np.inf)
+    np.minimum.at(want, cells.reshape(-1), np.repeat(om.cell_inradius, 3))
+    assert np.allclose(_half_min_inradius(pts, cells), 0.5 * want, rtol=1e-13)
+
+    # 1. a callback that returns what it gets changes nothing for methods that pin the
+    #    boundary themselves: same trajectory as the plain loop
+    for method in ("cpt-fixed-point", "cvt-block-diagonal"):
+        log = []
+        dm = _OracleMesh(pts, cells)
+        steps = _run_loop(dm, method, 0.0, 6, omega=1.0, boundary_step=lambda x: x, log=log)
+        rlog = []
+        rp, rc = oracle.optimize_points_cells(pts, cells, method, 0.0, 6, log=rlog)
+        assert steps == 6 and np.array_equal(dm.cells(), rc)
+        assert np.allclose(dm.points, rp, rtol=0, atol=1e-13)
+        assert [l["n_limited"] for l in log] == [l["n_limited"] for l in rlog]
+
+    # 2. Lloyd proposes the control-volume centroid for boundary vertices too; projecting it
+    #    back onto the circle lets them slide along the boundary
+    def to_circle(x):
+        return x / np.sqrt(np.einsum("ij,ij->j", x, x))
+
+    dm = _OracleMesh(pts, cells)
+    _run_loop(dm, "lloyd", 0.0, 8, omega=1.0, boundary_step=to_circle)
+    p, c = dm.points, dm.cells()
+    bnd = oracle.MeshTri(pts, cells).is_boundary_point
+    assert not np.allclose(p[bnd], pts[bnd])             # they moved ...
+    assert np.abs(np.linalg.norm(p[bnd], axis=1) - 1.0).max() < 0.02  # ... near the circle
+    a = p[c[:, 1]] - p[c[:, 0]]
+    b = p[c[:, 2]] - p[c[:, 0]]
+    assert oracle.MeshTri(p, c).num_delaunay_violations() == 0
+    assert np.all(np.abs(a[:, 0] * b[:, 1] - a[:, 1] * b[:, 0]) > 0)  # no degenerate cell
+    with pytest.raises(ValueError):
+        _run_loop(_OracleMesh(pts, cells), "lloyd", 0.0, 1, boundary_step=lambda x: x[:, :-1])
+    with pytest.raises(TypeError):
+        _run_loop(_OracleMesh(pts, cells), "lloyd", 0.0, 1, boundary_step=1.0)
+
+
 def test_print_stats_runs(capsys):
     from optimesh_b200.helpers import print_stats
     import oracle
