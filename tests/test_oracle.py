@@ -167,6 +167,28 @@ def test_cpt_quasi_newton_matrix_properties():
     assert len(n_qn) < len(n_fp)
 
 
+@pytest.mark.parametrize("method", sorted(oracle.METHODS))
+def test_methods_are_similarity_and_relabelling_equivariant(method):
+    """new(s R x + t) = s R new(x) + t, and renumbering vertices / reordering or reorienting
+    cells does not change the geometry of the result: the restated formulas depend on the
+    mesh only, not on coordinates or labels."""
+    pts, cells = G.disk(30, 5)
+    base = oracle.get_new_points(MeshTri(pts, cells), method)
+    th, s, t = 0.7, 2.5, np.array([3.0, -1.5])
+    R = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+    moved = oracle.get_new_points(MeshTri(s * pts @ R.T + t, cells), method)
+    assert np.allclose(moved, s * base @ R.T + t, rtol=0, atol=5e-12)
+    rs = np.random.RandomState(11)
+    perm = rs.permutation(len(pts))           # new label of old vertex i is inv[i]
+    inv = np.argsort(perm)
+    c2 = inv[cells][rs.permutation(len(cells))]
+    flip = rs.rand(len(c2)) < 0.5             # mixed orientation, rotated slots
+    c2[flip] = c2[flip][:, ::-1]
+    c2 = np.where((rs.rand(len(c2)) < 0.5)[:, None], np.roll(c2, 1, axis=1), c2)
+    relabelled = oracle.get_new_points(MeshTri(pts[perm], c2), method)
+    assert np.allclose(relabelled, base[perm], rtol=0, atol=5e-13)
+
+
 def test_degenerate_cell_raises():
     pts = np.array([[0.0, 0.0], [1.0, 0.0], [2.0, 0.0]])
     with pytest.raises(DegenerateCellsError):
