@@ -189,6 +189,81 @@ def test_methods_are_similarity_and_relabelling_equivariant(method):
     assert np.allclose(relabelled, base[perm], rtol=0, atol=5e-13)
 
 
+def test_odt_update_is_the_gradient_of_the_odt_energy(monkeypatch):
+    """Chen-Holst (README.md:244-251): with the triangulation fixed, the ODT energy is
+    E = 1/(d+1) sum_i |x_i|^2 |w_i| + const, and dE/dx_i = 2/(d+1) |w_i| (x_i - x_i*) where
+    x_i* is the area-weighted mean of the circumcenters of the star.  Checked by central
+    differences on an energy evaluated independently of the oracle (d = 2)."""
+    import oracle.methods as om
+
+    monkeypatch.setattr(om, "ODT_BOUNDARY_BARYCENTERS", False)  # the formula of the paper
+    pts, cells = G.disk(24, 9)
+
+    def areas(x):
+        a, b = x[cells[:, 1]] - x[cells[:, 0]], x[cells[:, 2]] - x[cells[:, 0]]
+        return 0.5 * np.abs(a[:, 0] * b[:, 1] - a[:, 1] * b[:, 0])
+
+    def energy(x):
+        star = np.zeros(len(x))
+        np.add.at(star, cells.reshape(-1), np.repeat(areas(x), 3))
+        return np.sum(np.einsum("ij,ij->i", x, x) * star) / 3.0
+
+    mesh = MeshTri(pts, cells)
+    target = om.odt_fixed_point(mesh)
+    star = np.zeros(len(pts))
+    np.add.at(star, cells.reshape(-1), np.repeat(areas(pts), 3))
+    inner = np.nonzero(mesh.is_interior_point)[0]
+    h = 1.0e-6
+    for i in inner[:: max(1, len(inner) // 12)]:
+        for k in range(2):
+            xp, xm = pts.copy(), pts.copy()
+            xp[i, k] += h
+            xm[i, k] -= h
+            fd = (energy(xp) - energy(xm)) / (2 * h)
+            want = (2.0 / 3.0) * star[i] * (pts[i, k] - target[i, k])
+            assert abs(fd - want) <= 1e-8 * max(1.0, abs(want)), (i, k, fd, want)
+
+
+def test_control_volumes_are_voronoi_cells():
+    """A.4 against an independent construction: on a Delaunay mesh the control volume of an
+    interior vertex whose star has no boundary cell is its Voronoi cell (Qhull via
+    scipy.spatial.Voronoi); areas and centroids must agree, and with them the Lloyd target and
+    the gradient 2 |V_i| (x_i - c_i) of the CVT energy (Du-Faber-Gunzburger)."""
+    from scipy.spatial import Voronoi
+
+    pts, cells = G.disk(40, 2)
+    mesh = MeshTri(pts, cells)
+    mask = np.any(mesh.ce_ratios < -0.5, axis=0)
+    cv = mesh.get_control_volumes(cell_mask=mask)
+    cen = mesh.get_control_volume_centroids(cell_mask=mask)
+    touched = np.zeros(mesh.n, dtype=bool)  # vertices of boundary cells or masked cells
+    touched[cells[mesh.is_boundary_cell | mask].reshape(-1)] = True
+    vor = Voronoi(pts)
+    checked = 0
+    for i in np.nonzero(mesh.is_interior_point & ~touched)[0]:
+        region = vor.regions[vor.point_region[i]]
+        if not region or -1 in region:
+            continue
+        poly = vor.vertices[region]
+        if np.linalg.norm(poly, axis=1).max() > 0.98:  # leaves the meshed domain
+            continue
+        # order the polygon around its vertex, then shoelace area and centroid
+        ang = np.arctan2(poly[:, 1] - pts[i, 1], poly[:, 0] - pts[i, 0])
+        poly = poly[np.argsort(ang)]
+        x, y = poly[:, 0], poly[:, 1]
+        xn, yn = np.roll(x, -1), np.roll(y, -1)
+        cross = x * yn - xn * y
+        area = 0.5 * cross.sum()
+        cx = ((x + xn) * cross).sum() / (6 * area)
+        cy = ((y + yn) * cross).sum() / (6 * area)
+        assert abs(cv[i] - area) <= 1e-12 * area
+        assert np.allclose(cen[i], [cx, cy], rtol=0, atol=1e-12)
+        checked += 1
+    assert checked > 50
+    lloyd = oracle.get_new_points(mesh, "lloyd")
+    assert np.array_equal(lloyd[mesh.is_interior_point], cen[mesh.is_interior_point])
+
+
 def test_degenerate_cell_raises():
     pts = np.array([[0.0, 0.0], [1.0, 0.0], [2.0, 0.0]])
     with pytest.raises(DegenerateCellsError):
