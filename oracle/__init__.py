@@ -2,7 +2,8 @@
 
 This package is a plain numpy/scipy restatement of the arithmetic of the reference's
 hot path: ``optimesh.optimize_points_cells`` -> per-step ``get_new_points`` (relaxed
-Lloyd, CVT block-diagonal, CPT fixed-point / linear-solve, ODT fixed-point), the
+Lloyd, CVT block-diagonal, CPT fixed-point / quasi-Newton / linear-solve, ODT fixed-point
+in its uniform and density-preserving forms), the
 driver loop (pin boundary, omega relaxation, step limiter, surface projection) and
 meshplex's ``MeshTri`` geometry + ``flip_until_delaunay``.
 
@@ -19,7 +20,11 @@ PARITY UNPINNED: the reference source and its tests are absent from
 pins this oracle instead (tests/test_oracle.py): the recollected upstream
 known-answer literals for the 5-point "simple1" mesh, Qhull
 (``scipy.spatial.Delaunay``/``ConvexHull``) as an independent topology oracle,
-``scipy.sparse.linalg.spsolve`` for the CPT linear solve, and analytic invariants.
+Qhull's Voronoi cells (``scipy.spatial.Voronoi``) for control volumes and their centroids,
+central differences of the published ODT energy for the ODT target,
+``scipy.sparse.linalg.spsolve`` for the CPT solves, and analytic invariants
+(equivariance under similarity transforms and relabelling, conservation of area,
+hexagonal-patch fixed points).
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
 ``--impl reference`` legs may import this package.  The product (``optimesh_b200``)
