@@ -43,6 +43,39 @@ def test_struct_layout_matches_header():
     assert ctypes.sizeof(_lib.StepStats) == 48
 
 
+def test_header_is_plain_c_and_links_against_the_library(tmp_path):
+    """The boundary is a C ABI: the header must compile as C99 (and C++), and a C program
+    that takes the address of every declared entry point must link against the library."""
+    import re
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = os.path.join(root, "include", "optimesh_b200.h")
+    names = sorted(set(re.findall(r"\b(om_[a-z0-9_]+)\s*\(", open(header).read())))
+    assert len(names) > 40
+    src = tmp_path / "abi.c"
+    src.write_text(
+        '#include "optimesh_b200.h"\n#include <stdio.h>\n'
+        "int main(void) {\n  void* fns[] = {" + ", ".join(f"(void*){n}" for n in names) + "};\n"
+        "  unsigned i, ok = 1;\n  for (i = 0; i < sizeof(fns) / sizeof(fns[0]); i++) ok &= fns[i] != 0;\n"
+        '  printf("%u %u\\n", (unsigned)sizeof(om_step_stats), ok);\n  return 0;\n}\n')
+    exe = tmp_path / "abi"
+    libdir = os.path.join(root, "optimesh_b200")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.dirname(header), str(src),
+                    "-o", str(exe), "-L", libdir, "-loptimesh_b200", f"-Wl,-rpath,{libdir}"],
+                   check=True, capture_output=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert out == ["48", "1"]
+    gxx = shutil.which("g++")
+    if gxx:
+        subprocess.run([gxx, "-std=c++11", "-fsyntax-only", "-x", "c++", "-I",
+                        os.path.dirname(header), str(src)], check=True, capture_output=True)
+
+
 def test_no_gpu_fails_loudly(lib):
     import torch
 
