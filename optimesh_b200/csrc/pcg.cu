@@ -387,6 +387,12 @@ __global__ void k_shift(PcgScal* sc, bool from_init) {
 
 int build_neighbours(om_handle* h) {
   if (h->nbr_valid) return OM_OK;
+  // the neighbour rows are indexed with 32-bit offsets (about 6 entries per vertex)
+  if (h->N > (int64_t)268000000) {
+    om_set_error("mesh too large for the solve methods (%lld vertices; limit 268 M)",
+                 (long long)h->N);
+    return OM_ERR_ARG;
+  }
   const int N = (int)h->N;
   const int G = om_grid(N, 256);
   if (!h->nbr_ptr) CUDA_TRY(om_malloc(h, &h->nbr_ptr, sizeof(int) * (N + 1)));
