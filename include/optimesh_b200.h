@@ -120,6 +120,13 @@ int om_project(om_handle* h, int32_t* sweeps);
 int om_run(om_handle* h, double tol, int64_t max_num_steps, int64_t* steps_done,
            om_step_stats* last);
 
+/* Synthetic workloads ("a randomly generated disk mesh", README.md:70-74): `rounds` times,
+ * every free vertex moves by a random vector of length <= amplitude/2 x its smallest
+ * incident inradius (no cell can invert), followed by flip-until-Delaunay.  Turns any valid
+ * flat mesh into a random Delaunay mesh of the same domain without leaving the device; the
+ * random numbers depend on (seed, round, caller vertex id) only.  2D meshes. */
+int om_random_walk(om_handle* h, int rounds, uint64_t seed, double amplitude, int64_t* n_flips);
+
 /* optimesh.get_new_points(mesh, method) (README.md:141): un-relaxed, un-limited target
  * positions, N x dim, caller numbering. */
 int om_new_points(om_handle* h, double* out_host);

@@ -454,7 +454,8 @@ int om_destroy(om_handle* h) {
   om_free(h, h->ring);
   om_free(h, h->dirty);
   om_free(h, h->dirty_epoch);
-  om_free(h, h->over);
+  om_free(h, h->diff2);
+  om_free(h, h->vflags);
   om_free(h, h->valid_epoch);
   om_free(h, h->band);
   om_free(h, h->band_mark);
@@ -578,6 +579,25 @@ int om_run(om_handle* h, double tol, int64_t max_num_steps, int64_t* steps_done,
   }
   if (steps_done) *steps_done = k;
   if (last) *last = st;
+  return OM_OK;
+}
+
+int om_random_walk(om_handle* h, int rounds, uint64_t seed, double amplitude, int64_t* n_flips) {
+  OM_ENTER(h);
+  if (rounds < 0 || !(amplitude > 0.0) || amplitude > 1.0) {
+    om_set_error("om_random_walk: rounds >= 0 and 0 < amplitude <= 1 expected");
+    return OM_ERR_ARG;
+  }
+  int64_t total = 0, nf = 0;
+  int32_t nr = 0, cap = 0;
+  OM_TRY(om_flip_impl(h, 0.0, 100, &nf, &nr, &cap));
+  total += nf;
+  for (int r = 0; r < rounds; r++) {
+    OM_TRY(om_random_move_impl(h, seed, r, amplitude));
+    OM_TRY(om_flip_impl(h, 0.0, 100, &nf, &nr, &cap));
+    total += nf;
+  }
+  if (n_flips) *n_flips = total;
   return OM_OK;
 }
 

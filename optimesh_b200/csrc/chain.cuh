@@ -1,0 +1,348 @@
+// The star of a vertex evaluated as a chain of SPOKES (shared by every step kernel).
+//
+// With P0 the vertex and n_0 .. n_{k-1} its one-ring in walk order, spoke q is
+// d_q = x[n_q] - P0 and cell q = (P0, n_q, n_{q+1}) lies between the spokes q and q+1.  In the
+// cell's local terms (A.1 with the vertex in slot 0) e2 = d_q, e1 = -d_{q+1}, so with
+//   L_q = d_q.d_q,  c_q = d_q.d_{q+1}:   ee2 = L_q, ee1 = L_{q+1}, ed0 = -c_q,
+//   ed1 = c_q - L_q (angle at n_q),  ed2 = c_q - L_{q+1} (angle at n_{q+1}),
+//   V4 = L_q L_{q+1} - c_q^2 = (2A)^2.
+// Every per-vertex sum of SURVEY.md A.4 / A.8 / A.9 is a combination of the two spokes of each
+// cell, hence regroups into ONE coefficient per spoke, fed by the two cells next to it:
+//   spoke q:  cH_q = t2(cell q) + t1(cell q-1),  cN_q = s2(cell q) + s1(cell q-1)
+//   W += L_q cH_q,   H += cH_q d_q d_q^T,   NUM += cN_q d_q.
+// cH_q is (minus twice) the Delaunay indicator s of the edge (v, n_q) (A.7), so the fused
+// check of the flip pass costs two more instructions per spoke.
+//
+// Cost per cell visit (2D, CVT block-diagonal, lazy limiter): 36 fp64 instructions -- one new
+// spoke (2 sub, 2 for L, 2 for c), V4 (2), one rsqrt (MUFU seed + 5), ed1/ed2 (2), three t (3),
+// w1 w2 (2), ws uu (2), s1 s2 (2), spoke coefficients (2), W (1), H (5), NUM (2), limiter bound
+// (2) -- against 46 in the cell-by-cell form (step.cu of round 1), and no operand selects:
+// the formulas are symmetric in the orientation of a cell, only the walk direction matters.
+// Scaling: rs = 1/sqrt(V4) = 1/(2A) is used as it comes; t'' = ed rs = 2 t (t = -ce, A.2),
+// w'' = 2 w, s'' = 4 s.  Constant factors are undone once per vertex (finish()).
+//
+// tests/chain_model.py restates this file in Python; tests/test_chain_model.py checks that
+// restatement against the oracle on the CPU.
+#pragma once
+#include "common.cuh"
+#include "geom.cuh"
+
+// method id of a chain that only tracks the step limiter (solve methods)
+#define OM_CHAIN_LIMITER_ONLY (-1)
+
+// 1/sqrt(x) for positive, normal x: hardware seed (rsqrt.approx.f64, relative error < 2^-22)
+// + ONE third-order step  e = 1 - x y^2,  y <- y (1 + e/2 + 3 e^2/8)   (remainder < 2^-67)
+__device__ __forceinline__ double fast_rsqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double e = fma(-x * y, y, 1.0);
+  const double p = fma(0.375, e, 0.5);
+  return fma(y * e, p, y);
+}
+
+// 1/x for normal x: hardware seed (rcp.approx.f64, < 2^-22) + two Newton steps (< 2^-80)
+__device__ __forceinline__ double fast_rcp(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  return fma(y, e, y);
+}
+
+// x is a positive, normal, finite double (integer pipe: the fp64 pipe is the busy one)
+__device__ __forceinline__ bool pos_normal(double x) {
+  return (unsigned)(__double2hiint(x) - 0x00100000) < 0x7fe00000u;
+}
+
+template <int D>
+__device__ __forceinline__ bool solve_sym(const double* H, double diag, const Vec<D>& rhs,
+                                          Vec<D>& out);
+template <>
+__device__ __forceinline__ bool solve_sym<2>(const double* H, double diag, const Vec<2>& rhs,
+                                             Vec<2>& out) {
+  const double a = diag - H[0], b = -H[1], d = diag - H[2];
+  const double det = fma(a, d, -b * b);
+  if (det == 0.0) return false;
+  const double inv = fast_rcp(det);
+  out.v[0] = fma(d, rhs.v[0], -b * rhs.v[1]) * inv;
+  out.v[1] = fma(a, rhs.v[1], -b * rhs.v[0]) * inv;
+  return true;
+}
+template <>
+__device__ __forceinline__ bool solve_sym<3>(const double* H, double diag, const Vec<3>& rhs,
+                                             Vec<3>& out) {
+  const double a = diag - H[0], b = -H[1], c = -H[2], d = diag - H[3], e = -H[4],
+               f = diag - H[5];
+  const double c00 = d * f - e * e, c01 = c * e - b * f, c02 = b * e - c * d;
+  const double det = a * c00 + b * c01 + c * c02;
+  if (det == 0.0) return false;
+  const double inv = 1.0 / det;
+  const double c11 = a * f - c * c, c12 = b * c - a * e, c22 = a * d - b * b;
+  out.v[0] = (c00 * rhs.v[0] + c01 * rhs.v[1] + c02 * rhs.v[2]) * inv;
+  out.v[1] = (c01 * rhs.v[0] + c11 * rhs.v[1] + c12 * rhs.v[2]) * inv;
+  out.v[2] = (c02 * rhs.v[0] + c12 * rhs.v[1] + c22 * rhs.v[2]) * inv;
+  return true;
+}
+
+// EXACT: track the smallest incident inradius (as the fraction 2A / perimeter);
+// otherwise only a division-free lower bound of it (smallest V4, largest half sum of the
+// squared edges, both as high words).  CHECK: collect the spokes that may violate the
+// Delaunay criterion (bit q of `flags`).
+template <int D, int METHOD, bool EXACT, bool CHECK>
+struct Chain {
+  static constexpr bool LLOYD_LIKE = METHOD == OM_LLOYD || METHOD == OM_CVT_BLOCK_DIAGONAL;
+  static constexpr bool CVT = METHOD == OM_CVT_BLOCK_DIAGONAL;
+  static constexpr bool CPT = METHOD == OM_CPT_FIXED_POINT;
+  static constexpr bool ODT = METHOD == OM_ODT_FIXED_POINT || METHOD == OM_ODT_DP_FP;
+  static constexpr bool DP = METHOD == OM_ODT_DP_FP;
+  static constexpr bool NONE = METHOD == OM_CHAIN_LIMITER_ONLY;
+  static constexpr bool NEED_T = LLOYD_LIKE || ODT || CHECK;
+  static constexpr int NH = D * (D + 1) / 2;
+
+  Vec<D> P0;
+  // accumulators (scaled, see the header)
+  double W;
+  Vec<D> NUM;
+  double H[NH];
+  // limiter
+  double rn, rd;          // EXACT: 2A and perimeter of the cell with the smallest inradius
+  int minv4_hi, maxsh_hi; // lazy bound
+  // current spoke (the second spoke of the last cell) and what that cell leaves for it
+  Vec<D> dq;
+  double Lq, lenq;
+  double t1p, s1p;
+  // what cell 0 leaves for spoke 0 (closed fans finish it last)
+  double t2_0, s2_0;
+  unsigned flags;
+  int q;      // cells done
+  int err;
+
+  __device__ __forceinline__ void init(const Vec<D>& p0) {
+    P0 = p0;
+    W = 0.0;
+#pragma unroll
+    for (int k = 0; k < D; k++) NUM.v[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < NH; k++) H[k] = 0.0;
+    rn = INFINITY;
+    rd = 1.0;
+    minv4_hi = 0x7ff00000;
+    maxsh_hi = 0;
+    t1p = s1p = t2_0 = s2_0 = 0.0;
+    lenq = 0.0;
+    flags = 0u;
+    q = 0;
+    err = 0;
+  }
+
+  __device__ __forceinline__ void spoke(const Vec<D>& P, Vec<D>& d, double& L, double& len) {
+    d = vsub<D>(P, P0);
+    L = vdot<D>(d, d);
+    if (EXACT) len = L * fast_rsqrt(L);
+  }
+
+  // first spoke of the chain
+  __device__ __forceinline__ void start(const Vec<D>& P) { spoke(P, dq, Lq, lenq); }
+
+  // adds what the two cells next to spoke `d` leave for it
+  __device__ __forceinline__ void finish_spoke(const Vec<D>& d, double L, double t2, double s2,
+                                               double t1, double s1, int bit, bool interior) {
+    if (!NONE) {
+      const double cN = s2 + s1;
+#pragma unroll
+      for (int k = 0; k < D; k++) NUM.v[k] = fma(cN, d.v[k], NUM.v[k]);
+    }
+    if (LLOYD_LIKE || CHECK) {
+      const double cH = t2 + t1;
+      if (LLOYD_LIKE) W = fma(L, cH, W);
+      if (CVT) {
+        Vec<D> a;
+#pragma unroll
+        for (int k = 0; k < D; k++) a.v[k] = cH * d.v[k];
+        int qi = 0;
+#pragma unroll
+        for (int i = 0; i < D; i++)
+#pragma unroll
+          for (int j = i; j < D; j++) {
+            H[qi] = fma(a.v[i], d.v[j], H[qi]);
+            qi++;
+          }
+      }
+      if (CHECK && interior) {
+        // s = ce + ce' < 0  <=>  cH > 0; everything within rounding of it is kept (sign bit
+        // clear also catches +0 and NaN); the flip pass decides on the exact s
+        const double g = fma(1.0e-9, fabs(t2) + fabs(t1), cH);
+        if (__double2hiint(g) >= 0) flags |= 1u << bit;
+      }
+    }
+  }
+
+  // The cell between the current spoke and the spoke dn.  bary: ODT methods, the cell has a
+  // boundary edge and contributes its barycenter.  Leaves what the cell gives to its two
+  // spokes: (t2, s2) to the current one, (t1, s1) to dn.
+  __device__ __forceinline__ void cell(const Vec<D>& dn, double Ln, double lenn, bool bary,
+                                       double& t1, double& t2, double& s1, double& s2,
+                                       bool& masked) {
+    masked = false;
+    const double c = vdot<D>(dq, dn);
+    const double V4 = fma(Lq, Ln, -c * c);
+    // a degenerate cell raises the error and the step is abandoned by the host: no need to
+    // keep its garbage (NaN at worst) out of the sums
+    if (!pos_normal(V4)) err |= OM_DEV_DEGENERATE;
+    const double rs = fast_rsqrt(V4);  // 1 / (2A)
+    const double Ls = Lq + Ln;
+    if (EXACT) {
+      // inradius 2A / (l0 + l1 + l2), compared as fractions (no division per cell)
+      const double A2 = V4 * rs;
+      const double ee0 = fma(-2.0, c, Ls);
+      const double per = (lenq + lenn) + ee0 * fast_rsqrt(ee0);
+      if (__double_as_longlong(A2 * rd) < __double_as_longlong(rn * per)) {
+        rn = A2;
+        rd = per;
+      }
+    } else {
+      // r_in^2 >= V4 / (6 Sh) with Sh = (ee0 + ee1 + ee2) / 2: keep the smallest V4 and the
+      // largest Sh of the star as high words (rounded the safe way in proves_unlimited())
+      minv4_hi = min(minv4_hi, __double2hiint(V4));
+      maxsh_hi = max(maxsh_hi, __double2hiint(Ls - c));
+    }
+    if (NEED_T) {
+      const double T1 = (c - Lq) * rs, T2 = (c - Ln) * rs;  // 2 t: angles at n_q, n_{q+1}
+      if (LLOYD_LIKE) {
+        const double T0 = -c * rs;
+        // cell masked (an angle > 135 deg): some t > 1/2, i.e. some T > 1
+        const int hmax = max(max(__double2hiint(T0), __double2hiint(T1)), __double2hiint(T2));
+        if (hmax >= 0x3ff00000 && (T0 > 1.0 || T1 > 1.0 || T2 > 1.0)) {
+          masked = true;
+          t1 = t2 = s1 = s2 = 0.0;
+        } else {
+          const double w1 = Ln * T1, w2 = Lq * T2;
+          const double uu = rs * (w1 + w2);
+          t1 = T1;
+          t2 = T2;
+          s2 = fma(-uu, w1, w2);
+          s1 = fma(-uu, w2, w1);
+        }
+      } else if (ODT) {
+        W += DP ? 1.0 : V4 * rs;
+        if (bary) {
+          s1 = s2 = DP ? 1.0 : V4 * rs;
+        } else {
+          const double f = DP ? -1.5 * rs : -1.5;
+          s2 = f * (Ln * T1);
+          s1 = f * (Lq * T2);
+        }
+        t1 = T1;
+        t2 = T2;
+      } else if (CPT) {
+        const double A2 = V4 * rs;
+        W += A2;
+        s1 = s2 = A2;
+        t1 = T1;
+        t2 = T2;
+      } else {
+        s1 = s2 = 0.0;
+        t1 = T1;
+        t2 = T2;
+      }
+    } else if (CPT) {
+      const double A2 = V4 * rs;
+      W += A2;
+      s1 = s2 = A2;
+      t1 = t2 = 0.0;
+    } else {
+      t1 = t2 = s1 = s2 = 0.0;
+    }
+  }
+
+  // second spoke of the chain: the first cell.  first_spoke_interior: closed fan (spoke 0 is
+  // finished by close()); otherwise spoke 0 is a boundary edge with this cell only.
+  __device__ __forceinline__ void first(const Vec<D>& P, bool bary, bool first_spoke_interior) {
+    Vec<D> dn;
+    double Ln, lenn = 0.0, t1, t2, s1, s2;
+    bool masked;
+    spoke(P, dn, Ln, lenn);
+    cell(dn, Ln, lenn, bary, t1, t2, s1, s2, masked);
+    if (CHECK && masked) flags |= 3u;  // both spokes of a masked cell are suspicious
+    t2_0 = t2;
+    s2_0 = s2;
+    if (!first_spoke_interior) finish_spoke(dq, Lq, t2, s2, 0.0, 0.0, 0, false);
+    t1p = t1;
+    s1p = s1;
+    dq = dn;
+    Lq = Ln;
+    lenq = lenn;
+    q = 1;
+  }
+
+  // next spoke of the chain: processes the cell between the current spoke and P
+  __device__ __forceinline__ void next(const Vec<D>& P, bool bary) {
+    Vec<D> dn;
+    double Ln, lenn = 0.0, t1, t2, s1, s2;
+    bool masked;
+    spoke(P, dn, Ln, lenn);
+    cell(dn, Ln, lenn, bary, t1, t2, s1, s2, masked);
+    if (CHECK && masked) flags |= 3u << q;
+    finish_spoke(dq, Lq, t2, s2, t1p, s1p, q, true);
+    t1p = t1;
+    s1p = s1;
+    dq = dn;
+    Lq = Ln;
+    lenq = lenn;
+    q++;
+  }
+
+  // closed fan: the cell between the last spoke and the first one (P = first ring vertex)
+  __device__ __forceinline__ void close(const Vec<D>& P, bool bary) {
+    Vec<D> dn;
+    double Ln, lenn = 0.0, t1, t2, s1, s2;
+    bool masked;
+    spoke(P, dn, Ln, lenn);
+    cell(dn, Ln, lenn, bary, t1, t2, s1, s2, masked);
+    if (CHECK && masked) flags |= (1u << q) | 1u;
+    finish_spoke(dq, Lq, t2, s2, t1p, s1p, q, true);
+    finish_spoke(dn, Ln, t2_0, s2_0, t1, s1, 0, true);
+    q++;
+  }
+
+  // open fan: the last spoke is a boundary edge with the last cell only
+  __device__ __forceinline__ void end_open() { finish_spoke(dq, Lq, 0.0, 0.0, t1p, s1p, q, false); }
+
+  // offset of the un-relaxed target from the vertex; false: 0/0 (every cell masked) or a
+  // singular block -- the vertex stays where it is
+  __device__ __forceinline__ bool target_offset(Vec<D>& d) const {
+    if (NONE) return false;
+    if (W == 0.0) return false;
+    if (CVT) {
+      // (2 cv I + Hess) d = -2 cv (x - c)  <=>  (W I - H) d = NUM / 6 in the scaled sums
+      Vec<D> rhs;
+#pragma unroll
+      for (int k = 0; k < D; k++) rhs.v[k] = NUM.v[k] * (1.0 / 6.0);
+      return solve_sym<D>(H, W, rhs, d);
+    }
+    const double inv = fast_rcp((LLOYD_LIKE ? 6.0 : 3.0) * W);
+#pragma unroll
+    for (int k = 0; k < D; k++) d.v[k] = NUM.v[k] * inv;
+    return true;
+  }
+
+  // lazy limiter: true if |d|^2 = diff2 provably stays below (r_in / 2)^2 for every cell
+  __device__ __forceinline__ bool proves_unlimited(double diff2) const {
+    // high words rounded the safe way: V4 down, Sh up
+    const double v4 = __hiloint2double(minv4_hi, 0);
+    const double sh = __hiloint2double(maxsh_hi + 1, 0);
+    return 24.0 * diff2 * sh <= v4;
+  }
+
+  // exact limiter: scales d if it is longer than half the smallest incident inradius
+  __device__ __forceinline__ bool limit(Vec<D>& d, double diff2) const {
+    // |d| > rn / (2 rd)  <=>  4 diff2 rd^2 > rn^2
+    const double lhs = 4.0 * diff2 * rd * rd, rhs = rn * rn;
+    if (!(lhs > rhs)) return false;
+    const double s = 0.5 * rn / (rd * sqrt(diff2));
+#pragma unroll
+    for (int k = 0; k < D; k++) d.v[k] *= s;
+    return true;
+  }
+};

@@ -81,7 +81,8 @@ struct om_handle {
   int* dirty = nullptr;      // N: vertices touched by flips (ring rows to rebuild)
   int* dirty_epoch = nullptr;// N: dedupe stamps for `dirty`
   int dirty_pass = 0;
-  int* over = nullptr;       // N: vertices the ring-row kernel left to the walk kernel
+  double* diff2 = nullptr;   // N: |diff|^2 of the last point update, sign bit = limited
+  unsigned short* vflags = nullptr;  // N (+pad): per-vertex flag words between step kernels
   bool use_rings = true;
   int* perm = nullptr;       // internal -> caller vertex id (nullptr: identity)
   int* inv_perm = nullptr;   // caller -> internal
@@ -199,8 +200,12 @@ int om_update_points_impl(om_handle* h, double tol, om_step_stats* out, bool tar
                           double* target_out, bool defer_fetch = false);
 void om_step_stats_from_scalars(om_handle* h, double tol, om_step_stats* out);
 int om_project_impl(om_handle* h, int32_t* sweeps);
+int om_random_move_impl(om_handle* h, uint64_t seed, int round, double amplitude);
 int om_commit_points_impl(om_handle* h);
-int om_rebuild_rings(om_handle* h, bool all);
+int om_rebuild_rings(om_handle* h, bool all, bool device = false);
+int om_launch_point_update(om_handle* h, double* out, bool check);
+int om_launch_reduce_stats(om_handle* h);
+int om_launch_fixup(om_handle* h, double* out);
 // pcg.cu
 int om_pcg_impl(om_handle* h, double rtol, int max_iter, int32_t* iters, double* relres,
                 double* out /* N*PD, may alias h->xnew */);

@@ -362,7 +362,10 @@ int om_setup_mesh(om_handle* h, const double* points_dev, const void* cells_dev,
     CUDA_TRY(om_malloc(h, &h->ring, sizeof(int) * OM_RING_W * N));
     CUDA_TRY(om_malloc(h, &h->dirty, sizeof(int) * N));
     CUDA_TRY(om_malloc(h, &h->dirty_epoch, sizeof(int) * N));
-    CUDA_TRY(om_malloc(h, &h->over, sizeof(int) * N));
+    CUDA_TRY(om_malloc(h, &h->diff2, sizeof(double) * N));
+    CUDA_TRY(om_malloc(h, &h->vflags, sizeof(unsigned short) * (N + 16)));
+    CUDA_TRY(cudaMemsetAsync(h->diff2, 0, sizeof(double) * N, h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->vflags, 0, sizeof(unsigned short) * (N + 16), h->stream));
     CUDA_TRY(cudaMemsetAsync(h->dirty_epoch, 0, sizeof(int) * N, h->stream));
     OM_TRY(om_rebuild_rings(h, true));
   }

@@ -1,197 +1,149 @@
-// K1: the fused smoothing step.  One thread per vertex walks the vertex star through the
-// half-edge twin table (a deterministic vertex-centric gather: no atomics on coordinates),
-// recomputes the fp64 geometry of every incident cell, applies the method formula, pins the
-// boundary, relaxes with omega, limits the step to half the smallest incident inradius and
-// writes the new position -- one pass over the mesh per step.
+// K1: the fused smoothing step.
 //
-// Replaces, per step: get_new_points of the five methods
+// Replaces, per step: get_new_points of the fixed-point methods
 // (/root/reference/README.md:80, :90, :104, :141), the numpy scatter-adds
 // (np.bincount / np.add.at / np.minimum.at) and the body of the optimize() loop
-// (README.md:131-132).  Arithmetic: SURVEY.md Appendix A.2-A.5, A.8, A.9.
+// (README.md:131-132).  Arithmetic: SURVEY.md Appendix A.2-A.5, A.8, A.9, regrouped per spoke
+// (chain.cuh).
 //
-// Instruction budget (ncu: the kernel is bound by instruction issue -- 70 % of the issue slots
-// busy, fp64 pipe 47 % -- not by HBM): one rsqrt per cell
-// visit and no division -- 1/(4A) = rsqrt(16 A^2), the circumcentre weights use
-// sum_k ee_k ed_k = -8 A^2, thirds are applied once per vertex.  The inradius (3 sqrt +
-// 1 div per cell) is only needed where the limiter bites, so the LAZY variant first tests
-// the division-free bound r_in^2 >= 4 A^2 / (3 sum ee) and re-walks the star exactly only
-// for vertices that fail it; both variants produce identical bits.
+//   k_step_ring  one thread per vertex of [lo, hi): the one-ring comes from the vertex's ring
+//                row (8 neighbour ids in walk order), the ring coordinates are staged in
+//                shared memory by cp.async (all in flight at once, slot [q][thread]: conflict
+//                free, every thread reads only what it staged -- no barrier anywhere in the
+//                kernel), the star is evaluated as a chain of spokes, then method formula,
+//                pin, omega, limiter, write.  Per vertex it leaves |diff|^2 (sign bit = "was
+//                limited") in `diff2` and, where something is left to do, a flag word:
+//                bit 8 "update me in k_post" (no ring row: more than 8 cells; or the lazy
+//                limiter bound failed), bits 0-7 "spoke q may violate the Delaunay criterion",
+//                bit 9 "check all my spokes" (fused check of the flip pass, CHECK variants).
+//   k_post       scans the flag words, compacts the flagged vertices block by block and
+//                updates them by a star walk over the twin table with the exact limiter.
+//   k_walk_list  the same walk for an explicit vertex list (vertices whose star was changed
+//                by flips: the pipelined loop recomputes them, flip.cu).
+//   k_reduce_stats  max |diff|^2 and the number of limited vertices from `diff2`.
+// No kernel on this path uses an atomic on coordinates or a floating-point atomic: every sum
+// runs in walk order, which is a function of the mesh only (bitwise reproducible).
 #include <cstring>
 #include <utility>
 
+#include "chain.cuh"
 #include "common.cuh"
 #include "geom.cuh"
 
 // tuning knobs of the ring-row step kernel
-#ifndef OM_K1_UNROLL
-#define OM_K1_UNROLL 2
+#ifndef OM_K1_BLOCK
+#define OM_K1_BLOCK 128
 #endif
 #ifndef OM_K1_MINB
 #define OM_K1_MINB 8
 #endif
+#ifndef OM_K1_UNROLL
+#define OM_K1_UNROLL 2
+#endif
+#ifndef OM_K1_MINB_EXACT
+#define OM_K1_MINB_EXACT 6
+#endif
 
 namespace {
 
+constexpr int MAX_RING = 4096;
 constexpr int K1_UNROLL = OM_K1_UNROLL;
 
-// Per-vertex accumulators, kept in SCALED units so that constant factors are applied once
-// per vertex instead of once per cell visit (q = 1/(4A), t_k = ed_k q = -ce_k,
-// w_k = ee_k t_k = -4 part_k):
-//   Lloyd/CVT:  w   = sum (w_1 + w_2)               = -4 cv
-//               num = sum s2' e2 - s1' e1           = -12 cv (centroid - x)
-//               H   = sum t_1 e1 e1^T + t_2 e2 e2^T = 2 x (CVT Hessian block without 2 cv I)
-//   CPT/ODT:    w = sum A, num = 3 sum A (r_c - x)
+// ---- ring rows: the one-ring of a free interior vertex as OM_RING_W neighbour vertex ids in
+// walk order.  Entry q < k holds n_q | (b_q << 29) where b_q says that cell q = (v, n_q,
+// n_{q+1}) has a boundary edge (ODT uses its barycenter); bit 30 of the entries 0..2 holds
+// the three bits of k - 1 (3 <= k <= 8 cells); unused entries hold v itself, so that the
+// staging copy of all eight entries is unconditional.  Entry 0 < 0 marks a vertex without a
+// row: RING_WALK (free vertex with more than OM_RING_W cells: k_post walks its star),
+// RING_FIXED (pinned or boundary vertex with cells), RING_ORPHAN (no cell).
+constexpr int RING_BCELL = 1 << 29;
+constexpr int RING_KBIT = 1 << 30;
+constexpr int RING_MASK = RING_BCELL - 1;
+constexpr int RING_WALK = -2, RING_FIXED = -3, RING_ORPHAN = -4;
+
+// flag word of a vertex (om_handle::vflags)
+constexpr unsigned VF_SPOKES = 0xffu, VF_DEFER = 0x100u, VF_CHECKALL = 0x200u;
+
 template <int D>
-struct Acc {
-  double w;
-  Vec<D> num;
-  double H[D * (D + 1) / 2];  // upper triangle
-  double rmin;                // EXACT: smallest incident inradius
-  double lb_num, lb_den;      // LAZY: cell minimising A^2 / (sum(ee)/2) (kept as a fraction)
-};
-
-// 1/sqrt(x) for positive, normal x (the caller has checked x > 0): hardware seed
-// (rsqrt.approx.f64, relative error < 2^-22) + ONE third-order step
-//   e = 1 - x y^2,  y <- y (1 + e/2 + 3 e^2/8)        (remainder 5 e^3/16 < 2^-67)
-// -- five fp64 instructions instead of the seven of two Newton steps (the kernel is bound by
-// instruction issue: every instruction saved counts, whatever its pipe).
-__device__ __forceinline__ double fast_rsqrt(double x) {
-  double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  const double e = fma(-x * y, y, 1.0);
-  const double p = fma(0.375, e, 0.5);
-  return fma(y * e, p, y);
+__host__ __device__ constexpr int step_block() {
+  return OM_K1_BLOCK;
 }
 
-// t > 0.5 on the integer pipe (exact: compares the bit pattern with that of 0.5)
-__device__ __forceinline__ bool gt_half(double t) {
-  // as one 64-bit integer compare: t > 0.5  <=>  bits(t) > bits(0.5) for every non-NaN t
-  // (negative t have the sign bit set, i.e. are negative as signed integers)
-  return __double_as_longlong(t) > 0x3fe0000000000000ll;
-}
-
-// a < b for non-negative doubles (or +inf) on the integer pipe: their order is the order of
-// their bit patterns
-__device__ __forceinline__ bool lt_nonneg(double a, double b) {
-  return __double_as_longlong(a) < __double_as_longlong(b);
-}
-
-// exact inradius of one cell (A.3): 2A / (l0 + l1 + l2)
-template <int D>
-__device__ __forceinline__ double inradius(const CellGeo<D>& g) {
-  const double A = sqrt(g.vol2);
-  return 2.0 * A / (sqrt(g.ee0) + sqrt(g.ee1) + sqrt(g.ee2));
-}
-
-// Contribution of one incident cell to vertex P0 (P1, P2 follow in slot order).
-// Only the two edges at the vertex are formed (e1 = P0 - P2, e2 = P1 - P0); since
-// e0 + e1 + e2 = 0 every other product follows from ee1, ee2 and ed0 = e1.e2:
-//   ed1 = -(ed0 + ee2), ed2 = -(ed0 + ee1), ee0 = ee1 + ee2 + 2 ed0, A^2 = (ee1 ee2 - ed0^2)/4.
-// bary: ODT methods only -- the cell has a boundary edge and contributes its barycenter
-// instead of its circumcenter (which may lie outside the domain there).
-template <int D, int METHOD, bool EXACT>
-__device__ __forceinline__ void accumulate_cell(const Vec<D>& P0, const Vec<D>& P1,
-                                                const Vec<D>& P2, Acc<D>& a, int& err,
-                                                bool bary) {
-  const Vec<D> e1 = vsub<D>(P0, P2), e2 = vsub<D>(P1, P0);
-  const double ee1 = vdot<D>(e1, e1), ee2 = vdot<D>(e2, e2), ed0 = vdot<D>(e1, e2);
-  const double vol2 = 0.25 * fma(ee1, ee2, -ed0 * ed0);
-  if (!(vol2 > 0.0)) {
-    err |= OM_DEV_DEGENERATE;
-    return;
-  }
-  const double ed1 = -(ed0 + ee2), ed2 = -(ed0 + ee1);
-  if (EXACT) {
-    const double A = sqrt(vol2);
-    a.rmin = fmin(a.rmin, 2.0 * A / (sqrt(-(ed1 + ed2)) + sqrt(ee1) + sqrt(ee2)));  // ee0
-  } else {
-    const double Sh = ee2 - ed2;  // (ee0 + ee1 + ee2) / 2 = ee1 + ee2 + ed0
-    if (lt_nonneg(vol2 * a.lb_den, a.lb_num * Sh)) {
-      a.lb_num = vol2;
-      a.lb_den = Sh;
-    }
-  }
-  const double r = fast_rsqrt(vol2);  // 1/A
-  if (METHOD == OM_CPT_FIXED_POINT) {
-    // 3 (barycenter - P0) = e2 - e1
-    const double A = vol2 * r;
-    a.w += A;
+template <bool LIST>
+__global__ void __launch_bounds__(256)
+    k_build_rings(const int4* __restrict__ cells, const int* __restrict__ adj,
+                  const int* __restrict__ v2c, const uint8_t* __restrict__ bflag, int n,
+                  const int* __restrict__ list, const int* __restrict__ n_dev,
+                  int* __restrict__ ring, int lo, int hi) {
+  if (n_dev) n = *n_dev;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int v = LIST ? list[i] : i;
+    if (v < lo || v >= hi) continue;  // partitioned run: only the own range's rows are read
+    int e[OM_RING_W];
 #pragma unroll
-    for (int k = 0; k < D; k++) a.num.v[k] += A * (e2.v[k] - e1.v[k]);
-    return;
-  }
-  if (METHOD == OM_ODT_FIXED_POINT || METHOD == OM_ODT_DP_FP) {
-    // volume averaged: weight A = vol2 r; count averaged (density preserving): weight 1
-    // 3 (circumcenter - P0) = 3 (al1 e2 - al2 e1), al_k = ee_k ed_k / (-8 A^2)
-    const bool dp = METHOD == OM_ODT_DP_FP;
-    const double A = vol2 * r;
-    a.w += dp ? 1.0 : A;
-    const double f = -0.375 * r * (dp ? r : 1.0);
-    const double wb = dp ? 1.0 : A;  // barycenter: 3 (b - P0) = e2 - e1
-    const double s2 = bary ? wb : ee1 * ed1 * f, s1 = bary ? wb : ee2 * ed2 * f;
+    for (int q = 0; q < OM_RING_W; q++) e[q] = v;
+    int marker = RING_ORPHAN;
+    const int c0 = v2c[v];
+    if (c0 != OM_NONE_CELL) {
+      marker = RING_FIXED;
+      if (!bflag[v]) {
+        marker = RING_WALK;
+        const int4 cell0 = __ldg(cells + c0);
+        const int j = slot_of(cell0, v);
+        if (j >= 0) {
+          int k = 0;  // cells closed so far
+          int last = cell_get(cell0, (j + 2) % 3);
+          e[0] = cell_get(cell0, (j + 1) % 3);  // cell 0 = (v, n0, n1)
+          int cur = c0, kexit = (j + 1) % 3;
+          bool ok = true;
+          while (true) {
+            // twin row of cell k (`cur`): the exit edge, and whether it has a boundary edge
+            const int4 ta = __ldg(reinterpret_cast<const int4*>(adj) + cur);
+            if (ta.x < 0 || ta.y < 0 || ta.z < 0) {
 #pragma unroll
-    for (int k = 0; k < D; k++) a.num.v[k] = fma(s2, e2.v[k], fma(-s1, e1.v[k], a.num.v[k]));
-    return;
-  }
-  // Lloyd / CVT block-diagonal (A.4, A.9), scaled as described at Acc
-  const double q = 0.25 * r;
-  const double t0 = ed0 * q, t1 = ed1 * q, t2 = ed2 * q;  // -ce_k
-  if (gt_half(t0) | gt_half(t1) | gt_half(t2)) return;  // cell masked (an angle > 135 deg)
-  const double w1 = ee1 * t1, w2 = ee2 * t2;  // -4 part_k
-  const double ws = w1 + w2;
-  a.w += ws;
-  // al_k = ee_k ed_k (-1/(8A^2)) = -2 q w_k;  -12 x [part1 (cc - e1/2) + part2 (cc + e2/2)]
-  //   = e2 (u w1 + w2/2 ... ) with u = -2 q ws:  s2' = u w1 - 0.5 w2 ... (signs folded below)
-  const double u = -2.0 * q * ws;
-  const double s2 = fma(u, w1, 0.5 * w2), s1 = fma(u, w2, 0.5 * w1);
-  // accumulated by fma chains: two fp64 instructions per component instead of three
+              for (int q = 0; q < OM_RING_W; q++)
+                if (q == k) e[q] |= RING_BCELL;
+            }
+            k++;
+            const int t = cell_get(ta, kexit);
+            if (t < 0) {  // open fan (cannot happen for a vertex that is not on the boundary)
+              ok = false;
+              break;
+            }
+            const int cn = t >> 2, kn = t & 3;
+            if (cn == c0) break;  // closed: the vertex opposite the entry edge is n0 again
+            if (k >= OM_RING_W) {
+              ok = false;
+              break;
+            }
+            const int4 cl = __ldg(cells + cn);
+            const int jn = slot_of(cl, v);
+            if (jn < 0 || jn == kn) {
+              ok = false;
+              break;
+            }
 #pragma unroll
-  for (int k = 0; k < D; k++) a.num.v[k] = fma(s2, e2.v[k], fma(-s1, e1.v[k], a.num.v[k]));
-  if (METHOD == OM_CVT_BLOCK_DIAGONAL) {
-    Vec<D> a1, a2;
-#pragma unroll
-    for (int k = 0; k < D; k++) {
-      a1.v[k] = t1 * e1.v[k];
-      a2.v[k] = t2 * e2.v[k];
-    }
-    int qi = 0;
-#pragma unroll
-    for (int i = 0; i < D; i++)
-#pragma unroll
-      for (int j = i; j < D; j++) {
-        a.H[qi] = fma(a1.v[i], e1.v[j], fma(a2.v[i], e2.v[j], a.H[qi]));
-        qi++;
+            for (int q = 1; q < OM_RING_W; q++)
+              if (q == k) e[q] = last;
+            last = cell_get(cl, kn);  // the vertex opposite the edge we came through
+            cur = cn;
+            kexit = 3 - jn - kn;
+          }
+          if (ok && k >= 3) {
+            marker = 0;
+            const int km = k - 1;
+            e[0] |= (km & 1) ? RING_KBIT : 0;
+            e[1] |= (km & 2) ? RING_KBIT : 0;
+            e[2] |= (km & 4) ? RING_KBIT : 0;
+          }
+        }
       }
+    }
+    if (marker) e[0] = marker;
+    int4* out = reinterpret_cast<int4*>(ring + (size_t)OM_RING_W * v);
+    out[0] = make_int4(e[0], e[1], e[2], e[3]);
+    out[1] = make_int4(e[4], e[5], e[6], e[7]);
   }
-}
-
-template <int D>
-__device__ __forceinline__ bool solve_sym(const double* H, double diag, const Vec<D>& rhs,
-                                          Vec<D>& out);
-template <>
-__device__ __forceinline__ bool solve_sym<2>(const double* H, double diag, const Vec<2>& rhs,
-                                             Vec<2>& out) {
-  const double a = H[0] + diag, b = H[1], d = H[2] + diag;
-  const double det = a * d - b * b;
-  if (det == 0.0) return false;
-  const double inv = 1.0 / det;
-  out.v[0] = (d * rhs.v[0] - b * rhs.v[1]) * inv;
-  out.v[1] = (a * rhs.v[1] - b * rhs.v[0]) * inv;
-  return true;
-}
-template <>
-__device__ __forceinline__ bool solve_sym<3>(const double* H, double diag, const Vec<3>& rhs,
-                                             Vec<3>& out) {
-  const double a = H[0] + diag, b = H[1], c = H[2], d = H[3] + diag, e = H[4], f = H[5] + diag;
-  const double c00 = d * f - e * e, c01 = c * e - b * f, c02 = b * e - c * d;
-  const double det = a * c00 + b * c01 + c * c02;
-  if (det == 0.0) return false;
-  const double inv = 1.0 / det;
-  const double c11 = a * f - c * c, c12 = b * c - a * e, c22 = a * d - b * b;
-  out.v[0] = (c00 * rhs.v[0] + c01 * rhs.v[1] + c02 * rhs.v[2]) * inv;
-  out.v[1] = (c01 * rhs.v[0] + c11 * rhs.v[1] + c12 * rhs.v[2]) * inv;
-  out.v[2] = (c02 * rhs.v[0] + c12 * rhs.v[1] + c22 * rhs.v[2]) * inv;
-  return true;
 }
 
 struct StepParams {
@@ -201,8 +153,9 @@ struct StepParams {
   const int* adj;  // flat view of the int4 twin table: adj[4*c + k]
   const int* v2c;
   const uint8_t* bflag;
-  const int* ring;  // N x OM_RING_W ring rows, or nullptr
-  int* over;        // vertices the main launch leaves to the list-driven (SRC 2) launch
+  const int* ring;          // N x OM_RING_W ring rows
+  double* diff2;            // N: |omega (target - x)|^2, sign bit = limited
+  unsigned short* vflags;   // N: flag words (zero except between the kernels of one step)
   // partitioned coordinates: foreign vertices are only current if pinned or stamped by the
   // last band exchange (nullptr: everything is current)
   const int* valid_epoch;
@@ -215,469 +168,532 @@ struct StepParams {
   int lo, hi;  // vertices [lo, hi) are processed
   double omega;
   int limiter;
-  int odt_bary;  // ODT: cells with a boundary edge contribute their barycenter
+  int odt_bary;    // ODT: cells with a boundary edge contribute their barycenter
+  int force_walk;  // diagnostics (OM_NO_RINGS): every free vertex goes through k_post
   DevScalars* ds;
 };
 
-// Block-level reduction of the step statistics (up to 256 threads): one conditional atomic per
-// block on the shared scalars (max and integer add are order independent).
-__device__ __forceinline__ void reduce_step_stats(double diff2, int limited, DevScalars* ds) {
-  __shared__ double s_d[8];
-  __shared__ int s_l[8];
-  for (int o = 16; o > 0; o >>= 1) {
-    diff2 = fmax(diff2, __shfl_xor_sync(0xffffffffu, diff2, o));
-    limited += __shfl_xor_sync(0xffffffffu, limited, o);
-  }
-  if ((threadIdx.x & 31) == 0) {
-    s_d[threadIdx.x >> 5] = diff2;
-    s_l[threadIdx.x >> 5] = limited;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double d = s_d[0];
-    int l = s_l[0];
-    for (int w = 1; w < (int)(blockDim.x >> 5); w++) {
-      d = fmax(d, s_d[w]);
-      l += s_l[w];
+// ------------------------------------------------------------------ ring-row kernel
+// EXACT: exact inradius in this pass (most vertices limited: early steps); otherwise the
+// lazy bound, and the few vertices that fail it are left to k_post.  CHECK: also collect the
+// spokes that may violate the Delaunay criterion.  PART: coordinates are partitioned, every
+// foreign ring vertex is validated.
+template <int D, int METHOD, bool EXACT, bool CHECK, bool PART>
+__global__ void __launch_bounds__(OM_K1_BLOCK, (D == 2 ? (EXACT ? OM_K1_MINB_EXACT : OM_K1_MINB) : 4))
+    k_step_ring(StepParams p) {
+  constexpr int BLOCK = OM_K1_BLOCK;
+  constexpr int PER = (D == 2) ? 1 : 2;  // 16-byte pieces per vertex
+  constexpr bool ODT = METHOD == OM_ODT_FIXED_POINT || METHOD == OM_ODT_DP_FP;
+  __shared__ double2 ring_sm[OM_RING_W * PER * BLOCK];
+  const int v = p.lo + (int)(blockIdx.x * BLOCK + threadIdx.x);
+  if (v >= p.hi) return;
+  const int4* rp = reinterpret_cast<const int4*>(p.ring + (size_t)OM_RING_W * v);
+  const int4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+  const Vec<D> P0 = ld_point<D>(p.x, v);
+  if (r0.x < 0 || p.force_walk) {
+    if (r0.x == RING_WALK || (p.force_walk && r0.x >= 0)) {
+      // free vertex without a row: k_post updates it and checks its spokes
+      p.vflags[v] = (unsigned short)(VF_DEFER | (CHECK ? VF_CHECKALL : 0u));
+    } else {
+      st_point<D>(p.xout, v, P0);
+      p.diff2[v] = 0.0;
+      if (CHECK && r0.x == RING_FIXED) p.vflags[v] = (unsigned short)VF_CHECKALL;
     }
-    if (d > 0.0) {
-      const unsigned long long bits = (unsigned long long)__double_as_longlong(d);
-      if (bits > *(volatile unsigned long long*)&ds->max_diff2_bits)
-        atomicMax(&ds->max_diff2_bits, bits);
-    }
-    if (l) atomicAdd(&ds->n_limited, (unsigned long long)l);
+    return;
   }
-}
-
-constexpr int MAX_RING = 4096;
-
-// Visits every cell around vertex v, starting at cell c0 (where v sits in slot j) and
-// leaving through local edge (j+1)%3; an open fan (boundary vertex) is completed from the
-// start cell in the other direction.  f(P1, P2) receives the other two vertices of each
-// cell in slot order.  The visiting order depends only on the mesh, never on scheduling.
-// BC: f also receives "this cell has a boundary edge" (read from the cell's twin row).
-template <int D, bool BC = false, typename F>
-__device__ __forceinline__ void walk_star(const StepParams& p, int v, int c0, const int4& cell0,
-                                          int j, int& err, F&& f) {
-  auto has_boundary_edge = [&](int c) {
-    if (!BC) return false;
-    const int4 ta = __ldg(reinterpret_cast<const int4*>(p.adj) + c);
-    return ta.x < 0 || ta.y < 0 || ta.z < 0;
+  const int e[OM_RING_W] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+  const int k = 1 + ((e[0] >> 30) & 1) + ((e[1] >> 29) & 2) + ((e[2] >> 28) & 4);
+  unsigned bcells = 0u;
+#pragma unroll
+  for (int q = 0; q < OM_RING_W; q++) {
+    const unsigned u = (unsigned)e[q] & (unsigned)RING_MASK;
+    if (PART && q < k && !p.valid((int)u)) p.ds->stale = 1;  // caller refreshes and repeats
+    if (ODT) bcells |= ((unsigned)(e[q] >> 29) & 1u) << q;
+    const double2* src = reinterpret_cast<const double2*>(
+        reinterpret_cast<const char*>(p.x) + (unsigned long long)u * (16ull * PER));
+#pragma unroll
+    for (int h2 = 0; h2 < PER; h2++) {
+      const unsigned dst =
+          (unsigned)__cvta_generic_to_shared(&ring_sm[(q * PER + h2) * BLOCK + threadIdx.x]);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + h2));
+    }
+  }
+  asm volatile("cp.async.commit_group;");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  auto ld_ring = [&](int q) {
+    Vec<D> r;
+    const double2 a = ring_sm[(q * PER) * BLOCK + threadIdx.x];
+    r.v[0] = a.x;
+    r.v[1] = a.y;
+    if (D == 3) r.v[D - 1] = ring_sm[(q * PER + PER - 1) * BLOCK + threadIdx.x].x;
+    return r;
   };
-  if (!(p.valid(cell_get(cell0, (j + 1) % 3)) && p.valid(cell_get(cell0, (j + 2) % 3))))
-    p.ds->stale = 1;
-  f(ld_point<D>(p.x, cell_get(cell0, (j + 1) % 3)), ld_point<D>(p.x, cell_get(cell0, (j + 2) % 3)),
-    has_boundary_edge(c0));
-  bool closed = false;
-  for (int dir = 0; dir < 2 && !closed; dir++) {
-    int cur = c0;
-    int kexit = (j + 1 + dir) % 3;
-    int hops = 0;
-    while (true) {
-      const int t = __ldg(p.adj + 4 * (size_t)cur + kexit);
-      if (t < 0) break;  // boundary edge: open fan
-      const int cn = t >> 2, kn = t & 3;
-      if (cn == c0) {
-        closed = true;
-        break;
-      }
-      const int4 cl = __ldg(p.cells + cn);
-      const int jn = slot_of(cl, v);
-      if (jn < 0 || jn == kn || ++hops > MAX_RING) {
-        err |= OM_DEV_WALK;
-        closed = true;
-        break;
-      }
-      if (!(p.valid(cell_get(cl, (jn + 1) % 3)) && p.valid(cell_get(cl, (jn + 2) % 3))))
-        p.ds->stale = 1;
-      f(ld_point<D>(p.x, cell_get(cl, (jn + 1) % 3)), ld_point<D>(p.x, cell_get(cl, (jn + 2) % 3)),
-        has_boundary_edge(cn));
-      cur = cn;
-      kexit = 3 - jn - kn;
+  const bool odt_bary = ODT && p.odt_bary != 0;
+  Chain<D, METHOD, EXACT, CHECK> ch;
+  ch.init(P0);
+  ch.start(ld_ring(0));
+  ch.first(ld_ring(1), odt_bary && (bcells & 1u), true);
+#pragma unroll K1_UNROLL
+  for (int j = 2; j < k; j++) ch.next(ld_ring(j), odt_bary && ((bcells >> (j - 1)) & 1u));
+  ch.close(ld_ring(0), odt_bary && ((bcells >> (k - 1)) & 1u));
+
+  Vec<D> d;
+  Vec<D> out = P0;
+  double diff2 = 0.0;
+  bool deferred = false, limited = false;
+  if (ch.target_offset(d)) {
+#pragma unroll
+    for (int i = 0; i < D; i++) d.v[i] *= p.omega;
+    diff2 = vdot<D>(d, d);
+    if (p.limiter) {
+      if (EXACT)
+        limited = ch.limit(d, diff2);
+      else
+        deferred = !ch.proves_unlimited(diff2);
     }
+#pragma unroll
+    for (int i = 0; i < D; i++) out.v[i] = P0.v[i] + d.v[i];
   }
+  if (!deferred) {
+    st_point<D>(p.xout, v, out);
+    p.diff2[v] = limited ? -diff2 : diff2;
+  }
+  const unsigned f = (CHECK ? (ch.flags & VF_SPOKES) : 0u) | (deferred ? VF_DEFER : 0u);
+  if (f) p.vflags[v] = (unsigned short)f;
+  if (ch.err) atomicOr(&p.ds->err, ch.err);
 }
 
-// ---- ring rows: the one-ring of a vertex as (up to) OM_RING_W neighbour vertex ids
-// Entry q holds n_q | (f_q << 30); cell q of the star is (v, n_q, n_{q+1 mod k}) and f_q says
-// whether its slot order is (v, n_{q+1}, n_q) instead of (v, n_q, n_{q+1}).  Unused entries are
-// -1; entry 0 == -2 marks a vertex the kernel must walk instead (pinned/boundary vertex, open
-// fan, or more than OM_RING_W cells).  The order is the walk order, so the sums are
-// bit-identical to the walk; the rows only remove the dependent adj -> cell -> point chains.
-// threads per block of the step kernels (3D: smaller, its ring staging is twice as wide)
-// 128-thread blocks, 8 per SM: the same 1024 resident threads as 256 x 4, but a block retires as
-// soon as its four warps are done (measured: 0.461 ms against 0.470 ms; 64 x 16: 0.464 ms)
-#ifndef OM_K1_BLOCK
-#define OM_K1_BLOCK 128
-#endif
-template <int D>
-__host__ __device__ constexpr int step_block() {
-  return D == 2 ? OM_K1_BLOCK : 128;
-}
-constexpr int RING_FLAG = 1 << 30;   // cell q has slot order (v, n_{q+1}, n_q)
-constexpr int RING_BCELL = 1 << 29;  // cell q has a boundary edge (ODT uses its barycenter)
-constexpr int RING_MASK = RING_BCELL - 1;
-
-template <bool LIST>
-__global__ void __launch_bounds__(256)
-    k_build_rings(const int4* __restrict__ cells, const int* __restrict__ adj,
-                  const int* __restrict__ v2c, const uint8_t* __restrict__ bflag, int n,
-                  const int* __restrict__ list, int* __restrict__ ring, int lo, int hi) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int v = LIST ? list[i] : i;
-  if (v < lo || v >= hi) return;  // partitioned run: only the own range's rows are read
-  int e[OM_RING_W];
-#pragma unroll
-  for (int q = 0; q < OM_RING_W; q++) e[q] = -1;
-  bool ok = false;
-  const int c0 = v2c[v];
-  if (c0 != OM_NONE_CELL && !bflag[v]) {
-    const int4 cell0 = __ldg(cells + c0);
-    const int j = slot_of(cell0, v);
-    if (j >= 0) {
-      int k = 0;  // cells closed so far
-      int last = cell_get(cell0, (j + 2) % 3);
-      e[0] = cell_get(cell0, (j + 1) % 3);  // cell 0 = (v, n0, n1), slot order kept
-      int cur = c0, kexit = (j + 1) % 3;
-      ok = true;
+// ------------------------------------------------------------------ star walk
+// Updates one vertex by walking its star through the twin table, in the order the ring row
+// would list it (so a vertex gets the same bits whichever kernel updates it): closed fans start
+// at v2c[v]; open fans (boundary vertices: Lloyd targets only) are first rewound to one end.
+// TARGET: un-relaxed, un-limited target (get_new_points); otherwise the step with the exact
+// limiter.
+template <int D, int METHOD, bool TARGET>
+__device__ __forceinline__ void walk_vertex(const StepParams& p, int v, int& err) {
+  constexpr bool ODT = METHOD == OM_ODT_FIXED_POINT || METHOD == OM_ODT_DP_FP;
+  const Vec<D> P0 = ld_point<D>(p.x, v);
+  Vec<D> out = P0;
+  double diff2 = 0.0;
+  bool limited = false;
+  const int c0 = p.v2c[v];
+  const bool pinned = p.bflag[v] != 0;
+  // the Lloyd target of a boundary vertex is its real control-volume centroid; every other
+  // consumer pins boundary vertices
+  const bool move = (c0 != OM_NONE_CELL) && (!pinned || (TARGET && METHOD == OM_LLOYD));
+  if (move) {
+    int cur = c0;
+    int4 cl = __ldg(p.cells + cur);
+    int jc = slot_of(cl, v);
+    bool open = false, bad = jc < 0;
+    if (!bad && pinned) {
+      // rewind against the walk direction until a boundary edge (open) or back at c0 (closed)
+      int kexit = (jc + 2) % 3, hops = 0;
       while (true) {
-        // twin row of cell k (`cur`): the exit edge, and whether the cell has a boundary edge
-        const int4 ta = __ldg(reinterpret_cast<const int4*>(adj) + cur);
-        if (ta.x < 0 || ta.y < 0 || ta.z < 0) {
-#pragma unroll
-          for (int q = 0; q < OM_RING_W; q++)
-            if (q == k) e[q] |= RING_BCELL;
-        }
-        k++;
-        const int t = cell_get(ta, kexit);
-        if (t < 0) {  // open fan
-          ok = false;
+        const int t = __ldg(p.adj + 4 * (size_t)cur + kexit);
+        if (t < 0) {
+          open = true;
           break;
         }
         const int cn = t >> 2, kn = t & 3;
-        if (cn == c0) break;  // closed: `last` is n0 again
-        if (k >= OM_RING_W) {
-          ok = false;
+        if (cn == c0) {
+          cur = c0;
+          cl = __ldg(p.cells + cur);
+          jc = slot_of(cl, v);
           break;
         }
-        const int4 cl = __ldg(cells + cn);
-        const int jn = slot_of(cl, v);
-        if (jn < 0 || jn == kn) {
-          ok = false;
+        const int4 cln = __ldg(p.cells + cn);
+        const int jn = slot_of(cln, v);
+        if (jn < 0 || jn == kn || ++hops > MAX_RING) {
+          bad = true;
           break;
         }
-        const int p1 = cell_get(cl, (jn + 1) % 3), p2 = cell_get(cl, (jn + 2) % 3);
-        // cell k = (v, last, new): slot order (v, last, new) iff p1 == last
-        const int flag = (p1 == last) ? 0 : RING_FLAG;
-        const int nxt = (p1 == last) ? p2 : p1;
-#pragma unroll
-        for (int q = 1; q < OM_RING_W; q++)
-          if (q == k) e[q] = last | flag;
-        last = nxt;
         cur = cn;
+        cl = cln;
+        jc = jn;
         kexit = 3 - jn - kn;
       }
+      // open: the boundary edge of `cur` is opposite slot kexit; walk away from it
+      if (open) jc = jc | (kexit << 2);
     }
-  }
-  if (!ok) e[0] = -2;
-  int4* out = reinterpret_cast<int4*>(ring + (size_t)OM_RING_W * v);
-  out[0] = make_int4(e[0], e[1], e[2], e[3]);
-  out[1] = make_int4(e[4], e[5], e[6], e[7]);
-}
-
-// MODE 0: step, exact inradius in the main pass (most vertices limited: early steps)
-// MODE 1: step, lazy limiter (bound first, exact second pass only where needed)
-// MODE 2: write the un-relaxed, un-limited target (get_new_points)
-// SRC 0: vertices [lo, hi), one-ring from the ring rows; vertices without a row that must
-//        move are appended to p.over and left to a SRC 2 launch
-// SRC 1: vertices [lo, hi), star walk
-// SRC 2: vertices p.list[0 .. n_list), star walk
-template <int D, int METHOD, int MODE, int SRC>
-__global__ void __launch_bounds__(step_block<D>(), (D == 2 ? OM_K1_MINB : 3))
-    k_step(StepParams p) {
-  constexpr bool TARGET = MODE == 2;
-  constexpr bool EXACT = MODE == 0;
-  // SRC 2: the list and its length live on the device (written by the SRC 0/1 launch that
-  // precedes this one on the stream): block-stride loop, uniform trip count per block
-  const int n_list = SRC == 2 ? p.ds->n_over : 0;
-  for (int base = blockIdx.x * blockDim.x; SRC != 2 ? base == (int)(blockIdx.x * blockDim.x)
-                                                      : base < n_list;
-       base += gridDim.x * blockDim.x) {
-  const int i = base + threadIdx.x;
-  const bool active = SRC == 2 ? (i < n_list) : (p.lo + i < p.hi);
-  double diff2 = 0.0;
-  int limited = 0;
-  int err = 0;
-  bool deferred = false;  // left to the list-driven exact launch
-  int vdef = 0;
-  if (active) {
-    const int v = SRC == 2 ? p.over[i] : p.lo + i;
-    vdef = v;
-    const Vec<D> P0 = ld_point<D>(p.x, v);
-    Vec<D> out = P0;
-    const int c0 = p.v2c[v];
-    const bool pinned = p.bflag[v] != 0;
-    // the Lloyd target of a boundary vertex is its real control-volume centroid; every
-    // other consumer pins boundary vertices
-    bool walk = (c0 != OM_NONE_CELL) && (!pinned || (TARGET && METHOD == OM_LLOYD));
-
-    // SRC 0: the ring vertices are staged in shared memory by cp.async (one 16-byte copy
-    // per vertex in 2D, two in 3D; all in flight at once, no registers held), slot
-    // [q][thread] so that a warp's accesses are conflict free.  Every thread only reads the
-    // slots it filled itself: no block barrier is needed.
-    __shared__ double2 ring_sm[SRC == 0 ? OM_RING_W * (D == 2 ? 1 : 2) * step_block<D>() : 1];
-    int nring = 0;         // cells (= ring vertices) in the row
-    unsigned rflags = 0u;  // bit q: cell q has slot order (v, n_{q+1}, n_q)
-    unsigned bcells = 0u;  // bit q: cell q has a boundary edge (ODT methods only)
-    constexpr bool ODT = METHOD == OM_ODT_FIXED_POINT || METHOD == OM_ODT_DP_FP;
-    int4 cell = make_int4(0, 0, 0, 0);
-    int j = 0;
-    if (walk) {
-      if (SRC == 0) {
-        const int4* rp = reinterpret_cast<const int4*>(p.ring + (size_t)OM_RING_W * v);
-        const int4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
-        const int e[OM_RING_W] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-        if (e[0] == -2) {
-          // no row (more than OM_RING_W cells, or an open fan): the walk kernel does it
-          deferred = true;
-          walk = false;
-        } else {
-          constexpr int PER = (D == 2) ? 1 : 2;  // 16-byte pieces per vertex
-#pragma unroll
-          for (int q = 0; q < OM_RING_W; q++)
-            if (e[q] >= 0) {
-              if (!p.valid(e[q] & RING_MASK)) p.ds->stale = 1;  // caller refreshes and repeats
-              const double2* src =
-                  reinterpret_cast<const double2*>(p.x) + (size_t)PER * (e[q] & RING_MASK);
-#pragma unroll
-              for (int h2 = 0; h2 < PER; h2++) {
-                const unsigned dst = (unsigned)__cvta_generic_to_shared(
-                    &ring_sm[(q * PER + h2) * step_block<D>() + threadIdx.x]);
-                #ifdef OM_K1_CPASYNC_CG
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst),
-                             "l"(src + h2));
-#else
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst),
-                             "l"(src + h2));
-#endif
-              }
-              nring = q + 1;
-              rflags |= (e[q] & RING_FLAG) ? (1u << q) : 0u;
-              if (ODT) bcells |= (e[q] & RING_BCELL) ? (1u << q) : 0u;
-            }
-          asm volatile("cp.async.commit_group;");
-          asm volatile("cp.async.wait_group 0;" ::: "memory");
-        }
+    if (bad) {
+      err |= OM_DEV_WALK;
+    } else {
+      // first and second spoke of the start cell, and the edge we leave through
+      int sf, ss;
+      if (open) {
+        const int kb = jc >> 2;
+        jc &= 3;
+        ss = kb;             // the vertex opposite the boundary edge comes second
+        sf = 3 - jc - kb;    // the other end of the boundary edge comes first
       } else {
-        cell = __ldg(p.cells + c0);
-        j = slot_of(cell, v);
-        if (j < 0) {
-          err |= OM_DEV_WALK;
-          walk = false;
-        }
+        sf = (jc + 1) % 3;
+        ss = (jc + 2) % 3;
       }
-    }
-    if (walk) {
-      Acc<D> acc;
-      acc.w = 0.0;
-      acc.rmin = INFINITY;
-      acc.lb_num = INFINITY;
-      acc.lb_den = 1.0;
-#pragma unroll
-      for (int k = 0; k < D; k++) acc.num.v[k] = 0.0;
-#pragma unroll
-      for (int k = 0; k < D * (D + 1) / 2; k++) acc.H[k] = 0.0;
-      // visits the cells of the star in walk order; f(P1, P2) gets the other two vertices
-      // of each cell in slot order
-      auto for_each_cell = [&](auto&& f) {
-        if (SRC == 0) {
-          constexpr int PER = (D == 2) ? 1 : 2;
-          auto ld_ring = [&](int q) {
-            Vec<D> r;
-            const double2 a = ring_sm[(q * PER) * step_block<D>() + threadIdx.x];
-            r.v[0] = a.x;
-            r.v[1] = a.y;
-            if (D == 3) r.v[D - 1] = ring_sm[(q * PER + PER - 1) * step_block<D>() + threadIdx.x].x;
-            return r;
-          };
-          Vec<D> A = ld_ring(0);
-#pragma unroll K1_UNROLL
-          for (int q = 0; q < nring; q++) {
-            const Vec<D> B = ld_ring(q + 1 < nring ? q + 1 : 0);
-            // select the operands (no divergent branch around the cell arithmetic)
-            const bool sw = (rflags >> q) & 1u;
-            Vec<D> X1, X2;
-#pragma unroll
-            for (int k = 0; k < D; k++) {
-              X1.v[k] = sw ? B.v[k] : A.v[k];
-              X2.v[k] = sw ? A.v[k] : B.v[k];
-            }
-            f(X1, X2, ODT && ((bcells >> q) & 1u));
-            A = B;
-          }
-        } else {
-          walk_star<D, ODT>(p, v, c0, cell, j, err, f);
-        }
-      };
-
+      const int first = cell_get(cl, sf);
+      int newid = cell_get(cl, ss);
+      if (!(p.valid(first) && p.valid(newid))) p.ds->stale = 1;
+      const Vec<D> Pfirst = ld_point<D>(p.x, first);
       const bool odt_bary = ODT && p.odt_bary != 0;
-      for_each_cell([&](const Vec<D>& P1, const Vec<D>& P2, bool bcell) {
-        accumulate_cell<D, METHOD, EXACT>(P0, P1, P2, acc, err, odt_bary && bcell);
-      });
-      // method formula -> offset of the target from the vertex.  The reference divides by
-      // the control volume whatever its sign; only 0/0 (every adjacent cell masked) leaves
-      // the vertex where it is.
-      Vec<D> d;
-      bool ok = acc.w != 0.0;
-      if (METHOD == OM_CVT_BLOCK_DIAGONAL) {
-        // (2 cv I + Hess) d = -2 cv (x - c) in the scaled accumulators: (w I - H) d = num / 3
-        Vec<D> rhs;
-        double Hn[D * (D + 1) / 2];
-#pragma unroll
-        for (int k = 0; k < D; k++) rhs.v[k] = acc.num.v[k] * (1.0 / 3.0);
-#pragma unroll
-        for (int k = 0; k < D * (D + 1) / 2; k++) Hn[k] = -acc.H[k];
-        ok = ok && solve_sym<D>(Hn, acc.w, rhs, d);
-      } else if (ok) {
-        const double inv = 1.0 / (3.0 * acc.w);
-#pragma unroll
-        for (int k = 0; k < D; k++) d.v[k] = acc.num.v[k] * inv;
+      Chain<D, METHOD, !TARGET, false> ch;
+      ch.init(P0);
+      ch.start(Pfirst);
+      int4 ta = __ldg(reinterpret_cast<const int4*>(p.adj) + cur);
+      ch.first(ld_point<D>(p.x, newid), odt_bary && (ta.x < 0 || ta.y < 0 || ta.z < 0), !open);
+      int kexit = sf;  // leave through the edge (v, second spoke): opposite the first spoke
+      int hops = 0;
+      while (true) {
+        const int t = cell_get(ta, kexit);
+        if (t < 0) {
+          if (open)
+            ch.end_open();
+          else
+            err |= OM_DEV_WALK;
+          break;
+        }
+        const int cn = t >> 2, kn = t & 3;
+        const int4 cln = __ldg(p.cells + cn);
+        const int jn = slot_of(cln, v);
+        if (jn < 0 || jn == kn || ++hops > MAX_RING) {
+          err |= OM_DEV_WALK;
+          break;
+        }
+        newid = cell_get(cln, kn);
+        ta = __ldg(reinterpret_cast<const int4*>(p.adj) + cn);
+        const bool bary = odt_bary && (ta.x < 0 || ta.y < 0 || ta.z < 0);
+        if (!open && newid == first) {
+          ch.close(Pfirst, bary);
+          break;
+        }
+        if (!p.valid(newid)) p.ds->stale = 1;
+        ch.next(ld_point<D>(p.x, newid), bary);
+        kexit = 3 - jn - kn;
       }
-      if (ok && !(pinned && !TARGET)) {
+      err |= ch.err;
+      Vec<D> d;
+      if (ch.target_offset(d) && !(pinned && !TARGET)) {
         if (!TARGET) {
 #pragma unroll
-          for (int k = 0; k < D; k++) d.v[k] *= p.omega;
+          for (int i = 0; i < D; i++) d.v[i] *= p.omega;
           diff2 = vdot<D>(d, d);
-          if (p.limiter) {
-            // limited iff |d| > r/2 with r the smallest incident inradius.  LAZY: every
-            // inradius satisfies r^2 >= 4 A^2 / (3 sum ee), so 3 |d|^2 sum_ee <= A^2 (lb_den holds sum_ee / 2) for
-            // the minimising cell proves "not limited" without a sqrt or a division.
-            const bool check =
-                EXACT || !(6.0 * diff2 * acc.lb_den * (1.0 + 1e-12) <= acc.lb_num);
-            if (check && !EXACT) {
-              // rare (a few % of the vertices) and expensive: running it here would keep
-              // whole warps busy for one lane.  The vertex goes to the list-driven exact
-              // launch instead, where all lanes have work.
-              deferred = true;
-              diff2 = 0.0;
-            } else if (check) {
-              const double len = sqrt(diff2);
-              const double maxs = 0.5 * acc.rmin;
-              if (len > maxs) {
-                const double s = maxs / len;
-#pragma unroll
-                for (int k = 0; k < D; k++) d.v[k] *= s;
-                limited = 1;
-              }
-            }
-          }
+          if (p.limiter) limited = ch.limit(d, diff2);
         }
 #pragma unroll
-        for (int k = 0; k < D; k++) out.v[k] = P0.v[k] + d.v[k];
+        for (int i = 0; i < D; i++) out.v[i] = P0.v[i] + d.v[i];
       }
     }
-    if (!deferred) st_point<D>(p.xout, v, out);
   }
-  if (!TARGET) reduce_step_stats(diff2, limited, p.ds);
-  if (!TARGET && SRC != 2) {
-    const int vals[1] = {vdef};
-    const bool preds[1] = {deferred};
-    block_append<1>(&p.ds->n_over, p.over, vals, preds);
-  }
-  if (err) atomicOr(&p.ds->err, err);
-  }  // block-stride loop (one trip unless SRC == 2)
+  st_point<D>(p.xout, v, out);
+  if (!TARGET) p.diff2[v] = limited ? -diff2 : diff2;
 }
 
-template <int D, int MODE, int SRC>
-int launch_step(om_handle* h, const StepParams& p) {
-  const int B = step_block<D>();
-  const int G = SRC == 2 ? 148 * 4 : om_grid(p.hi - p.lo, B);
+// get_new_points: every vertex by its star walk
+template <int D, int METHOD>
+__global__ void __launch_bounds__(128) k_target(StepParams p) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= p.N) return;
+  int err = 0;
+  walk_vertex<D, METHOD, true>(p, v, err);
+  if (err) atomicOr(&p.ds->err, err);
+}
+
+// Vertices left by k_step_ring (flag bit VF_DEFER): the flag words of [lo, hi) are scanned in
+// chunks, the flagged vertices of a chunk are compacted into shared memory (no global
+// counter, no atomics: the order is the vertex order) and updated with all lanes busy.
+constexpr int POST_BLOCK = 256;
+constexpr int POST_PER = 8;  // flag words per thread and chunk (one 16-byte load)
+template <int D, int METHOD>
+__global__ void __launch_bounds__(POST_BLOCK) k_post(StepParams p) {
+  constexpr int CHUNK = POST_BLOCK * POST_PER;
+  __shared__ int s_v[CHUNK];
+  __shared__ int s_warp[POST_BLOCK / 32];
+  __shared__ int s_total;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int base0 = p.lo & ~(POST_PER - 1);  // 16-byte aligned start of the scan
+  const int nchunks = (p.hi - base0 + CHUNK - 1) / CHUNK;
+  int err = 0;
+  for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    const int vb = base0 + chunk * CHUNK + threadIdx.x * POST_PER;
+    unsigned hits = 0u;  // bit i: vertex vb + i is to be updated here
+    if (vb < p.hi) {
+      // (the flag array is padded to a multiple of POST_PER words beyond N)
+      uint4 raw = *reinterpret_cast<const uint4*>(p.vflags + vb);
+      unsigned r[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+      for (int i = 0; i < POST_PER; i++) {
+        const unsigned bit = VF_DEFER << (16 * (i & 1));
+        const int v = vb + i;
+        if ((r[i >> 1] & bit) && v >= p.lo && v < p.hi) {
+          hits |= 1u << i;
+          r[i >> 1] &= ~bit;  // the other bits belong to the flip pass
+        }
+      }
+      if (hits) {
+        raw = make_uint4(r[0], r[1], r[2], r[3]);
+        *reinterpret_cast<uint4*>(p.vflags + vb) = raw;
+      }
+    }
+    const int cnt = __popc(hits);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int q = 0; q < POST_BLOCK / 32; q++) {
+        const int t = s_warp[q];
+        s_warp[q] = tot;
+        tot += t;
+      }
+      s_total = tot;
+    }
+    __syncthreads();
+    int pos = s_warp[warp] + incl - cnt;
+    while (hits) {
+      const int i = __ffs(hits) - 1;
+      hits &= hits - 1;
+      s_v[pos++] = vb + i;
+    }
+    __syncthreads();
+    const int total = s_total;
+    for (int i = threadIdx.x; i < total; i += POST_BLOCK)
+      walk_vertex<D, METHOD, false>(p, s_v[i], err);
+    __syncthreads();  // s_v / s_warp are reused by the next chunk
+  }
+  if (err) atomicOr(&p.ds->err, err);
+}
+
+// the same walk for an explicit list whose length lives on the device
+template <int D, int METHOD>
+__global__ void __launch_bounds__(128)
+    k_walk_list(StepParams p, const int* __restrict__ list, const int* __restrict__ n_dev) {
+  const int n = *n_dev;
+  int err = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int v = list[i];
+    if (v >= p.lo && v < p.hi) walk_vertex<D, METHOD, false>(p, v, err);
+  }
+  if (err) atomicOr(&p.ds->err, err);
+}
+
+// max |diff|^2 and number of limited vertices (sign bit) over [lo, hi)
+__global__ void __launch_bounds__(256)
+    k_reduce_stats(const double* __restrict__ diff2, int lo, int hi, DevScalars* ds) {
+  unsigned long long mx = 0ull;
+  int lim = 0;
+  for (int v = lo + blockIdx.x * blockDim.x + threadIdx.x; v < hi; v += gridDim.x * blockDim.x) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(__ldg(diff2 + v));
+    lim += (int)(b >> 63);
+    mx = max(mx, b & 0x7fffffffffffffffull);  // non-negative doubles order like integers
+  }
+  __shared__ unsigned long long s_m[8];
+  __shared__ int s_l[8];
+  for (int o = 16; o > 0; o >>= 1) {
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    lim += __shfl_xor_sync(0xffffffffu, lim, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    s_m[threadIdx.x >> 5] = mx;
+    s_l[threadIdx.x >> 5] = lim;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); w++) {
+      mx = max(mx, s_m[w]);
+      lim += s_l[w];
+    }
+    if (mx) atomicMax(&ds->max_diff2_bits, mx);
+    if (lim) atomicAdd(&ds->n_limited, (unsigned long long)lim);
+  }
+}
+
+template <int D, int METHOD, bool CHECK>
+int launch_ring(om_handle* h, const StepParams& p, bool exact, bool part) {
+  const int B = OM_K1_BLOCK, G = om_grid(p.hi - p.lo, B);
   if (G == 0) return OM_OK;
+  if (exact) {
+    if (part)
+      OM_LAUNCH(h, (k_step_ring<D, METHOD, true, CHECK, true>), G, B, p);
+    else
+      OM_LAUNCH(h, (k_step_ring<D, METHOD, true, CHECK, false>), G, B, p);
+  } else {
+    if (part)
+      OM_LAUNCH(h, (k_step_ring<D, METHOD, false, CHECK, true>), G, B, p);
+    else
+      OM_LAUNCH(h, (k_step_ring<D, METHOD, false, CHECK, false>), G, B, p);
+  }
+  return OM_OK;
+}
+
+// what: 0 ring kernel, 1 ring kernel with the fused Delaunay check, 2 k_post, 3 k_target,
+// 4 k_walk_list over h->dirty
+template <int D, int METHOD>
+int launch_method(om_handle* h, const StepParams& p, int what, bool exact, bool part) {
+  switch (what) {
+    case 0:
+      return launch_ring<D, METHOD, false>(h, p, exact, part);
+    case 1:
+      return launch_ring<D, METHOD, true>(h, p, exact, part);
+    case 2: {
+      const int chunks = om_grid(p.hi - (p.lo & ~(POST_PER - 1)), POST_BLOCK * POST_PER);
+      OM_LAUNCH(h, (k_post<D, METHOD>), std::min(chunks, 148 * 4), POST_BLOCK, p);
+      return OM_OK;
+    }
+    case 3:
+      OM_LAUNCH(h, (k_target<D, METHOD>), om_grid(p.N, 128), 128, p);
+      return OM_OK;
+    default:
+      OM_LAUNCH(h, (k_walk_list<D, METHOD>), 148 * 8, 128, p, (const int*)h->dirty,
+                (const int*)&h->ds->n_dirty);
+      return OM_OK;
+  }
+}
+
+template <int D>
+int launch_dim(om_handle* h, const StepParams& p, int what, bool exact, bool part) {
   switch (h->method) {
     case OM_LLOYD:
-      OM_LAUNCH(h, (k_step<D, OM_LLOYD, MODE, SRC>), G, B, p);
-      break;
+      return launch_method<D, OM_LLOYD>(h, p, what, exact, part);
     case OM_CVT_BLOCK_DIAGONAL:
-      OM_LAUNCH(h, (k_step<D, OM_CVT_BLOCK_DIAGONAL, MODE, SRC>), G, B, p);
-      break;
+      return launch_method<D, OM_CVT_BLOCK_DIAGONAL>(h, p, what, exact, part);
     case OM_CPT_FIXED_POINT:
-      OM_LAUNCH(h, (k_step<D, OM_CPT_FIXED_POINT, MODE, SRC>), G, B, p);
-      break;
+      return launch_method<D, OM_CPT_FIXED_POINT>(h, p, what, exact, part);
     case OM_ODT_FIXED_POINT:
-      OM_LAUNCH(h, (k_step<D, OM_ODT_FIXED_POINT, MODE, SRC>), G, B, p);
-      break;
+      return launch_method<D, OM_ODT_FIXED_POINT>(h, p, what, exact, part);
     case OM_ODT_DP_FP:
-      OM_LAUNCH(h, (k_step<D, OM_ODT_DP_FP, MODE, SRC>), G, B, p);
-      break;
+      return launch_method<D, OM_ODT_DP_FP>(h, p, what, exact, part);
     default:
       om_set_error("method %d has no fixed-point kernel", h->method);
       return OM_ERR_ARG;
   }
+}
+
+int launch_step(om_handle* h, const StepParams& p, int what, bool exact = true) {
+  const bool part = p.valid_epoch != nullptr;
+  const int rc = h->D == 2 ? launch_dim<2>(h, p, what, exact, part)
+                           : launch_dim<3>(h, p, what, exact, part);
+  if (rc != OM_OK) return rc;
   CUDA_TRY(cudaGetLastError());
   return OM_OK;
 }
 
-// src: 0 ring rows over [lo,hi), 1 walk over [lo,hi), 2 walk over the overflow list
+// Smallest incident inradius of a free vertex with a closed fan, by a star walk (as the
+// fraction rn / rd = 2A / perimeter of the minimising cell).
 template <int D>
-int launch_step_mode(om_handle* h, const StepParams& p, int mode, int src) {
-  if (mode == 2) return launch_step<D, 2, 1>(h, p);
-  if (mode == 0) {
-    if (src == 0) return launch_step<D, 0, 0>(h, p);
-    if (src == 1) return launch_step<D, 0, 1>(h, p);
-    return launch_step<D, 0, 2>(h, p);
+__device__ __forceinline__ void star_limiter(const StepParams& p, int v, int c0, const Vec<D>& P0,
+                                             Chain<D, OM_CHAIN_LIMITER_ONLY, true, false>& ch,
+                                             int& err) {
+  ch.init(P0);
+  const int4 cl = __ldg(p.cells + c0);
+  const int j = slot_of(cl, v);
+  if (j < 0) {
+    err |= OM_DEV_WALK;
+    return;
   }
-  if (src == 0) return launch_step<D, 1, 0>(h, p);
-  if (src == 1) return launch_step<D, 1, 1>(h, p);
-  return launch_step<D, 0, 2>(h, p);  // the deferred list is always done exactly
+  const int first = cell_get(cl, (j + 1) % 3);
+  const Vec<D> Pfirst = ld_point<D>(p.x, first);
+  ch.start(Pfirst);
+  ch.first(ld_point<D>(p.x, cell_get(cl, (j + 2) % 3)), false, true);
+  int cur = c0, kexit = (j + 1) % 3, hops = 0;
+  while (true) {
+    const int t = __ldg(p.adj + 4 * (size_t)cur + kexit);
+    if (t < 0) {
+      err |= OM_DEV_WALK;
+      break;
+    }
+    const int cn = t >> 2, kn = t & 3;
+    const int4 cln = __ldg(p.cells + cn);
+    const int jn = slot_of(cln, v);
+    if (jn < 0 || jn == kn || ++hops > MAX_RING) {
+      err |= OM_DEV_WALK;
+      break;
+    }
+    const int newid = cell_get(cln, kn);
+    if (newid == first) {
+      ch.close(Pfirst, false);
+      break;
+    }
+    ch.next(ld_point<D>(p.x, newid), false);
+    cur = cn;
+    kexit = 3 - jn - kn;
+  }
+  err |= ch.err;
 }
 
 // x <- x + omega (target - x), limited: the driver-loop tail for methods whose target
-// comes from a solve (cpt-linear-solve).
+// comes from a solve (cpt-linear-solve, cpt-quasi-newton).
 template <int D>
-__global__ void __launch_bounds__(256) k_relax_from_target(StepParams p, const double* target) {
+__global__ void __launch_bounds__(128) k_relax_from_target(StepParams p, const double* target) {
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= p.N) return;
+  int err = 0;
+  const Vec<D> P0 = ld_point<D>(p.x, v);
+  Vec<D> out = P0;
   double diff2 = 0.0;
-  int limited = 0, err = 0;
-  if (v < p.N) {
-    const Vec<D> P0 = ld_point<D>(p.x, v);
-    Vec<D> out = P0;
-    const int c0 = p.v2c[v];
-    if (c0 != OM_NONE_CELL && !p.bflag[v]) {
-      const Vec<D> T = ld_point<D>(target, v);
-      Vec<D> d;
+  bool limited = false;
+  const int c0 = p.v2c[v];
+  if (c0 != OM_NONE_CELL && !p.bflag[v]) {
+    const Vec<D> T = ld_point<D>(target, v);
+    Vec<D> d;
 #pragma unroll
-      for (int k = 0; k < D; k++) d.v[k] = p.omega * (T.v[k] - P0.v[k]);
-      diff2 = vdot<D>(d, d);
-      if (p.limiter) {
-        const int4 cell = __ldg(p.cells + c0);
-        const int j = slot_of(cell, v);
-        double rmin = INFINITY;
-        if (j < 0) {
-          err |= OM_DEV_WALK;
-        } else {
-          walk_star<D>(p, v, c0, cell, j, err, [&](const Vec<D>& P1, const Vec<D>& P2, bool) {
-            const CellGeo<D> g = cell_geo<D>(P0, P1, P2);
-            if (g.vol2 > 0.0)
-              rmin = fmin(rmin, inradius<D>(g));
-            else
-              err |= OM_DEV_DEGENERATE;
-          });
-        }
-        const double len = sqrt(diff2), maxs = 0.5 * rmin;
-        if (len > maxs) {
-          const double s = maxs / len;
-#pragma unroll
-          for (int k = 0; k < D; k++) d.v[k] *= s;
-          limited = 1;
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < D; k++) out.v[k] = P0.v[k] + d.v[k];
+    for (int k = 0; k < D; k++) d.v[k] = p.omega * (T.v[k] - P0.v[k]);
+    diff2 = vdot<D>(d, d);
+    if (p.limiter) {
+      Chain<D, OM_CHAIN_LIMITER_ONLY, true, false> ch;
+      star_limiter<D>(p, v, c0, P0, ch, err);
+      if (!err) limited = ch.limit(d, diff2);
     }
-    st_point<D>(p.xout, v, out);
+#pragma unroll
+    for (int k = 0; k < D; k++) out.v[k] = P0.v[k] + d.v[k];
   }
-  reduce_step_stats(diff2, limited, p.ds);
+  st_point<D>(p.xout, v, out);
+  p.diff2[v] = limited ? -diff2 : diff2;
+  if (err) atomicOr(&p.ds->err, err);
+}
+
+// ---- synthetic workloads (om_random_walk): every free vertex moves by a random vector of
+// length <= amplitude/2 x its smallest incident inradius (no cell can invert: every height
+// of a triangle is at least twice its inradius).  The random numbers are a hash of (seed,
+// round, caller vertex id): the result does not depend on the internal numbering.
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long z) {
+  z += 0x9e3779b97f4a7c15ull;
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+  return z ^ (z >> 31);
+}
+
+__global__ void __launch_bounds__(128)
+    k_random_move(StepParams p, const int* __restrict__ perm, unsigned long long seed, int round,
+                  double amplitude) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= p.N) return;
+  int err = 0;
+  const Vec<2> P0 = ld_point<2>(p.x, v);
+  Vec<2> out = P0;
+  const int c0 = p.v2c[v];
+  if (c0 != OM_NONE_CELL && !p.bflag[v]) {
+    Chain<2, OM_CHAIN_LIMITER_ONLY, true, false> ch;
+    star_limiter<2>(p, v, c0, P0, ch, err);
+    if (!err) {
+      const unsigned long long id = (unsigned long long)(perm ? perm[v] : v);
+      const unsigned long long h0 =
+          splitmix64(seed ^ splitmix64(id + ((unsigned long long)round << 40)));
+      const unsigned long long h1 = splitmix64(h0);
+      const double u1 = (double)(h0 >> 11) * (1.0 / 9007199254740992.0);
+      const double u2 = (double)(h1 >> 11) * (1.0 / 9007199254740992.0);
+      // uniform in the disk of radius amplitude/2 x r_min
+      const double r = 0.5 * amplitude * (ch.rn / ch.rd) * sqrt(u1);
+      double sn, cs;
+      sincospi(2.0 * u2, &sn, &cs);
+      out.v[0] = P0.v[0] + r * cs;
+      out.v[1] = P0.v[1] + r * sn;
+    }
+  }
+  st_point<2>(p.xout, v, out);
   if (err) atomicOr(&p.ds->err, err);
 }
 
@@ -739,7 +755,8 @@ StepParams make_params(om_handle* h, double* out) {
   p.v2c = h->v2c;
   p.bflag = h->bflag;
   p.ring = h->ring;
-  p.over = h->over;
+  p.diff2 = h->diff2;
+  p.vflags = h->vflags;
   p.valid_epoch = (h->own_hi >= 0 && h->valid_epoch && !h->all_valid) ? h->valid_epoch : nullptr;
   p.valid_stamp = h->valid_stamp;
   p.N = (int)h->N;
@@ -748,6 +765,7 @@ StepParams make_params(om_handle* h, double* out) {
   p.omega = h->omega;
   p.limiter = h->limiter;
   p.odt_bary = h->odt_bary;
+  p.force_walk = h->use_rings ? 0 : 1;
   p.ds = h->ds;
   return p;
 }
@@ -780,6 +798,43 @@ void om_step_stats_from_scalars(om_handle* h, double tol, om_step_stats* out) {
   }
 }
 
+// The point update of the fixed-point methods on [lo, hi) into `out`: ring-row kernel, the
+// vertices it left behind, statistics.  check: also collect the suspicious spokes (fused
+// Delaunay check of the pipelined loop).
+int om_launch_point_update(om_handle* h, double* out, bool check) {
+  StepParams p = make_params(h, out);
+  if (h->own_hi >= 0) {
+    p.lo = (int)h->own_lo;
+    p.hi = (int)h->own_hi;
+  }
+  // the lazy limiter pays off once few vertices are limited (the previous step tells)
+  const bool exact = h->limiter && h->limited_frac > 0.25;
+  if (h->timing) cudaEventRecord(h->ev[0], h->stream);
+  OM_TRY(launch_step(h, p, check ? 1 : 0, exact));
+  if (h->timing) {
+    cudaEventRecord(h->ev[1], h->stream);
+    h->ev_pending = true;
+  }
+  OM_TRY(launch_step(h, p, 2));
+  return OM_OK;
+}
+
+int om_launch_reduce_stats(om_handle* h) {
+  const int lo = h->own_hi >= 0 ? (int)h->own_lo : 0;
+  const int hi = h->own_hi >= 0 ? (int)h->own_hi : (int)h->N;
+  if (hi > lo)
+    OM_LAUNCH(h, k_reduce_stats, std::min(om_grid(hi - lo, 256 * 8), 148 * 8), 256, h->diff2, lo, hi,
+              h->ds);
+  CUDA_TRY(cudaGetLastError());
+  return OM_OK;
+}
+
+// recomputes the vertices of h->dirty (stars changed by flips) from h->x into `out`
+int om_launch_fixup(om_handle* h, double* out) {
+  StepParams p = make_params(h, out);
+  return launch_step(h, p, 4);
+}
+
 int om_update_points_impl(om_handle* h, double tol, om_step_stats* out, bool target_only,
                           double* target_out, bool defer_fetch) {
   if (h->N == 0) return OM_OK;
@@ -797,7 +852,7 @@ int om_update_points_impl(om_handle* h, double tol, om_step_stats* out, bool tar
       double* tmp = nullptr;
       CUDA_TRY(om_malloc(h, &tmp, sizeof(double) * h->N * h->PD));
       StepParams p = make_params(h, tmp);
-      const int B = 256, G = om_grid(h->N, B);
+      const int B = 128, G = om_grid(h->N, B);
       if (h->D == 2)
         OM_LAUNCH(h, k_relax_from_target<2>, G, B, p, sol);
       else
@@ -805,37 +860,15 @@ int om_update_points_impl(om_handle* h, double tol, om_step_stats* out, bool tar
       CUDA_TRY(cudaGetLastError());
       CUDA_TRY(cudaMemcpyAsync(h->xnew, tmp, sizeof(double) * h->N * h->PD,
                                cudaMemcpyDeviceToDevice, h->stream));
-      CUDA_TRY(cudaStreamSynchronize(h->stream));
-      om_free(h, tmp);
+      om_free(h, tmp);  // stream ordered: released after the copy
+      OM_TRY(om_launch_reduce_stats(h));
     }
+  } else if (target_only) {
+    StepParams p = make_params(h, target_out);
+    OM_TRY(launch_step(h, p, 3));
   } else {
-    StepParams p = make_params(h, target_only ? target_out : h->xnew);
-    const bool ranged = !target_only && h->own_hi >= 0;
-    if (ranged) {
-      p.lo = (int)h->own_lo;
-      p.hi = (int)h->own_hi;
-    }
-    // the lazy limiter pays off once few vertices are limited (the previous step tells)
-    const int mode = target_only ? 2 : ((h->limiter && h->limited_frac > 0.25) ? 0 : 1);
-    const int src = (mode != 2 && h->ring && h->use_rings) ? 0 : 1;
-    if (h->timing) cudaEventRecord(h->ev[0], h->stream);
-    if (h->D == 2)
-      OM_TRY(launch_step_mode<2>(h, p, mode, src));
-    else
-      OM_TRY(launch_step_mode<3>(h, p, mode, src));
-    if (h->timing) {
-      cudaEventRecord(h->ev[1], h->stream);
-      h->ev_pending = true;
-    }
-    if (mode != 2) {
-      // vertices the main launch deferred (no ring row, or the lazy limiter bound failed):
-      // second, list-driven launch with the exact limiter; it reads the list length on the
-      // device, so no readback is needed in between
-      if (h->D == 2)
-        OM_TRY(launch_step_mode<2>(h, p, mode, 2));
-      else
-        OM_TRY(launch_step_mode<3>(h, p, mode, 2));
-    }
+    OM_TRY(om_launch_point_update(h, h->xnew, false));
+    OM_TRY(om_launch_reduce_stats(h));
   }
   if (defer_fetch && !target_only && !om_is_solve_method(h->method)) {
     // om_step reads the statistics back together with the first flip-round readback
@@ -876,6 +909,20 @@ int om_update_points_impl(om_handle* h, double tol, om_step_stats* out, bool tar
   return OM_OK;
 }
 
+int om_random_move_impl(om_handle* h, uint64_t seed, int round, double amplitude) {
+  if (h->N == 0) return OM_OK;
+  if (h->D != 2) {
+    om_set_error("om_random_walk is for flat (2D) meshes");
+    return OM_ERR_ARG;
+  }
+  StepParams p = make_params(h, h->xnew);
+  OM_LAUNCH(h, k_random_move, om_grid(h->N, 128), 128, p, (const int*)h->perm,
+            (unsigned long long)seed, round, amplitude);
+  CUDA_TRY(cudaGetLastError());
+  std::swap(h->x, h->xnew);
+  return OM_OK;
+}
+
 int om_project_impl(om_handle* h, int32_t* sweeps) {
   if (sweeps) *sweeps = 0;
   if (h->surf_kind == 0 || h->N == 0) return OM_OK;
@@ -901,24 +948,31 @@ int om_project_impl(om_handle* h, int32_t* sweeps) {
   return OM_OK;
 }
 
-// (Re)builds ring rows: all vertices, or the vertices touched by flips since the last call.
-int om_rebuild_rings(om_handle* h, bool all) {
+// (Re)builds ring rows: all vertices, or the vertices touched by flips since the last call
+// (device == true: the list length is read on the device, no host copy of it is needed).
+int om_rebuild_rings(om_handle* h, bool all, bool device) {
   if (!h->ring || h->N == 0) return OM_OK;
   const int B = 256;
   if (all) {
     OM_LAUNCH(h, (k_build_rings<false>), om_grid(h->N, B), B, h->cells, (const int*)h->adj, h->v2c,
-              h->bflag, (int)h->N, (const int*)nullptr, h->ring, 0, (int)h->N);
+              h->bflag, (int)h->N, (const int*)nullptr, (const int*)nullptr, h->ring, 0, (int)h->N);
     h->rings_partial = false;
   } else {
-    const int n = h->hs->n_dirty;  // fetched by the flip pass
     // with an owned range only its rows are kept current (nothing else reads ring rows);
     // om_set_owned_range(whole mesh) rebuilds all of them
     const bool ranged = h->own_hi >= 0;
     if (ranged) h->rings_partial = true;
-    if (n > 0)
-      OM_LAUNCH(h, (k_build_rings<true>), om_grid(n, B), B, h->cells, (const int*)h->adj, h->v2c,
-                h->bflag, n, h->dirty, h->ring, ranged ? (int)h->own_lo : 0,
-                ranged ? (int)h->own_hi : (int)h->N);
+    const int lo = ranged ? (int)h->own_lo : 0, hi = ranged ? (int)h->own_hi : (int)h->N;
+    if (device) {
+      OM_LAUNCH(h, (k_build_rings<true>), 148 * 4, B, h->cells, (const int*)h->adj, h->v2c, h->bflag,
+                0, h->dirty, (const int*)&h->ds->n_dirty, h->ring, lo, hi);
+    } else {
+      const int n = h->hs->n_dirty;  // fetched by the flip pass
+      if (n > 0)
+        OM_LAUNCH(h, (k_build_rings<true>), std::min(om_grid(n, B), 148 * 8), B, h->cells,
+                  (const int*)h->adj, h->v2c, h->bflag, n, h->dirty, (const int*)nullptr, h->ring,
+                  lo, hi);
+    }
   }
   CUDA_TRY(cudaGetLastError());
   return OM_OK;
@@ -937,10 +991,11 @@ __device__ __forceinline__ void for_each_neighbour(const int4* __restrict__ cell
   const int4* rp = reinterpret_cast<const int4*>(ring + (size_t)OM_RING_W * v);
   const int4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
   const int e[OM_RING_W] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-  if (e[0] != -2) {
+  if (e[0] >= 0) {
+    const int k = 1 + ((e[0] >> 30) & 1) + ((e[1] >> 29) & 2) + ((e[2] >> 28) & 4);
 #pragma unroll
     for (int q = 0; q < OM_RING_W; q++)
-      if (e[q] >= 0) f(e[q] & RING_MASK);
+      if (q < k) f(e[q] & RING_MASK);
     return;
   }
   const int c0 = v2c[v];

@@ -165,6 +165,14 @@ class DeviceMesh:
             warnings.warn("Maximum number of edge flips reached.")
         return steps.value, st.as_dict()
 
+    def random_walk(self, rounds: int, seed: int = 0, amplitude: float = 1.0) -> int:
+        """Synthetic workloads: `rounds` random moves bounded by half the smallest incident
+        inradius, each followed by flip-until-Delaunay (om_random_walk).  Returns the flips."""
+        nf = C.c_int64()
+        check(self._lib.om_random_walk(self._h, int(rounds), int(seed), float(amplitude),
+                                       C.byref(nf)))
+        return nf.value
+
     def new_points(self) -> np.ndarray:
         out = np.empty((self.n, self.dim), dtype=np.float64)
         check(self._lib.om_new_points(self._h, out.ctypes.data))
