@@ -19,7 +19,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "liboptimesh_b200.so")
-SOURCES = ["api.cu", "setup.cu", "step.cu", "flip.cu", "stats.cu", "pcg.cu"]
+SOURCES = ["api.cu", "setup.cu", "step.cu", "flip.cu", "stats.cu", "pcg.cu", "loop.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
@@ -27,6 +27,11 @@ NVCC_FLAGS = [
     "--expt-relaxed-constexpr",
     "-diag-suppress", "177,550",
 ] + os.environ.get("OM_NVCC_EXTRA", "").split()
+
+
+# step.cu: no implicit contraction -- every instantiation of the step kernels must give a
+# vertex the same bits (chain.cuh writes its fused multiply-adds out)
+FILE_FLAGS = {"step.cu": ["-fmad=false"]}
 
 
 def _nvcc() -> str:
@@ -50,14 +55,15 @@ def _headers_hash() -> str:
 def _compile(src: str, hh: str, force: bool, verbose: bool) -> str:
     path = os.path.join(CSRC, src)
     with open(path, "rb") as f:
-        key = hashlib.sha256(f.read() + hh.encode()).hexdigest()[:16]
+        key = hashlib.sha256(f.read() + hh.encode()
+                             + " ".join(FILE_FLAGS.get(src, [])).encode()).hexdigest()[:16]
     obj = os.path.join(BUILD, f"{os.path.splitext(src)[0]}.{key}.o")
     if os.path.exists(obj) and not force:
         return obj
     for old in os.listdir(BUILD):
         if old.startswith(os.path.splitext(src)[0] + ".") and old.endswith(".o"):
             os.remove(os.path.join(BUILD, old))
-    cmd = [_nvcc(), *NVCC_FLAGS, "-c", path, "-o", obj]
+    cmd = [_nvcc(), *NVCC_FLAGS, *FILE_FLAGS.get(src, []), "-c", path, "-o", obj]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -444,6 +444,7 @@ int om_destroy(om_handle* h) {
   if (!h) return OM_OK;
   DeviceGuard guard(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  om_pl_destroy(h);
   om_free(h, h->x);
   om_free(h, h->xnew);
   om_free(h, h->cells);
@@ -566,6 +567,16 @@ int om_step(om_handle* h, double tol, om_step_stats* out) {
 int om_run(om_handle* h, double tol, int64_t max_num_steps, int64_t* steps_done,
            om_step_stats* last) {
   OM_ENTER(h);
+  if (max_num_steps < 1) {
+    om_set_error("max_num_steps must be >= 1");
+    return OM_ERR_ARG;
+  }
+  // fixed-point methods on the whole mesh without a surface: the loop runs on the device
+  // (loop.cu); OM_NO_PIPELINE=1 keeps the step-by-step order below (diagnostics)
+  static const bool no_pipeline = getenv("OM_NO_PIPELINE") != nullptr;
+  if (!no_pipeline && !om_is_solve_method(h->method) && h->surf_kind == 0 && h->own_hi < 0 &&
+      h->N > 0 && h->C > 0)
+    return om_run_pipelined(h, tol, max_num_steps, steps_done, last);
   om_step_stats st;
   memset(&st, 0, sizeof(st));
   int64_t nf = 0;

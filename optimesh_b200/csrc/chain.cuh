@@ -13,13 +13,21 @@
 // cH_q is (minus twice) the Delaunay indicator s of the edge (v, n_q) (A.7), so the fused
 // check of the flip pass costs two more instructions per spoke.
 //
-// Cost per cell visit (2D, CVT block-diagonal, lazy limiter): 36 fp64 instructions -- one new
-// spoke (2 sub, 2 for L, 2 for c), V4 (2), one rsqrt (MUFU seed + 5), ed1/ed2 (2), three t (3),
-// w1 w2 (2), ws uu (2), s1 s2 (2), spoke coefficients (2), W (1), H (5), NUM (2), limiter bound
-// (2) -- against 46 in the cell-by-cell form (step.cu of round 1), and no operand selects:
-// the formulas are symmetric in the orientation of a cell, only the walk direction matters.
+// Cost per cell visit (2D, CVT block-diagonal, lazy limiter): 31 fp64 instructions -- one new
+// spoke (2 sub, 2 for L, 2 for c), V4 (2), one rsqrt (MUFU seed + 5), ed1/ed2 (2), two t (2),
+// w1 w2 (2), ws uu (2), s1 s2 (2), spoke coefficients (2), W (1), H (3: its trace is W, so the
+// last diagonal entry is never summed), NUM (2) -- against 46 in the cell-by-cell form (step.cu
+// of round 1), and no operand selects: the formulas are symmetric in the orientation of a
+// cell, only the walk direction matters.  Everything that is a comparison (degenerate cell,
+// masked cell, limiter bound, Delaunay pre-check) runs on the integer pipe: the fp64 pipe is
+// the one that bounds the kernel.
 // Scaling: rs = 1/sqrt(V4) = 1/(2A) is used as it comes; t'' = ed rs = 2 t (t = -ce, A.2),
 // w'' = 2 w, s'' = 4 s.  Constant factors are undone once per vertex (finish()).
+//
+// Every vertex must get the same bits whichever kernel evaluates it (ring rows with the lazy
+// or the exact limiter, with or without the fused check, or a star walk): the file is compiled
+// with -fmad=false and every fused multiply-add is written out, so that no instantiation is
+// contracted differently from another.
 //
 // tests/chain_model.py restates this file in Python; tests/test_chain_model.py checks that
 // restatement against the oracle on the CPU.
@@ -61,7 +69,8 @@ __device__ __forceinline__ bool solve_sym(const double* H, double diag, const Ve
 template <>
 __device__ __forceinline__ bool solve_sym<2>(const double* H, double diag, const Vec<2>& rhs,
                                              Vec<2>& out) {
-  const double a = diag - H[0], b = -H[1], d = diag - H[2];
+  // H[2] is not summed: trace(H) = diag, so diag - H[2] = H[0]
+  const double a = diag - H[0], b = -H[1], d = H[0];
   const double det = fma(a, d, -b * b);
   if (det == 0.0) return false;
   const double inv = fast_rcp(det);
@@ -72,8 +81,9 @@ __device__ __forceinline__ bool solve_sym<2>(const double* H, double diag, const
 template <>
 __device__ __forceinline__ bool solve_sym<3>(const double* H, double diag, const Vec<3>& rhs,
                                              Vec<3>& out) {
+  // H[5] is not summed: trace(H) = diag, so diag - H[5] = H[0] + H[3]
   const double a = diag - H[0], b = -H[1], c = -H[2], d = diag - H[3], e = -H[4],
-               f = diag - H[5];
+               f = H[0] + H[3];
   const double c00 = d * f - e * e, c01 = c * e - b * f, c02 = b * e - c * d;
   const double det = a * c00 + b * c01 + c * c02;
   if (det == 0.0) return false;
@@ -107,7 +117,7 @@ struct Chain {
   double H[NH];
   // limiter
   double rn, rd;          // EXACT: 2A and perimeter of the cell with the smallest inradius
-  int minv4_hi, maxsh_hi; // lazy bound
+  int minv4_hi, maxl_hi;  // lazy bound
   // current spoke (the second spoke of the last cell) and what that cell leaves for it
   Vec<D> dq;
   double Lq, lenq;
@@ -128,7 +138,7 @@ struct Chain {
     rn = INFINITY;
     rd = 1.0;
     minv4_hi = 0x7ff00000;
-    maxsh_hi = 0;
+    maxl_hi = 0;
     t1p = s1p = t2_0 = s2_0 = 0.0;
     lenq = 0.0;
     flags = 0u;
@@ -143,7 +153,10 @@ struct Chain {
   }
 
   // first spoke of the chain
-  __device__ __forceinline__ void start(const Vec<D>& P) { spoke(P, dq, Lq, lenq); }
+  __device__ __forceinline__ void start(const Vec<D>& P) {
+    spoke(P, dq, Lq, lenq);
+    if (!EXACT) maxl_hi = __double2hiint(Lq);
+  }
 
   // adds what the two cells next to spoke `d` leave for it
   __device__ __forceinline__ void finish_spoke(const Vec<D>& d, double L, double t2, double s2,
@@ -157,23 +170,26 @@ struct Chain {
       const double cH = t2 + t1;
       if (LLOYD_LIKE) W = fma(L, cH, W);
       if (CVT) {
-        Vec<D> a;
-#pragma unroll
-        for (int k = 0; k < D; k++) a.v[k] = cH * d.v[k];
+        // trace(H) = sum cH |d|^2 = W: the last diagonal entry follows in target_offset()
         int qi = 0;
 #pragma unroll
-        for (int i = 0; i < D; i++)
+        for (int i = 0; i < D - 1; i++) {
+          const double a = cH * d.v[i];
 #pragma unroll
           for (int j = i; j < D; j++) {
-            H[qi] = fma(a.v[i], d.v[j], H[qi]);
+            H[qi] = fma(a, d.v[j], H[qi]);
             qi++;
           }
+        }
       }
       if (CHECK && interior) {
         // s = ce + ce' < 0  <=>  cH > 0; everything within rounding of it is kept (sign bit
-        // clear also catches +0 and NaN); the flip pass decides on the exact s
-        const double g = fma(1.0e-9, fabs(t2) + fabs(t1), cH);
-        if (__double2hiint(g) >= 0) flags |= 1u << bit;
+        // clear also catches +0 and NaN); the flip pass decides on the exact s.
+        // cH >= 0, or so small against its two terms (2^-30) that rounding could hide a
+        // positive value: exponent fields compared as integers
+        const int hc = __double2hiint(cH);
+        const int em = max(__double2hiint(t2) & 0x7ff00000, __double2hiint(t1) & 0x7ff00000);
+        if (hc >= 0 || (hc & 0x7ff00000) + (30 << 20) < em) flags |= 1u << bit;
       }
     }
   }
@@ -186,48 +202,52 @@ struct Chain {
                                        bool& masked) {
     masked = false;
     const double c = vdot<D>(dq, dn);
-    const double V4 = fma(Lq, Ln, -c * c);
+    const double cc = c * c;
+    const double V4 = fma(Lq, Ln, -cc);
     // a degenerate cell raises the error and the step is abandoned by the host: no need to
     // keep its garbage (NaN at worst) out of the sums
     if (!pos_normal(V4)) err |= OM_DEV_DEGENERATE;
     const double rs = fast_rsqrt(V4);  // 1 / (2A)
-    const double Ls = Lq + Ln;
     if (EXACT) {
       // inradius 2A / (l0 + l1 + l2), compared as fractions (no division per cell)
       const double A2 = V4 * rs;
-      const double ee0 = fma(-2.0, c, Ls);
-      const double per = (lenq + lenn) + ee0 * fast_rsqrt(ee0);
+      const double ee0 = fma(-2.0, c, Lq + Ln);
+      const double per = fma(ee0, fast_rsqrt(ee0), lenq + lenn);
       if (__double_as_longlong(A2 * rd) < __double_as_longlong(rn * per)) {
         rn = A2;
         rd = per;
       }
     } else {
-      // r_in^2 >= V4 / (6 Sh) with Sh = (ee0 + ee1 + ee2) / 2: keep the smallest V4 and the
-      // largest Sh of the star as high words (rounded the safe way in proves_unlimited())
+      // r_in^2 = V4 / (ee0 + ee1 + ee2 + 2 sum of products of lengths) >= V4 / (3 sum ee) and
+      // ee0 <= 2 (ee1 + ee2), so r_in^2 >= V4 / (18 max L): keep the smallest V4 and the
+      // largest spoke L of the star as high words (rounded the safe way in
+      // proves_unlimited()) -- two integer instructions per cell, nothing on the fp64 pipe
       minv4_hi = min(minv4_hi, __double2hiint(V4));
-      maxsh_hi = max(maxsh_hi, __double2hiint(Ls - c));
+      maxl_hi = max(maxl_hi, __double2hiint(Ln));
     }
     if (NEED_T) {
       const double T1 = (c - Lq) * rs, T2 = (c - Ln) * rs;  // 2 t: angles at n_q, n_{q+1}
       if (LLOYD_LIKE) {
-        const double T0 = -c * rs;
-        // cell masked (an angle > 135 deg): some t > 1/2, i.e. some T > 1
-        const int hmax = max(max(__double2hiint(T0), __double2hiint(T1)), __double2hiint(T2));
-        if (hmax >= 0x3ff00000 && (T0 > 1.0 || T1 > 1.0 || T2 > 1.0)) {
-          masked = true;
-          t1 = t2 = s1 = s2 = 0.0;
-        } else {
-          const double w1 = Ln * T1, w2 = Lq * T2;
-          const double uu = rs * (w1 + w2);
-          t1 = T1;
-          t2 = T2;
-          s2 = fma(-uu, w1, w2);
-          s1 = fma(-uu, w2, w1);
-        }
+        // cell masked (an angle > 135 deg): some t > 1/2, i.e. some T > 1.  T0 = -c rs > 1
+        // <=> c < 0 and c^2 > V4; bit patterns of positive doubles order like integers, so all
+        // three tests run on the integer pipe.  A masked cell gives nothing to its spokes:
+        // with t1 = t2 = 0 every product below is 0 -- selects, no branch, so that the
+        // compiler can overlap the rsqrt chain of the next cell with the sums of this one.
+        const long long one = 0x3ff0000000000000ll;
+        const bool m0 = (__double2hiint(c) < 0) & (__double_as_longlong(cc) > __double_as_longlong(V4));
+        const bool m1 = __double_as_longlong(T1) > one, m2 = __double_as_longlong(T2) > one;
+        masked = m0 | m1 | m2;
+        t1 = masked ? 0.0 : T1;
+        t2 = masked ? 0.0 : T2;
+        const double w1 = Ln * t1, w2 = Lq * t2;
+        const double uu = rs * (w1 + w2);
+        s2 = fma(-uu, w1, w2);
+        s1 = fma(-uu, w2, w1);
       } else if (ODT) {
-        W += DP ? 1.0 : V4 * rs;
+        const double A2 = V4 * rs;
+        W += DP ? 1.0 : A2;
         if (bary) {
-          s1 = s2 = DP ? 1.0 : V4 * rs;
+          s1 = s2 = DP ? 1.0 : A2;
         } else {
           const double f = DP ? -1.5 * rs : -1.5;
           s2 = f * (Ln * T1);
@@ -329,10 +349,11 @@ struct Chain {
 
   // lazy limiter: true if |d|^2 = diff2 provably stays below (r_in / 2)^2 for every cell
   __device__ __forceinline__ bool proves_unlimited(double diff2) const {
-    // high words rounded the safe way: V4 down, Sh up
+    // |d|^2 <= r_in^2 / 4 follows from 72 |d|^2 max L <= min V4; high words rounded the safe
+    // way: V4 down, L up
     const double v4 = __hiloint2double(minv4_hi, 0);
-    const double sh = __hiloint2double(maxsh_hi + 1, 0);
-    return 24.0 * diff2 * sh <= v4;
+    const double ml = __hiloint2double(maxl_hi + 1, 0);
+    return 72.0 * diff2 * ml <= v4;
   }
 
   // exact limiter: scales d if it is longer than half the smallest incident inradius

@@ -55,12 +55,26 @@ struct DevScalars {
   int stale;       // sharded check met a coordinate this rank does not hold
   int abort;       // gathered round rejected: 1 = some rank stale, 2 = some slot overflowed
   int max_count;   // largest record count among the gathered slots
-  int pad5;
+  int epoch;       // stamp of the current flip round (dedupe of the cell lists)
   int flips_prev;  // n_flips at the last round boundary
-  int pad3;
+  int dirty_pass;  // stamp of the current flip pass (dedupe of the dirty-vertex list)
   int err;         // OM_DEV_* bits
-  int pad;
+  int not_delaunay;  // a pass ended with flagged edges but no mutual pair (exact ties)
   double dot[4];   // PCG dot products
+  // ---- pipelined loop (loop.cu): everything the host would decide between two steps
+  int halt;        // 0 running, 1 final step reached, 3 device error
+  int mode_exact;  // the next point update tracks the exact inradius
+  int pl_go;       // another flip round follows (set by k_pl_round_end)
+  int cap_hit;     // a flip pass ran out of rounds with flagged edges left
+  int max_rounds;  // rounds a flip pass may take
+  long long k;     // point updates applied so far
+  long long max_steps;
+  double tol2;
+  long long total_flips, total_rounds, total_limited;  // over the steps of this run
+  long long n_free;  // vertices the limiter statistics refer to
+  long long pl_launches;  // kernels run by the pipelined loop (they are launched by the graph)
+  int limiter_on;
+  int pad_pl;
 };
 
 struct om_handle {
@@ -80,7 +94,6 @@ struct om_handle {
   int* ring = nullptr;       // N x OM_RING_W: one-ring vertex ids of free interior vertices
   int* dirty = nullptr;      // N: vertices touched by flips (ring rows to rebuild)
   int* dirty_epoch = nullptr;// N: dedupe stamps for `dirty`
-  int dirty_pass = 0;
   double* diff2 = nullptr;   // N: |diff|^2 of the last point update, sign bit = limited
   unsigned short* vflags = nullptr;  // N (+pad): per-vertex flag words between step kernels
   bool use_rings = true;
@@ -95,7 +108,6 @@ struct om_handle {
   FlipRec* recs = nullptr;   // C: records of the sharded check (allocated on first use)
   int8_t* best = nullptr;    // C: locally most negative flagged edge or -1
   int* flip_epoch = nullptr; // C
-  int epoch = 0;
   int* reloc = nullptr;      // 4C
   int4* adj_tmp = nullptr;   // C
   // PCG scratch (allocated on first use)
@@ -143,6 +155,7 @@ struct om_handle {
   bool timing = false;
   bool ev_pending = false;  // ev[0..1] recorded, elapsed time not read yet
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  void* pl = nullptr;  // cached graphs of the pipelined loop (loop.cu)
   double t_step_ms = 0.0, t_flip_ms = 0.0;
   int64_t n_step = 0, n_flip = 0;
 };
@@ -206,6 +219,17 @@ int om_rebuild_rings(om_handle* h, bool all, bool device = false);
 int om_launch_point_update(om_handle* h, double* out, bool check);
 int om_launch_reduce_stats(om_handle* h);
 int om_launch_fixup(om_handle* h, double* out);
+// pipelined loop (loop.cu): one iteration = update (with the fused Delaunay check) from xin
+// into xout, flip pass on xin, recomputation of the vertices whose star changed
+int om_pl_launch_update(om_handle* h, const double* xin, double* xout, bool timed);
+int om_pl_launch_tail(om_handle* h, const double* xin, double* xout);
+int om_pl_launch_flags_check(om_handle* h, const double* xin);
+int om_pl_launch_flips(om_handle* h);
+int om_pl_launch_round(om_handle* h, const double* xin);
+int om_pl_launch_round_end(om_handle* h, unsigned long long handle, int use_handle);
+int om_run_pipelined(om_handle* h, double tol, int64_t max_num_steps, int64_t* steps_done,
+                     om_step_stats* last);
+void om_pl_destroy(om_handle* h);
 // pcg.cu
 int om_pcg_impl(om_handle* h, double rtol, int max_iter, int32_t* iters, double* relres,
                 double* out /* N*PD, may alias h->xnew */);

@@ -59,6 +59,13 @@ __device__ __forceinline__ int sel3i(const int (&a)[3], int k) {
   return k == 0 ? a[0] : (k == 1 ? a[1] : a[2]);
 }
 
+// s = ce_k(c) + ce_k'(c') (A.7) from the two cells' own ed and squared areas: the one place
+// where s is evaluated, so that every kernel sees the same bits for the same edge
+__device__ __forceinline__ double delaunay_s(double edk, double vol2, double ednk, double vol2n) {
+  const double inv4A = 0.25 / sqrt(vol2), inv4An = 0.25 / sqrt(vol2n);
+  return __dadd_rn(__dmul_rn(-edk, inv4A), __dmul_rn(-ednk, inv4An));
+}
+
 // One thread per cell (all cells, or the work list).  A triangle has at most one obtuse
 // angle, and an edge can only violate the Delaunay criterion if one of its two opposite
 // angles is obtuse (ed > 0): so every cell examines at most ONE edge -- the one opposite
@@ -89,9 +96,10 @@ __global__ void __launch_bounds__(256, (D == 2 ? 5 : 4))  // 2D: <= 51 registers
     k_suspect(const double* __restrict__ x, const int4* __restrict__ cells,
               const int* __restrict__ adj, int off, int n, const int* __restrict__ list,
               double tol, double* __restrict__ sarr, int* __restrict__ cand,
-              int* __restrict__ cand_epoch, int epoch, FlipRec* __restrict__ recs,
+              int* __restrict__ cand_epoch, FlipRec* __restrict__ recs,
               DevScalars* ds, const int* __restrict__ n_dev, ShardInfo sh) {
   if (n_dev) n = *n_dev;  // length known only on the device (chained rounds)
+  const int epoch = ds->epoch;
   // list modes: block-stride loop (chained rounds run on a fixed grid whatever the list length
   // is); range modes: exactly one trip per block (the loop form cost the range check 0.1 ms)
   constexpr bool LOOP = MODE == 1 || MODE == 3;
@@ -156,9 +164,7 @@ __global__ void __launch_bounds__(256, (D == 2 ? 5 : 4))  // 2D: <= 51 registers
       const double ea = sel3(ed, k), eb = sel3(edn, kn);
       if (tol >= 0.0 && eb < 0.0 && !(ea * ea * vol2n > eb * eb * vol2 * (1.0 - 1e-9))) break;
     }
-    const double inv4A = 0.25 / sqrt(vol2), inv4An = 0.25 / sqrt(vol2n);
-    const double s =
-        __dadd_rn(__dmul_rn(-sel3(ed, k), inv4A), __dmul_rn(-sel3(edn, kn), inv4An));
+    const double s = delaunay_s(sel3(ed, k), vol2, sel3(edn, kn), vol2n);
     if (s < -tol) {
       he = 4 * c + k;
       tt = t;
@@ -210,9 +216,9 @@ __global__ void __launch_bounds__(256, (D == 2 ? 5 : 4))  // 2D: <= 51 registers
 // flagged-edge records (own or received from other ranks) -> s slots + candidate list
 __global__ void __launch_bounds__(256)
     k_apply_records(const FlipRec* __restrict__ recs, int n, double* __restrict__ sarr,
-                    int* __restrict__ cand, int* __restrict__ cand_epoch, int epoch,
-                    DevScalars* ds) {
+                    int* __restrict__ cand, int* __restrict__ cand_epoch, DevScalars* ds) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int epoch = ds->epoch;
   int c = -1, cn = -1;
   if (i < n) {
     const FlipRec r = recs[i];
@@ -262,8 +268,9 @@ __global__ void k_round_scan(const FlipRec* __restrict__ gathered, int P, int ca
 __global__ void __launch_bounds__(256)
     k_apply_gathered(const FlipRec* __restrict__ gathered, int P, int cap,
                      double* __restrict__ sarr, int* __restrict__ cand,
-                     int* __restrict__ cand_epoch, int epoch, DevScalars* ds) {
+                     int* __restrict__ cand_epoch, DevScalars* ds) {
   if (ds->abort) return;
+  const int epoch = ds->epoch;
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   int c = -1, cn = -1;
   if (i < (long long)P * cap) {
@@ -312,12 +319,13 @@ __global__ void __launch_bounds__(256)
 
 __global__ void __launch_bounds__(256)
     k_flip1(int4* __restrict__ cells, const int4* __restrict__ adj, const int8_t* __restrict__ best,
-            const int* __restrict__ cand, int n, int epoch, int* __restrict__ flip_epoch,
+            const int* __restrict__ cand, int n, int* __restrict__ flip_epoch,
             int* __restrict__ reloc, int4* __restrict__ adj_tmp, int* __restrict__ v2c,
-            int* __restrict__ dirty, int* __restrict__ dirty_epoch, int dirty_pass,
+            int* __restrict__ dirty, int* __restrict__ dirty_epoch,
             DevScalars* ds, const int* __restrict__ n_dev, int vlo, int vhi) {
   if (ds->abort) return;
   if (n_dev) n = *n_dev;
+  const int epoch = ds->epoch, dirty_pass = ds->dirty_pass;
   for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
   const int i = base + threadIdx.x;
   int nf = 0;
@@ -385,11 +393,12 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     k_flip2(int* __restrict__ adj, const int4* __restrict__ adj_tmp,
             const int* __restrict__ flip_epoch, const int* __restrict__ reloc,
-            const int* __restrict__ cand, int n, int epoch, int* __restrict__ work_epoch,
+            const int* __restrict__ cand, int n, int* __restrict__ work_epoch,
             int* __restrict__ work, int8_t* __restrict__ best, DevScalars* ds,
             const int* __restrict__ n_dev, int clo, int chi) {
   if (ds->abort) return;
   if (n_dev) n = *n_dev;
+  const int epoch = ds->epoch;
   for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
   const int i = base + threadIdx.x;
   // cells to enlist for the next round: self (flipped or lost), the two outer neighbours
@@ -428,23 +437,265 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// new_pass: also clears the per-pass counters (flips are counted over the whole pass)
+// Starts a check round: new stamp for the cell lists; new_pass also starts a flip pass (clears
+// the per-pass counters, new stamp for the dirty-vertex list).
 __global__ void k_reset_flip_scalars(DevScalars* ds, int new_pass) {
+  ds->epoch++;
   ds->n_flagged = 0;
   ds->stale = 0;
   ds->abort = 0;
   ds->n_cand = 0;
   ds->n_rec = 0;
   if (new_pass) {
+    ds->dirty_pass++;
+    ds->n_dirty = 0;
     ds->n_flips = 0;
     ds->n_work = 0;
     ds->n_rounds = 0;
     ds->flips_prev = 0;
+    ds->not_delaunay = 0;
   } else if (ds->n_flips > ds->flips_prev) {
     // the round that just ended flipped something (the reference counts only those)
     ds->n_rounds++;
     ds->flips_prev = ds->n_flips;
   }
+}
+
+// ---- fused check of the pipelined loop (loop.cu).  The step kernel evaluates, for every
+// spoke of every vertex, twice the Delaunay indicator of that edge on the way (chain.cuh) and
+// leaves "spoke q may violate the criterion" bits in the vertex's flag word (bit 9: check all
+// my spokes -- vertices the ring kernel does not evaluate itself).  This kernel scans the flag
+// words, compacts the flagged vertices chunk by chunk, walks their stars in ring-row order to
+// name the half-edge of each flagged spoke and takes the decision on the exact s, like
+// k_suspect.  Flagged cells go to the candidate list through a list in shared memory: one
+// atomic on the global counter per chunk.
+constexpr unsigned VF_SPOKES = 0xffu, VF_DEFER = 0x100u, VF_CHECKALL = 0x200u;
+constexpr int FLG_BLOCK = 256, FLG_PER = 8, FLG_OUT = 4096;
+
+template <int D>
+__device__ __forceinline__ void check_half_edge(const double* __restrict__ x,
+                                                const int4* __restrict__ cells,
+                                                const int* __restrict__ adj, int c, int k,
+                                                const int4& cl, double tol,
+                                                double* __restrict__ sarr,
+                                                int* __restrict__ cand_epoch, int epoch,
+                                                int* s_out, int* s_nout, int* __restrict__ cand,
+                                                DevScalars* ds) {
+  const int t = __ldg(adj + 4 * (size_t)c + k);
+  if (t < 0) return;  // boundary edge
+  const int cn = t >> 2, kn = t & 3;
+  const int4 cln = __ldg(cells + cn);
+  const Vec<D> P[3] = {ld_point<D>(x, cl.x), ld_point<D>(x, cl.y), ld_point<D>(x, cl.z)};
+  const Vec<D> Q[3] = {ld_point<D>(x, cln.x), ld_point<D>(x, cln.y), ld_point<D>(x, cln.z)};
+  double ed[3], edn[3];
+  cell_ed<D>(P, ed);
+  cell_ed<D>(Q, edn);
+  const double vol2 = vol2_of(ed), vol2n = vol2_of(edn);
+  if (!(vol2 > 0.0) || !(vol2n > 0.0)) {
+    atomicOr(&ds->err, OM_DEV_DEGENERATE);
+    return;
+  }
+  const double s = delaunay_s(sel3(ed, k), vol2, sel3(edn, kn), vol2n);
+  if (!(s < -tol)) return;
+  sarr[4 * (size_t)c + k] = s;
+  sarr[t] = s;
+  const int ids[2] = {c, cn};
+#pragma unroll
+  for (int i = 0; i < 2; i++)
+    if (atomicExch(&cand_epoch[ids[i]], epoch) != epoch) {
+      const int pos = atomicAdd(s_nout, 1);
+      if (pos < FLG_OUT)
+        s_out[pos] = ids[i];
+      else
+        cand[atomicAdd(&ds->n_cand, 1)] = ids[i];  // overflow of the block list (rare)
+    }
+}
+
+template <int D>
+__global__ void __launch_bounds__(FLG_BLOCK)
+    k_suspect_flags(const double* __restrict__ x, const int4* __restrict__ cells,
+                    const int* __restrict__ adj, const int* __restrict__ v2c,
+                    unsigned short* __restrict__ vflags, int N, double tol,
+                    double* __restrict__ sarr, int* __restrict__ cand,
+                    int* __restrict__ cand_epoch, DevScalars* ds) {
+  if (ds->halt) return;
+  constexpr int CHUNK = FLG_BLOCK * FLG_PER;
+  __shared__ int s_v[CHUNK];
+  __shared__ unsigned short s_f[CHUNK];
+  __shared__ int s_out[FLG_OUT];
+  __shared__ int s_warp[FLG_BLOCK / 32];
+  __shared__ int s_total, s_nout, s_base;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int epoch = ds->epoch;
+  const int nchunks = (N + CHUNK - 1) / CHUNK;
+  for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    const int vb = chunk * CHUNK + threadIdx.x * FLG_PER;
+    unsigned short w[FLG_PER];
+    int cnt = 0;
+    if (vb < N) {
+      // (the flag array is padded to a multiple of FLG_PER words beyond N)
+      const uint4 raw = *reinterpret_cast<const uint4*>(vflags + vb);
+      const unsigned r[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+      for (int i = 0; i < FLG_PER; i++) {
+        w[i] = (unsigned short)((r[i >> 1] >> (16 * (i & 1))) & (VF_SPOKES | VF_CHECKALL));
+        if (vb + i >= N) w[i] = 0;
+        cnt += w[i] ? 1 : 0;
+      }
+      if (raw.x | raw.y | raw.z | raw.w)  // every bit has been consumed by now
+        *reinterpret_cast<uint4*>(vflags + vb) = make_uint4(0u, 0u, 0u, 0u);
+    } else {
+#pragma unroll
+      for (int i = 0; i < FLG_PER; i++) w[i] = 0;
+    }
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    if (threadIdx.x == 0) s_nout = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int q = 0; q < FLG_BLOCK / 32; q++) {
+        const int t = s_warp[q];
+        s_warp[q] = tot;
+        tot += t;
+      }
+      s_total = tot;
+    }
+    __syncthreads();
+    int pos = s_warp[warp] + incl - cnt;
+#pragma unroll
+    for (int i = 0; i < FLG_PER; i++)
+      if (w[i]) {
+        s_v[pos] = vb + i;
+        s_f[pos] = w[i];
+        pos++;
+      }
+    __syncthreads();
+    const int total = s_total;
+    for (int it = threadIdx.x; it < total; it += FLG_BLOCK) {
+      const int v = s_v[it];
+      const unsigned f = s_f[it];
+      const bool all = (f & VF_CHECKALL) != 0;
+      const int c0 = v2c[v];
+      if (c0 == OM_NONE_CELL) continue;
+      int4 cl = __ldg(cells + c0);
+      int j = slot_of(cl, v);
+      if (j < 0) {
+        atomicOr(&ds->err, OM_DEV_WALK);
+        continue;
+      }
+      // spoke 0 is the edge of the start cell that the walk does NOT leave through
+      if (all || (f & 1u))
+        check_half_edge<D>(x, cells, adj, c0, (j + 2) % 3, cl, tol, sarr, cand_epoch, epoch, s_out,
+                           &s_nout, cand, ds);
+      int cur = c0, kexit = (j + 1) % 3, q = 1, hops = 0;
+      bool open = false;
+      while (true) {
+        // the walk leaves cell q-1 through spoke q
+        const int t = __ldg(adj + 4 * (size_t)cur + kexit);
+        if (t < 0) {
+          open = true;
+          break;
+        }
+        const int cn = t >> 2, kn = t & 3;
+        if (cn == c0) break;  // closed: this is spoke 0 again
+        if (all || (q < 8 && ((f >> q) & 1u)))
+          check_half_edge<D>(x, cells, adj, cur, kexit, cl, tol, sarr, cand_epoch, epoch, s_out,
+                             &s_nout, cand, ds);
+        cl = __ldg(cells + cn);
+        const int jn = slot_of(cl, v);
+        if (jn < 0 || jn == kn || ++hops > 4096) {
+          atomicOr(&ds->err, OM_DEV_WALK);
+          break;
+        }
+        cur = cn;
+        kexit = 3 - jn - kn;
+        q++;
+      }
+      if (open && all) {
+        // open fan (pinned boundary vertex): the spokes on the other side of the start cell
+        cur = c0;
+        cl = __ldg(cells + c0);
+        kexit = (j + 2) % 3;  // spoke 0 was checked above
+        hops = 0;
+        while (true) {
+          const int t = __ldg(adj + 4 * (size_t)cur + kexit);
+          if (t < 0) break;
+          const int cn = t >> 2, kn = t & 3;
+          cl = __ldg(cells + cn);
+          const int jn = slot_of(cl, v);
+          if (jn < 0 || jn == kn || ++hops > 4096) {
+            atomicOr(&ds->err, OM_DEV_WALK);
+            break;
+          }
+          cur = cn;
+          kexit = 3 - jn - kn;
+          check_half_edge<D>(x, cells, adj, cur, kexit, cl, tol, sarr, cand_epoch, epoch, s_out,
+                             &s_nout, cand, ds);
+        }
+      }
+    }
+    __syncthreads();
+    const int nout = min(s_nout, FLG_OUT);
+    if (threadIdx.x == 0) s_base = nout ? atomicAdd(&ds->n_cand, nout) : 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < nout; i += FLG_BLOCK) cand[s_base + i] = s_out[i];
+    __syncthreads();  // the shared lists are reused by the next chunk
+  }
+}
+
+// ---- control of the pipelined loop: what the host decides between the rounds of a pass
+// starts a flip pass (and its first check round)
+__global__ void k_pl_pass_begin(DevScalars* ds) {
+  if (ds->halt) return;
+  ds->epoch++;
+  ds->dirty_pass++;
+  ds->n_dirty = 0;
+  ds->n_flagged = 0;
+  ds->stale = 0;
+  ds->abort = 0;
+  ds->n_cand = 0;
+  ds->n_rec = 0;
+  ds->n_flips = 0;
+  ds->n_work = 0;
+  ds->n_rounds = 0;
+  ds->flips_prev = 0;
+  ds->not_delaunay = 0;
+}
+
+// starts the check of a further round
+__global__ void k_pl_round_begin(DevScalars* ds) {
+  if (ds->halt) return;
+  ds->epoch++;
+  ds->n_cand = 0;
+}
+
+// ends a round (its flips are done): counts it and decides whether another one follows
+__global__ void k_pl_round_end(DevScalars* ds, cudaGraphConditionalHandle handle, int use_handle) {
+  unsigned go = 0u;
+  if (!ds->halt) {
+    const bool progress = ds->n_flips > ds->flips_prev;
+    if (progress) {
+      ds->n_rounds++;
+      ds->flips_prev = ds->n_flips;
+    }
+    if (ds->n_cand > 0) {
+      if (!progress)
+        ds->not_delaunay = 1;  // flagged but no mutual pair (exact ties): leave it at that
+      else if (ds->n_rounds >= ds->max_rounds)
+        ds->cap_hit = 1;
+      else
+        go = 1u;
+    }
+  }
+  ds->pl_go = (int)go;
+  ds->pl_launches += 6;  // begin, check, select, flip1, flip2, end
+  if (use_handle) cudaGraphSetConditional(handle, go);
 }
 
 // Host loop of one flip pass.  Every round is ONE chain of launches -- check, select, flip,
@@ -456,7 +707,7 @@ __global__ void k_reset_flip_scalars(DevScalars* ds, int new_pass) {
 // flip_spec == 0 (the previous pass flagged nothing) reads back right after the check.
 template <int D>
 int flip_rounds(om_handle* h, double tol, int max_rounds, int64_t* n_flips, int32_t* n_rounds,
-                int32_t* cap_hit, bool first_round_given) {
+                int32_t* cap_hit, bool first_round_given, bool keep_pass = false) {
   const int C = (int)h->C;
   const int B = 256;
   const int GMAX = 148 * 8;  // resident blocks of the list kernels on one B200
@@ -466,21 +717,20 @@ int flip_rounds(om_handle* h, double tol, int max_rounds, int64_t* n_flips, int3
   auto launch_flips = [&](int n_host, const int* n_dev, long long bound) {
     const int G = grid_for(bound);
     OM_LAUNCH(h, k_select, G, B, h->sarr, h->cand, n_host, h->best, h->ds, n_dev);
-    OM_LAUNCH(h, k_flip1, G, B, h->cells, h->adj, h->best, h->cand, n_host, h->epoch,
+    OM_LAUNCH(h, k_flip1, G, B, h->cells, h->adj, h->best, h->cand, n_host,
               h->flip_epoch, h->reloc, h->adj_tmp, h->v2c, h->dirty, h->dirty_epoch,
-              h->dirty_pass, h->ds, n_dev, h->flt_vlo, h->flt_vhi);
+              h->ds, n_dev, h->flt_vlo, h->flt_vhi);
     OM_LAUNCH(h, k_flip2, G, B, (int*)h->adj, h->adj_tmp, h->flip_epoch, h->reloc, h->cand,
-              n_host, h->epoch, h->work_epoch, h->work, h->best, h->ds, n_dev, h->flt_clo, h->flt_chi);
+              n_host, h->work_epoch, h->work, h->best, h->ds, n_dev, h->flt_clo, h->flt_chi);
     h->nbr_valid = false;
   };
   int rounds = 0, cap = 0;
   int spec = first_round_given ? 0 : h->flip_spec;
   // ---- round 0: full check (or the records of the sharded check), then its flips
   if (!first_round_given) {
-    OM_LAUNCH(h, k_reset_flip_scalars, 1, 1, h->ds, 1);
-    h->epoch++;
+    OM_LAUNCH(h, k_reset_flip_scalars, 1, 1, h->ds, keep_pass ? 0 : 1);
     OM_LAUNCH(h, (k_suspect<D, 0>), om_grid(C, B), B, h->x, h->cells, (const int*)h->adj, 0, C,
-              (const int*)nullptr, tol, h->sarr, h->cand, h->cand_epoch, h->epoch,
+              (const int*)nullptr, tol, h->sarr, h->cand, h->cand_epoch,
               (FlipRec*)nullptr, h->ds, (const int*)nullptr, ShardInfo{0, 0, 0, 0, nullptr, 0, nullptr});
   }
   long long wb = 0;  // bound on the length of the next work list
@@ -512,9 +762,8 @@ int flip_rounds(om_handle* h, double tol, int max_rounds, int64_t* n_flips, int3
     for (int q = 0; q < chain && !capped; q++, r++) {
       const long long cb = std::min<long long>(2 * std::min<long long>(wb, C), C);  // candidates
       OM_LAUNCH(h, k_reset_flip_scalars, 1, 1, h->ds, 0);
-      h->epoch++;
       OM_LAUNCH(h, (k_suspect<D, 1>), grid_for(wb), B, h->x, h->cells, (const int*)h->adj, 0, 0,
-                h->work, tol, h->sarr, h->cand, h->cand_epoch, h->epoch, (FlipRec*)nullptr,
+                h->work, tol, h->sarr, h->cand, h->cand_epoch, (FlipRec*)nullptr,
                 h->ds, (const int*)&h->ds->n_work, ShardInfo{0, 0, 0, 0, nullptr, 0, nullptr});
       if (r < max_rounds) {
         launch_flips(0, &h->ds->n_cand, cb);
@@ -532,7 +781,12 @@ int flip_rounds(om_handle* h, double tol, int max_rounds, int64_t* n_flips, int3
       cap = 1;
       break;
     }
-    if (h->hs->n_flips == flips_seen) break;  // flagged but no mutual pair (exact ties)
+    if (h->hs->n_flips == flips_seen) {
+      // flagged but no mutual pair (exact ties of s around a cycle of cells): the mesh is
+      // left as it is and the caller is told (the Python layer warns)
+      cap = 2;
+      break;
+    }
     flips_seen = h->hs->n_flips;
     wb = 4ll * n_cand;
   }
@@ -562,8 +816,6 @@ static ShardInfo shard_info(om_handle* h, int64_t clo, int64_t chi) {
 //      om_flip_add_records / om_flip_round_apply / om_flip_pass_end)
 int om_flip_pass_begin_impl(om_handle* h) {
   if (!h->recs) CUDA_TRY(om_malloc(h, &h->recs, sizeof(FlipRec) * std::max<int64_t>(h->C, 1)));
-  h->dirty_pass++;
-  CUDA_TRY(cudaMemsetAsync(&h->ds->n_dirty, 0, sizeof(int), h->stream));
   OM_LAUNCH(h, k_reset_flip_scalars, 1, 1, h->ds, 1);
   h->pass_work_bound = 0;
   return OM_OK;
@@ -574,7 +826,6 @@ int om_flip_round_check_impl(om_handle* h, double tol, int first, int64_t clo, i
   const int B = 256;
   // also right for a repeated call after a coordinate refresh (clears records and `stale`)
   OM_LAUNCH(h, k_reset_flip_scalars, 1, 1, h->ds, 0);
-  h->epoch++;
   const ShardInfo sh = shard_info(h, clo, chi);
   // every rank applies all flips of the round, but enlists only what it will look at itself
   static const bool no_filter = getenv("OM_NO_LIST_FILTER") != nullptr;  // diagnostics
@@ -588,21 +839,21 @@ int om_flip_round_check_impl(om_handle* h, double tol, int first, int64_t clo, i
     const int n = (int)(chi - clo);
     if (h->D == 2)
       OM_LAUNCH(h, (k_suspect<2, 2>), om_grid(n, B), B, h->x, h->cells, (const int*)h->adj,
-                (int)clo, n, (const int*)nullptr, tol, h->sarr, h->cand, h->cand_epoch, h->epoch,
+                (int)clo, n, (const int*)nullptr, tol, h->sarr, h->cand, h->cand_epoch,
                 h->recs, h->ds, (const int*)nullptr, sh);
     else
       OM_LAUNCH(h, (k_suspect<3, 2>), om_grid(n, B), B, h->x, h->cells, (const int*)h->adj,
-                (int)clo, n, (const int*)nullptr, tol, h->sarr, h->cand, h->cand_epoch, h->epoch,
+                (int)clo, n, (const int*)nullptr, tol, h->sarr, h->cand, h->cand_epoch,
                 h->recs, h->ds, (const int*)nullptr, sh);
   } else if (h->pass_work_bound > 0) {
     const int nb = (int)std::min<int64_t>(h->pass_work_bound, h->C);
     if (h->D == 2)
       OM_LAUNCH(h, (k_suspect<2, 3>), om_grid(nb, B), B, h->x, h->cells, (const int*)h->adj, 0, 0,
-                h->work, tol, h->sarr, h->cand, h->cand_epoch, h->epoch, h->recs, h->ds,
+                h->work, tol, h->sarr, h->cand, h->cand_epoch, h->recs, h->ds,
                 (const int*)&h->ds->n_work, sh);
     else
       OM_LAUNCH(h, (k_suspect<3, 3>), om_grid(nb, B), B, h->x, h->cells, (const int*)h->adj, 0, 0,
-                h->work, tol, h->sarr, h->cand, h->cand_epoch, h->epoch, h->recs, h->ds,
+                h->work, tol, h->sarr, h->cand, h->cand_epoch, h->recs, h->ds,
                 (const int*)&h->ds->n_work, sh);
   }
   if (!fetch) return OM_OK;  // the counts stay on the device (om_flip_round_pack)
@@ -627,15 +878,15 @@ int om_flip_round_apply_gathered_impl(om_handle* h, const void* gathered, int P,
   const FlipRec* g = (const FlipRec*)gathered;
   OM_LAUNCH(h, k_round_scan, 1, 1, g, P, cap, h->ds);
   OM_LAUNCH(h, k_apply_gathered, om_grid((int64_t)P * cap, B), B, g, P, cap, h->sarr, h->cand,
-            h->cand_epoch, h->epoch, h->ds);
+            h->cand_epoch, h->ds);
   const int bound = (int)std::min<int64_t>(2ll * P * cap, h->C);
   const int* nd = &h->ds->n_cand;
   OM_LAUNCH(h, k_select, om_grid(bound, B), B, h->sarr, h->cand, 0, h->best, h->ds, nd);
-  OM_LAUNCH(h, k_flip1, om_grid(bound, B), B, h->cells, h->adj, h->best, h->cand, 0, h->epoch,
-            h->flip_epoch, h->reloc, h->adj_tmp, h->v2c, h->dirty, h->dirty_epoch, h->dirty_pass,
+  OM_LAUNCH(h, k_flip1, om_grid(bound, B), B, h->cells, h->adj, h->best, h->cand, 0,
+            h->flip_epoch, h->reloc, h->adj_tmp, h->v2c, h->dirty, h->dirty_epoch,
             h->ds, nd, h->flt_vlo, h->flt_vhi);
   OM_LAUNCH(h, k_flip2, om_grid(bound, B), B, (int*)h->adj, h->adj_tmp, h->flip_epoch, h->reloc,
-            h->cand, 0, h->epoch, h->work_epoch, h->work, h->best, h->ds, nd, h->flt_clo, h->flt_chi);
+            h->cand, 0, h->work_epoch, h->work, h->best, h->ds, nd, h->flt_clo, h->flt_chi);
   h->nbr_valid = false;
   OM_TRY(om_fetch_scalars(h));
   OM_TRY(om_check_dev_err(h));
@@ -655,11 +906,11 @@ int om_flip_round_apply_impl(om_handle* h, int64_t total_records, int64_t* n_can
   if (bound > 0) {
     const int* nd = &h->ds->n_cand;
     OM_LAUNCH(h, k_select, om_grid(bound, B), B, h->sarr, h->cand, 0, h->best, h->ds, nd);
-    OM_LAUNCH(h, k_flip1, om_grid(bound, B), B, h->cells, h->adj, h->best, h->cand, 0, h->epoch,
+    OM_LAUNCH(h, k_flip1, om_grid(bound, B), B, h->cells, h->adj, h->best, h->cand, 0,
               h->flip_epoch, h->reloc, h->adj_tmp, h->v2c, h->dirty, h->dirty_epoch,
-              h->dirty_pass, h->ds, nd, h->flt_vlo, h->flt_vhi);
+              h->ds, nd, h->flt_vlo, h->flt_vhi);
     OM_LAUNCH(h, k_flip2, om_grid(bound, B), B, (int*)h->adj, h->adj_tmp, h->flip_epoch, h->reloc,
-              h->cand, 0, h->epoch, h->work_epoch, h->work, h->best, h->ds, nd, h->flt_clo, h->flt_chi);
+              h->cand, 0, h->work_epoch, h->work, h->best, h->ds, nd, h->flt_clo, h->flt_chi);
     h->nbr_valid = false;
   }
   OM_TRY(om_fetch_scalars(h));
@@ -683,19 +934,16 @@ int om_flip_check_range_impl(om_handle* h, double tol, int64_t clo, int64_t chi,
                              int64_t* n_records) {
   const int B = 256;
   if (!h->recs) CUDA_TRY(om_malloc(h, &h->recs, sizeof(FlipRec) * std::max<int64_t>(h->C, 1)));
-  h->dirty_pass++;  // a new flip pass starts here
-  CUDA_TRY(cudaMemsetAsync(&h->ds->n_dirty, 0, sizeof(int), h->stream));
-  OM_LAUNCH(h, k_reset_flip_scalars, 1, 1, h->ds, 1);
-  h->epoch++;
+  OM_LAUNCH(h, k_reset_flip_scalars, 1, 1, h->ds, 1);  // a new flip pass starts here
   const int n = (int)(chi - clo);
   if (n > 0) {
     if (h->D == 2)
       OM_LAUNCH(h, (k_suspect<2, 2>), om_grid(n, B), B, h->x, h->cells, (const int*)h->adj,
-                (int)clo, n, (const int*)nullptr, tol, h->sarr, h->cand, h->cand_epoch, h->epoch,
+                (int)clo, n, (const int*)nullptr, tol, h->sarr, h->cand, h->cand_epoch,
                 h->recs, h->ds, (const int*)nullptr, shard_info(h, clo, chi));
     else
       OM_LAUNCH(h, (k_suspect<3, 2>), om_grid(n, B), B, h->x, h->cells, (const int*)h->adj,
-                (int)clo, n, (const int*)nullptr, tol, h->sarr, h->cand, h->cand_epoch, h->epoch,
+                (int)clo, n, (const int*)nullptr, tol, h->sarr, h->cand, h->cand_epoch,
                 h->recs, h->ds, (const int*)nullptr, shard_info(h, clo, chi));
   }
   OM_TRY(om_fetch_scalars(h));
@@ -707,7 +955,7 @@ int om_flip_check_range_impl(om_handle* h, double tol, int64_t clo, int64_t chi,
 int om_flip_add_records_impl(om_handle* h, const void* recs, int64_t n) {
   if (n <= 0) return OM_OK;
   OM_LAUNCH(h, k_apply_records, om_grid(n, 256), 256, (const FlipRec*)recs, (int)n, h->sarr,
-            h->cand, h->cand_epoch, h->epoch, h->ds);
+            h->cand, h->cand_epoch, h->ds);
   CUDA_TRY(cudaGetLastError());
   return OM_OK;
 }
@@ -723,10 +971,6 @@ int om_flip_impl(om_handle* h, double tol, int max_rounds, int64_t* n_flips, int
   // whole-mesh pass: every list covers the whole mesh
   h->flt_vlo = h->flt_clo = 0;
   h->flt_vhi = h->flt_chi = 0x7fffffff;
-  if (!first_round_given) {
-    h->dirty_pass++;
-    CUDA_TRY(cudaMemsetAsync(&h->ds->n_dirty, 0, sizeof(int), h->stream));
-  }
   if (h->timing) cudaEventRecord(h->ev[2], h->stream);
   int rc = (h->D == 2)
                ? flip_rounds<2>(h, tol, max_rounds, n_flips, n_rounds, cap_hit, first_round_given)
@@ -744,4 +988,57 @@ int om_flip_impl(om_handle* h, double tol, int max_rounds, int64_t* n_flips, int
     }
   }
   return rc;
+}
+
+// ---- launchers of the pipelined loop (loop.cu); everything reads its list lengths and
+// stamps on the device and returns at once when the loop has halted
+int om_pl_launch_flags_check(om_handle* h, const double* xin) {
+  OM_LAUNCH(h, k_pl_pass_begin, 1, 1, h->ds);
+  const int chunks = om_grid(h->N, FLG_BLOCK * FLG_PER);
+  const int G = std::min(chunks, 148 * 4);
+  if (h->D == 2)
+    OM_LAUNCH(h, k_suspect_flags<2>, G, FLG_BLOCK, xin, h->cells, (const int*)h->adj, h->v2c,
+              h->vflags, (int)h->N, 0.0, h->sarr, h->cand, h->cand_epoch, h->ds);
+  else
+    OM_LAUNCH(h, k_suspect_flags<3>, G, FLG_BLOCK, xin, h->cells, (const int*)h->adj, h->v2c,
+              h->vflags, (int)h->N, 0.0, h->sarr, h->cand, h->cand_epoch, h->ds);
+  CUDA_TRY(cudaGetLastError());
+  return OM_OK;
+}
+
+// select + flip + twin patch on the candidate list (k_select and the flip kernels return at
+// once on an empty list; ds->abort is 0 in the pipelined loop)
+int om_pl_launch_flips(om_handle* h) {
+  const int B = 256, G = 148 * 8;
+  const int* nd = &h->ds->n_cand;
+  OM_LAUNCH(h, k_select, G, B, h->sarr, h->cand, 0, h->best, h->ds, nd);
+  OM_LAUNCH(h, k_flip1, G, B, h->cells, h->adj, h->best, h->cand, 0, h->flip_epoch, h->reloc,
+            h->adj_tmp, h->v2c, h->dirty, h->dirty_epoch, h->ds, nd, 0, 0x7fffffff);
+  OM_LAUNCH(h, k_flip2, G, B, (int*)h->adj, h->adj_tmp, h->flip_epoch, h->reloc, h->cand, 0,
+            h->work_epoch, h->work, h->best, h->ds, nd, 0, 0x7fffffff);
+  CUDA_TRY(cudaGetLastError());
+  h->nbr_valid = false;
+  return OM_OK;
+}
+
+// a further round: exact check of the work list, then its flips
+int om_pl_launch_round(om_handle* h, const double* xin) {
+  const int B = 256, G = 148 * 8;
+  OM_LAUNCH(h, k_pl_round_begin, 1, 1, h->ds);
+  const ShardInfo none{0, 0, 0, 0, nullptr, 0, nullptr};
+  if (h->D == 2)
+    OM_LAUNCH(h, (k_suspect<2, 1>), G, B, xin, h->cells, (const int*)h->adj, 0, 0, h->work, 0.0,
+              h->sarr, h->cand, h->cand_epoch, (FlipRec*)nullptr, h->ds,
+              (const int*)&h->ds->n_work, none);
+  else
+    OM_LAUNCH(h, (k_suspect<3, 1>), G, B, xin, h->cells, (const int*)h->adj, 0, 0, h->work, 0.0,
+              h->sarr, h->cand, h->cand_epoch, (FlipRec*)nullptr, h->ds,
+              (const int*)&h->ds->n_work, none);
+  return om_pl_launch_flips(h);
+}
+
+int om_pl_launch_round_end(om_handle* h, unsigned long long handle, int use_handle) {
+  OM_LAUNCH(h, k_pl_round_end, 1, 1, h->ds, (cudaGraphConditionalHandle)handle, use_handle);
+  CUDA_TRY(cudaGetLastError());
+  return OM_OK;
 }

@@ -71,9 +71,10 @@ __device__ __forceinline__ Vec<D> vsub(const Vec<D>& a, const Vec<D>& b) {
 }
 template <int D>
 __device__ __forceinline__ double vdot(const Vec<D>& a, const Vec<D>& b) {
+  // explicit fma chain: the same bits in every kernel, whatever the compiler would contract
   double s = a.v[0] * b.v[0];
 #pragma unroll
-  for (int k = 1; k < D; k++) s += a.v[k] * b.v[k];
+  for (int k = 1; k < D; k++) s = fma(a.v[k], b.v[k], s);
   return s;
 }
 

@@ -23,6 +23,7 @@
 //   k_reduce_stats  max |diff|^2 and the number of limited vertices from `diff2`.
 // No kernel on this path uses an atomic on coordinates or a floating-point atomic: every sum
 // runs in walk order, which is a function of the mesh only (bitwise reproducible).
+#include <cstdlib>
 #include <cstring>
 #include <utility>
 
@@ -35,7 +36,7 @@
 #define OM_K1_BLOCK 128
 #endif
 #ifndef OM_K1_MINB
-#define OM_K1_MINB 8
+#define OM_K1_MINB 7
 #endif
 #ifndef OM_K1_UNROLL
 #define OM_K1_UNROLL 2
@@ -74,7 +75,8 @@ __global__ void __launch_bounds__(256)
     k_build_rings(const int4* __restrict__ cells, const int* __restrict__ adj,
                   const int* __restrict__ v2c, const uint8_t* __restrict__ bflag, int n,
                   const int* __restrict__ list, const int* __restrict__ n_dev,
-                  int* __restrict__ ring, int lo, int hi) {
+                  int* __restrict__ ring, int lo, int hi, const int* __restrict__ halt) {
+  if (halt && *halt) return;
   if (n_dev) n = *n_dev;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int v = LIST ? list[i] : i;
@@ -170,6 +172,8 @@ struct StepParams {
   int limiter;
   int odt_bary;    // ODT: cells with a boundary edge contribute their barycenter
   int force_walk;  // diagnostics (OM_NO_RINGS): every free vertex goes through k_post
+  int prefetch_ahead;  // vertices between a block and the one that runs a wave later
+  int gate;  // pipelined loop: return at once if the loop has halted / the other limiter mode is on
   DevScalars* ds;
 };
 
@@ -185,11 +189,24 @@ __global__ void __launch_bounds__(OM_K1_BLOCK, (D == 2 ? (EXACT ? OM_K1_MINB_EXA
   constexpr int PER = (D == 2) ? 1 : 2;  // 16-byte pieces per vertex
   constexpr bool ODT = METHOD == OM_ODT_FIXED_POINT || METHOD == OM_ODT_DP_FP;
   __shared__ double2 ring_sm[OM_RING_W * PER * BLOCK];
+  if (p.gate && (p.ds->halt || (p.ds->mode_exact != 0) != EXACT)) return;
   const int v = p.lo + (int)(blockIdx.x * BLOCK + threadIdx.x);
   if (v >= p.hi) return;
   const int4* rp = reinterpret_cast<const int4*>(p.ring + (size_t)OM_RING_W * v);
   const int4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
   const Vec<D> P0 = ld_point<D>(p.x, v);
+#ifndef OM_K1_NO_PREFETCH
+  {
+    // The first thing a warp does is wait for its ring row to arrive from DRAM (15 % of the
+    // stall samples).  Ask L2 for the row and the point of the vertex that the block one
+    // wave later will start with: same DRAM traffic, but that block finds them in L2.
+    const int vp = v + p.prefetch_ahead;
+    if (vp < p.hi) {
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(p.ring + (size_t)OM_RING_W * vp));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(p.x + (size_t)(D == 2 ? 2 : 4) * vp));
+    }
+  }
+#endif
   if (r0.x < 0 || p.force_walk) {
     if (r0.x == RING_WALK || (p.force_walk && r0.x >= 0)) {
       // free vertex without a row: k_post updates it and checks its spokes
@@ -408,6 +425,7 @@ __global__ void __launch_bounds__(POST_BLOCK) k_post(StepParams p) {
   __shared__ int s_v[CHUNK];
   __shared__ int s_warp[POST_BLOCK / 32];
   __shared__ int s_total;
+  if (p.gate && p.ds->halt) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int base0 = p.lo & ~(POST_PER - 1);  // 16-byte aligned start of the scan
   const int nchunks = (p.hi - base0 + CHUNK - 1) / CHUNK;
@@ -471,6 +489,7 @@ __global__ void __launch_bounds__(POST_BLOCK) k_post(StepParams p) {
 template <int D, int METHOD>
 __global__ void __launch_bounds__(128)
     k_walk_list(StepParams p, const int* __restrict__ list, const int* __restrict__ n_dev) {
+  if (p.gate && p.ds->halt) return;
   const int n = *n_dev;
   int err = 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -482,7 +501,8 @@ __global__ void __launch_bounds__(128)
 
 // max |diff|^2 and number of limited vertices (sign bit) over [lo, hi)
 __global__ void __launch_bounds__(256)
-    k_reduce_stats(const double* __restrict__ diff2, int lo, int hi, DevScalars* ds) {
+    k_reduce_stats(const double* __restrict__ diff2, int lo, int hi, DevScalars* ds, int gate) {
+  if (gate && ds->halt) return;
   unsigned long long mx = 0ull;
   int lim = 0;
   for (int v = lo + blockIdx.x * blockDim.x + threadIdx.x; v < hi; v += gridDim.x * blockDim.x) {
@@ -737,7 +757,8 @@ __global__ void k_sphere_sweep(double* x, int N, double cx, double cy, double cz
   if ((threadIdx.x & 31) == 0 && af > 0.0) atomic_max_nonneg(&ds->max_f_bits, af);
 }
 
-__global__ void k_reset_step_scalars(DevScalars* ds) {
+__global__ void k_reset_step_scalars(DevScalars* ds, int gate) {
+  if (gate && ds->halt) return;
   ds->n_over = 0;
   ds->stale = 0;
   ds->max_diff2_bits = 0ull;
@@ -766,6 +787,12 @@ StepParams make_params(om_handle* h, double* out) {
   p.limiter = h->limiter;
   p.odt_bary = h->odt_bary;
   p.force_walk = h->use_rings ? 0 : 1;
+  {
+    static const int waves = getenv("OM_K1_PREFETCH_BLOCKS") ? atoi(getenv("OM_K1_PREFETCH_BLOCKS"))
+                                                             : 148 * OM_K1_MINB;
+    p.prefetch_ahead = waves * OM_K1_BLOCK;
+  }
+  p.gate = 0;
   p.ds = h->ds;
   return p;
 }
@@ -824,7 +851,7 @@ int om_launch_reduce_stats(om_handle* h) {
   const int hi = h->own_hi >= 0 ? (int)h->own_hi : (int)h->N;
   if (hi > lo)
     OM_LAUNCH(h, k_reduce_stats, std::min(om_grid(hi - lo, 256 * 8), 148 * 8), 256, h->diff2, lo, hi,
-              h->ds);
+              h->ds, 0);
   CUDA_TRY(cudaGetLastError());
   return OM_OK;
 }
@@ -835,10 +862,50 @@ int om_launch_fixup(om_handle* h, double* out) {
   return launch_step(h, p, 4);
 }
 
+// ---- launchers of the pipelined loop (loop.cu).  Every kernel is gated: it returns at once
+// when the loop has halted, and of the two limiter variants of the ring kernel only the one
+// the device selected (ds->mode_exact) does the work -- the host enqueues both.
+int om_pl_launch_update(om_handle* h, const double* xin, double* xout, bool timed) {
+  StepParams p = make_params(h, xout);
+  p.x = xin;
+  p.gate = 1;
+  OM_LAUNCH(h, k_reset_step_scalars, 1, 1, h->ds, 1);
+  if (timed) cudaEventRecord(h->ev[0], h->stream);
+  OM_TRY(launch_step(h, p, 1, false));
+  OM_TRY(launch_step(h, p, 1, true));
+  if (timed) cudaEventRecord(h->ev[1], h->stream);
+  OM_TRY(launch_step(h, p, 2));
+  return OM_OK;
+}
+
+__global__ void k_pl_count(DevScalars* ds, int n) {
+  if (!ds->halt) ds->pl_launches += n;
+}
+
+// after the flip pass: ring rows of the vertices whose star changed, their update recomputed
+// from xin on the new topology, statistics of the whole update
+int om_pl_launch_tail(om_handle* h, const double* xin, double* xout) {
+  OM_LAUNCH(h, (k_build_rings<true>), 148 * 4, 256, h->cells, (const int*)h->adj, h->v2c, h->bflag,
+            0, h->dirty, (const int*)&h->ds->n_dirty, h->ring, 0, (int)h->N,
+            (const int*)&h->ds->halt);
+  StepParams p = make_params(h, xout);
+  p.x = xin;
+  p.gate = 1;
+  OM_TRY(launch_step(h, p, 4));
+  if (h->N > 0)
+    OM_LAUNCH(h, k_reduce_stats, std::min(om_grid(h->N, 256 * 8), 148 * 8), 256, h->diff2, 0,
+              (int)h->N, h->ds, 1);
+  // reset, 2 ring kernels, post, pass begin, flag check, select, flip1, flip2, round end,
+  // rings, fix-up, reduce, this one, iteration end
+  OM_LAUNCH(h, k_pl_count, 1, 1, h->ds, 9);
+  CUDA_TRY(cudaGetLastError());
+  return OM_OK;
+}
+
 int om_update_points_impl(om_handle* h, double tol, om_step_stats* out, bool target_only,
                           double* target_out, bool defer_fetch) {
   if (h->N == 0) return OM_OK;
-  OM_LAUNCH(h, k_reset_step_scalars, 1, 1, h->ds);
+  OM_LAUNCH(h, k_reset_step_scalars, 1, 1, h->ds, 0);
   int32_t iters = 0;
   if (om_is_solve_method(h->method)) {
     double relres = 0.0;
@@ -955,7 +1022,8 @@ int om_rebuild_rings(om_handle* h, bool all, bool device) {
   const int B = 256;
   if (all) {
     OM_LAUNCH(h, (k_build_rings<false>), om_grid(h->N, B), B, h->cells, (const int*)h->adj, h->v2c,
-              h->bflag, (int)h->N, (const int*)nullptr, (const int*)nullptr, h->ring, 0, (int)h->N);
+              h->bflag, (int)h->N, (const int*)nullptr, (const int*)nullptr, h->ring, 0, (int)h->N,
+              (const int*)nullptr);
     h->rings_partial = false;
   } else {
     // with an owned range only its rows are kept current (nothing else reads ring rows);
@@ -965,13 +1033,13 @@ int om_rebuild_rings(om_handle* h, bool all, bool device) {
     const int lo = ranged ? (int)h->own_lo : 0, hi = ranged ? (int)h->own_hi : (int)h->N;
     if (device) {
       OM_LAUNCH(h, (k_build_rings<true>), 148 * 4, B, h->cells, (const int*)h->adj, h->v2c, h->bflag,
-                0, h->dirty, (const int*)&h->ds->n_dirty, h->ring, lo, hi);
+                0, h->dirty, (const int*)&h->ds->n_dirty, h->ring, lo, hi, (const int*)nullptr);
     } else {
       const int n = h->hs->n_dirty;  // fetched by the flip pass
       if (n > 0)
         OM_LAUNCH(h, (k_build_rings<true>), std::min(om_grid(n, B), 148 * 8), B, h->cells,
                   (const int*)h->adj, h->v2c, h->bflag, n, h->dirty, (const int*)nullptr, h->ring,
-                  lo, hi);
+                  lo, hi, (const int*)nullptr);
     }
   }
   CUDA_TRY(cudaGetLastError());

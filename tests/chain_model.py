@@ -52,7 +52,7 @@ def chain_vertex(P0, R, method, omega=1.0, bary=None):
     """One vertex: P0 (d,), ring coordinates R (k, d) in walk order.
 
     Returns dict(d=offset of the relaxed, unlimited update, rmin=smallest incident inradius,
-    min_v4, max_sh (lazy limiter bound), flags=[suspicious spoke q], degenerate)."""
+    min_v4, max_l (lazy limiter bound), flags=[suspicious spoke q], degenerate)."""
     k = R.shape[0]
     d = R - P0
     L = np.einsum("ij,ij->i", d, d)
@@ -68,7 +68,7 @@ def chain_vertex(P0, R, method, omega=1.0, bary=None):
     t2raw = np.zeros(k)
     masked = np.zeros(k, dtype=bool)
     rmin_num, rmin_den = np.inf, 1.0
-    min_v4, max_sh = np.inf, 0.0
+    min_v4, max_l = np.inf, 0.0
     lens = np.sqrt(L)
     for q in range(k):
         r = (q + 1) % k
@@ -78,9 +78,8 @@ def chain_vertex(P0, R, method, omega=1.0, bary=None):
             return dict(degenerate=True)
         rs = 1.0 / np.sqrt(V4)
         # limiter
-        Sh = L[q] + L[r] - c
         min_v4 = min(min_v4, V4)
-        max_sh = max(max_sh, Sh)
+        max_l = max(max_l, L[q], L[r])
         A2 = V4 * rs
         per = lens[q] + lens[r] + np.sqrt(L[q] + L[r] - 2.0 * c)
         if A2 * rmin_den < rmin_num * per:
@@ -132,7 +131,7 @@ def chain_vertex(P0, R, method, omega=1.0, bary=None):
         off = np.linalg.solve(M, NUM / 6.0) if np.linalg.det(M) != 0.0 else np.zeros(dim)
     else:
         off = NUM / (3.0 * W)
-    return dict(d=omega * off, rmin=rmin_num / rmin_den, min_v4=min_v4, max_sh=max_sh,
+    return dict(d=omega * off, rmin=rmin_num / rmin_den, min_v4=min_v4, max_l=max_l,
                 flags=flags, degenerate=False)
 
 
@@ -164,7 +163,7 @@ def step_model(points, cells, method, omega=1.0, is_boundary=None, boundary_cell
         max_diff2 = max(max_diff2, diff2)
         limited = np.sqrt(diff2) > 0.5 * out["rmin"]
         # the lazy bound must never declare a limited vertex "not limited"
-        proves_free = 24.0 * diff2 * out["max_sh"] * (1.0 + 1e-12) <= out["min_v4"]
+        proves_free = 72.0 * diff2 * out["max_l"] * (1.0 + 1e-12) <= out["min_v4"]
         if proves_free and limited:
             lazy_ok = False
         if limited:

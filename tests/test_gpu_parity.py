@@ -734,3 +734,95 @@ def test_partitioned_simulation(ob, G):
     finally:
         for h in hs:
             h.close()
+
+
+# ------------------------------------------------------------------ pipelined loop (loop.cu)
+@pytest.mark.parametrize("method,omega", [("lloyd", 2.0), ("cvt-block-diagonal", 1.0),
+                                          ("cpt-fixed-point", 1.0), ("odt-fixed-point", 1.0),
+                                          ("odt-dp-fp", 1.5)])
+def test_pipelined_loop_equals_stepwise(ob, G, method, omega):
+    """om_run (update with the fused Delaunay check, flips, recomputation of the touched
+    vertices, all in one CUDA graph) against the reference order step by step (om_step):
+    same bytes, same statistics of the last step."""
+    meshes = [G.disk(80, 2), G.disk_mapped_grid(40, 0.28, 1, shuffle=True), G.disk(12, 5)]
+    for pts, cells in meshes:
+        for nsteps in (1, 2, 7):
+            with ob.DeviceMesh(pts, cells) as a:
+                a.set_method(method, omega)
+                steps, last = a.run(0.0, nsteps)
+                pa, ca = a.points, a.cells()
+            with ob.DeviceMesh(pts, cells) as b:
+                b.set_method(method, omega)
+                b.flip_until_delaunay()
+                for _ in range(nsteps):
+                    st = b.step(0.0)
+                pb, cb = b.points, b.cells()
+            assert steps == nsteps
+            assert np.array_equal(ca, cb), (method, nsteps)
+            assert np.array_equal(pa, pb), (method, nsteps)
+            for key in ("max_diff2", "n_limited", "n_flips", "n_flip_rounds"):
+                assert last[key] == st[key], (method, nsteps, key)
+
+
+def test_pipelined_loop_stops_at_tolerance(ob, G):
+    pts, cells = G.disk(60, 7)
+    for method, tol in (("lloyd", 2e-3), ("cvt-block-diagonal", 1e-3)):
+        log = []
+        p, c = ob.optimize_points_cells(pts, cells, method, tol, 200, log=log)  # step by step
+        with ob.DeviceMesh(pts, cells) as dm:
+            dm.set_method(method, 1.0)
+            steps, last = dm.run(tol, 200)
+            assert steps == len(log) and 1 < steps < 200
+            assert np.array_equal(dm.points, p) and np.array_equal(dm.cells(), c)
+            # a second run on the same handle continues from there (graph cache, buffer parity)
+            steps2, _ = dm.run(0.0, 3)
+            p3 = dm.points
+        p4, _ = ob.optimize_points_cells(p, c, method, 0.0, 3)
+        assert steps2 == 3 and rel_err(p3, p4) <= 1e-12
+
+
+def test_pipelined_loop_without_graph(ob, G, tmp_path):
+    """OM_NO_GRAPH=1 runs the same kernels from the stream: same bytes."""
+    import subprocess
+    import sys
+
+    pts, cells = G.disk(70, 3)
+    with ob.DeviceMesh(pts, cells) as dm:
+        dm.set_method("cvt-block-diagonal", 1.0)
+        dm.run(0.0, 6)
+        p, c = dm.points, dm.cells()
+    out = tmp_path / "nograph.npz"
+    code = ("import numpy as np, optimesh_b200 as ob\n"
+            "from optimesh_b200 import generators as G\n"
+            "pts, cells = G.disk(70, 3)\n"
+            "with ob.DeviceMesh(pts, cells) as dm:\n"
+            "    dm.set_method('cvt-block-diagonal', 1.0)\n"
+            "    dm.run(0.0, 6)\n"
+            f"    np.savez(r'{out}', p=dm.points, c=dm.cells())\n")
+    env = dict(os.environ, OM_NO_GRAPH="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run([sys.executable, "-c", code], check=True, env=env, cwd=root)
+    got = np.load(out)
+    assert np.array_equal(got["p"], p) and np.array_equal(got["c"], c)
+
+
+def test_random_walk_gives_a_random_delaunay_mesh(ob, G):
+    """om_random_walk (synthetic 'random disk mesh' workloads): the result is a valid Delaunay
+    triangulation of the same domain, boundary untouched, reproducible, independent of the
+    internal numbering, with the vertex-degree spread of a random mesh."""
+    pts, cells = G.disk_mapped_grid(50, 0.25, 0)
+    res = []
+    for renumber in (True, False, True):
+        with ob.DeviceMesh(pts, cells, renumber=renumber) as dm:
+            nf = dm.random_walk(80, seed=3)
+            res.append((dm.points, dm.cells(), nf))
+            bnd = dm.is_boundary_point
+    p, c, nf = res[0]
+    assert nf > 0
+    assert np.array_equal(res[2][0], p) and np.array_equal(res[2][1], c)
+    assert rel_err(res[1][0], p) <= 1e-13  # same random numbers whatever the numbering
+    assert np.array_equal(p[bnd], pts[bnd])
+    qh = scipy.spatial.Delaunay(p).simplices
+    assert np.array_equal(canonical_cells(c), canonical_cells(qh))
+    val = np.bincount(c.reshape(-1), minlength=len(p))[~bnd]
+    assert (val > 8).mean() > 0.01 and val.max() >= 9
