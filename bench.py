@@ -6,7 +6,9 @@ vertex-updates/s at ~10M vertices, achieved HBM GB/s against peak).
 
 One "step" = one iteration of the optimize() loop on the device: fused point update
 (K1) + flip-until-Delaunay.  At N=1 the workload is BASELINE.json configs[1]: CVT
-block-diagonal on a ~10M-vertex disk mesh, fp64.  Rank 0 prints ONE JSON line.
+block-diagonal on a ~10M-vertex RANDOM disk mesh, fp64 (generators.disk_gpu: mapped grid +
+120 random-walk rounds with flips on the device; Qhull needs 270 s for this size on the host).
+Rank 0 prints ONE JSON line.
 """
 from __future__ import annotations
 
@@ -22,7 +24,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "vertex-updates/s"
-DEFAULT_GRID = 3154  # disk_mapped_grid(3154): 9,947,716 vertices, 19,882,818 cells
+DEFAULT_GRID = 3154  # disk_gpu(3154): 9,947,716 vertices, 19,882,818 cells
+WALK_ROUNDS = 120    # random-walk rounds of disk_gpu (vertex degrees like a Qhull random mesh)
 
 
 def parse():
@@ -33,7 +36,9 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--method", default=None)
     ap.add_argument("--omega", type=float, default=None)
-    ap.add_argument("--grid", type=int, default=None, help="n of disk_mapped_grid(n) per GPU")
+    ap.add_argument("--grid", type=int, default=None, help="n of disk_gpu(n) per GPU")
+    ap.add_argument("--rounds", type=int, default=WALK_ROUNDS,
+                    help="random-walk rounds of the mesh generator (0: jittered mapped grid)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -129,19 +134,22 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
-def make_mesh(grid, seed):
+def random_disk_host(n_target):
+    """Random disk mesh of about n_target vertices built on the host alone (Qhull): the
+    reference's own workload class, used by the CPU arms."""
     from optimesh_b200 import generators as G
 
-    return G.disk_mapped_grid(grid, 0.25, seed)
+    nb = max(8, int(round(2.0 * np.pi / np.sqrt(4.0 * np.pi / (np.sqrt(3.0) * n_target * 2.0)))))
+    return G.disk(nb, 0), nb
 
 
 # --------------------------------------------------------------------------- CPU arms
-def cpu_step_rate(method, omega, grid, steps, warmup):
+def cpu_step_rate(method, omega, n_target, steps, warmup):
     """The oracle (numpy port of the reference's algorithm) timed on the host cores:
-    same step (update + limiter + flip-until-Delaunay), bounded sample."""
+    same step (update + limiter + flip-until-Delaunay) on a random disk mesh, bounded sample."""
     import oracle
 
-    pts, cells = make_mesh(grid, 0)
+    (pts, cells), nb = random_disk_host(n_target)
     mesh = oracle.MeshTri(pts, cells)
     mesh.flip_until_delaunay()
     for _ in range(warmup):
@@ -153,7 +161,7 @@ def cpu_step_rate(method, omega, grid, steps, warmup):
         mesh.flip_until_delaunay()
     dt = time.perf_counter() - t0
     n = pts.shape[0]
-    return n * steps / dt, dt, n, cells.shape[0]
+    return n * steps / dt, dt, n, cells.shape[0], nb
 
 
 def run_reference(args):
@@ -166,17 +174,17 @@ def run_reference(args):
     # the numpy port costs ~25 us per vertex per step on one core
     budget_s = 150.0
     n_target = int(min(1.0e6, max(2.0e4, budget_s / (total * 25e-6))))
-    sample_grid = min(grid, int(np.sqrt(n_target)))
-    v, dt, n, c = cpu_step_rate(method, omega, sample_grid, args.steps, args.warmup)
-    sample = (f"disk_mapped_grid({sample_grid}): {n} vertices / {c} cells, {args.steps} steps of "
-              f"{method} (omega={omega}) incl. limiter and flip-until-Delaunay")
+    v, dt, n, c, nb = cpu_step_rate(method, omega, n_target, args.steps, args.warmup)
+    sample = (f"random disk mesh disk({nb}) (Qhull): {n} vertices / {c} cells, {args.steps} "
+              f"steps of {method} (omega={omega}) incl. limiter and flip-until-Delaunay after "
+              f"{args.warmup} warm-up steps")
     line = {
         "impl": "reference",
         "metric": METRIC, "value": v, "unit": METRIC, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{method} omega={omega} on disk_mapped_grid({grid}) "
-                               f"[reference arm timed on a bounded sample]",
+        "config": {"workload": f"{method} omega={omega} on a random disk mesh "
+                               f"[reference arm timed on a bounded sample of {n} vertices]",
                    "method": method, "omega": omega},
         "cpu_baseline": {"value": v, "unit": METRIC, "cores": 1, "kind": "port", "sample": sample,
                          "host_cores_available": os.cpu_count(),
@@ -189,166 +197,161 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------- GPU arm
-def run_b200(args):
-    import torch
-    import torch.distributed as dist
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    import optimesh_b200 as ob
-
-    method, omega, grid = workload(args)
-    from optimesh_b200.dist import torch_stream_handle
-
-    stream = torch_stream_handle()
-    if world == 1:
-        pts, cells = make_mesh(grid, 0)
-        n, d = pts.shape
-        c = cells.shape[0]
-        dm = ob.DeviceMesh(pts, cells.astype(np.int32), device=local, stream=stream)
-        total_grid = grid
-    else:
-        # one mesh of world x (per-GPU size) vertices, built on every GPU from the same seed
-        from optimesh_b200 import generators as G
-
-        total_grid = int(round(grid * np.sqrt(world)))
-        tp, tc = G.disk_mapped_grid_torch(total_grid, 0.25, 0, device=f"cuda:{local}")
-        n, d = int(tp.shape[0]), int(tp.shape[1])
-        c = int(tc.shape[0])
-        dm = ob.DeviceMesh.from_torch(tp, tc, stream=stream)
-        del tp, tc
-        torch.cuda.empty_cache()
-    dm.set_method(method, omega)
-    band = None
-    if world > 1:
-        from optimesh_b200.dist import owned_range, partitioned_begin, partitioned_step
-
-        lo, hi = owned_range(n, rank, world)
-        band = partitioned_begin(dm)  # own ranges + the loop's initial flip pass (untimed)
-    else:
-        dm.flip_until_delaunay()  # the loop's initial flip pass (setup, untimed)
-
-    def one_step():
-        """One loop iteration; at world > 1 (dist.run_partitioned): own vertex range updated,
-        statistics all-reduced, band of coordinates exchanged over NCCL, every flip-check
-        round split by cell range with its flagged-edge records all-gathered."""
-        if world == 1:
-            return dm.step(0.0)
-        return partitioned_step(dm, band, 0.0)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        one_step()
-    dm.set_timing(True)
-    sampler = ClockSampler(local)
-    barrier()
-    sampler.start()
-    l0 = dm.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    flips = 0
-    rounds = 0
-    limited = 0
-    e0.record()
-    for _ in range(args.steps):
-        st = one_step()
-        flips += st["n_flips"]
-        rounds += st["n_flip_rounds"]
-        limited += st["n_limited"]
-    e1.record()
-    barrier()
-    clocks = sampler.stop()
-    ms = e0.elapsed_time(e1)
-    launches = dm.launch_count - l0
-    tim = dm.timing()
-    dm.set_timing(False)
-    if band is not None:
-        from optimesh_b200 import dist as _d
-
-        if _d.PROFILE:
-            steps_p = max(_d.PROFILE.get("steps", 1), 1)
-            print(f"[rank {rank}] ms/step: " + " ".join(
-                f"{k}={1e3 * v / steps_p:.3f}" if isinstance(v, float) else f"{k}={v}"
-                for k, v in _d.PROFILE.items()), file=sys.stderr)
-        line_band = {"band_vertices_all_ranks": int(sum(band.counts or [0])),
-                     "fallback_full_gathers": band.full_gathers,
-                     "slow_flip_rounds": band.slow_rounds}
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-        cnt = torch.tensor([launches], dtype=torch.int64, device="cuda")
-        dist.all_reduce(cnt)
-        launches = int(cnt[0].item())
-    value = n * args.steps / (ms * 1e-3)  # n = vertices of the whole (sharded) mesh
-
-    # roofline of the dominant kernel (K1, fused step)
-    peak, peak_src = measured_peak()
-    k1_ms = tim["step_kernel_ms"] / max(tim["step_kernel_launches"], 1)
-    n_own = n if world == 1 else (hi - lo)
-    b_alg = alg_bytes(n_own, int(round(c * n_own / max(n, 1))), d)  # this rank's launch
-    achieved = b_alg / (k1_ms * 1e-3) / 1e9
-    traffic = None
+def k1_profile(n, method):
+    """What the committed ncu capture of K1 says for this workload (profiles/k1_traffic.json):
+    DRAM bytes and fp64 warp instructions per launch."""
     tpath = os.path.join(ROOT, "profiles", "k1_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
             tj = json.load(f)
         if tj.get("n_vertices") == n and tj.get("method") == method:
-            traffic = tj.get("dram_bytes_per_launch")
-    roofline = {
-        "kernel": "k_step (fused smoothing step, one thread per vertex)",
+            return tj
+    return {}
+
+
+def roofline_of(k1_ms, b_alg, n, method, extra):
+    peak, peak_src = measured_peak()
+    achieved = b_alg / (k1_ms * 1e-3) / 1e9
+    prof = k1_profile(n, method)
+    out = {
+        "kernel": "k_step_ring (fused smoothing step: one thread per vertex, star evaluated as "
+                  "a chain of spokes, fused Delaunay pre-check)",
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-        "algorithmic_bytes_per_launch": b_alg, "kernel_ms": k1_ms,
-        "kernel_share_of_step": tim["step_kernel_ms"] / ms,
-        "flip_pass_ms": tim["flip_pass_ms"] / max(tim["flip_passes"], 1),
-        "note": "bound by instruction issue (70 % of issue slots, fp64 pipe 47 %): DESIGN.md section 4",
+        "frac": achieved / peak, "traffic": prof.get("dram_bytes_per_launch"),
+        "peak_source": peak_src, "algorithmic_bytes_per_launch": b_alg, "kernel_ms": k1_ms,
     }
+    fp64 = prof.get("fp64_warp_instructions_per_launch")
+    if fp64:
+        # second roofline: the fp64 pipe issues one warp instruction every 2 cycles per SM
+        # sub-partition (64 DFMA/clk/SM): 148 SMs x 4 x 0.5 x 1.965 GHz
+        rate = 148 * 4 * 0.5 * 1.965e9
+        floor_ms = fp64 / rate * 1e3
+        out["fp64_co_roofline"] = {
+            "fp64_warp_instructions_per_launch": fp64,
+            "peak_warp_instructions_per_s": rate,
+            "floor_ms": floor_ms,
+            "frac_of_fp64_peak": floor_ms / k1_ms,
+            "hbm_frac_at_fp64_peak": b_alg / (floor_ms * 1e-3) / 1e9 / peak,
+            "note": "the step is fp64-pipe / HBM co-bound (SURVEY.md hard part 1): with this "
+                    "many fp64 instructions per launch the kernel cannot exceed "
+                    "hbm_frac_at_fp64_peak of the HBM roofline, whatever the memory system does",
+        }
+    out.update(extra)
+    return out
+
+
+def run_single(args, torch, ob, local, stream):
+    """N = 1: BASELINE.json configs[1] through the public loop (DeviceMesh.run = om_run: one
+    CUDA graph holds update + fused Delaunay check + flip rounds + fix-up for all K steps)."""
+    from optimesh_b200 import generators as G
+
+    method, omega, grid = workload(args)
+    t_gen = time.perf_counter()
+    if args.rounds > 0:
+        dm = G.disk_gpu(grid, args.rounds, 0, device=local, stream=stream)
+        mesh_name = (f"random disk mesh disk_gpu({grid}, rounds={args.rounds}): mapped grid + "
+                     f"{args.rounds} random-walk rounds with flips on the device")
+    else:
+        tp, tc = G.disk_mapped_grid_torch(grid, 0.25, 0, device=f"cuda:{local}")
+        dm = ob.DeviceMesh.from_torch(tp, tc, stream=stream)
+        del tp, tc
+        mesh_name = f"jittered mapped grid disk_mapped_grid({grid})"
+    torch.cuda.synchronize()
+    t_gen = time.perf_counter() - t_gen
+    n, d, c = dm.n, dm.dim, dm.c
+    # host copy of the workload (input of the end-to-end calls), taken before any smoothing
+    pts = dm.points
+    cells64 = dm.cells(np.int64)
+    val = np.bincount(cells64.reshape(-1), minlength=n)
+    bnd = dm.is_boundary_point
+    high_valence = float((val[~bnd] > 8).mean())
+    dm.set_method(method, omega)
+    dm.run_prepare()  # graph build stays out of every timed region
+
+    def timed_run(k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        steps, last = dm.run(0.0, k)
+        e1.record()
+        torch.cuda.synchronize()
+        assert steps == k
+        return e0.elapsed_time(e1), dm.run_totals()
+
+    # early phase: the first steps on the fresh random mesh (most vertices limited: exact
+    # limiter variant; many flips).  Also serves as warm-up.
+    early_steps = 5
+    ms_early, tot_early = timed_run(early_steps)
+    if args.warmup > 0:
+        timed_run(args.warmup)
+    sampler = ClockSampler(local)
+    torch.cuda.synchronize()
+    sampler.start()
+    l0 = dm.launch_count
+    torch.cuda.profiler.start()  # ncu --profile-from-start off: only the timed region
+    ms, tot = timed_run(args.steps)
+    torch.cuda.profiler.stop()
+    clocks = sampler.stop()
+    launches = dm.launch_count - l0
+    value = n * args.steps / (ms * 1e-3)
+
+    # K1 with CUDA events around every launch: the same loop driven from the stream
+    # (om_set_timing), over the steps that follow the timed region
+    dm.set_timing(True)
+    dm.run(0.0, args.steps)
+    tim = dm.timing()
+    dm.set_timing(False)
+    k1_ms = tim["step_kernel_ms"] / max(tim["step_kernel_launches"], 1)
+    b_alg = alg_bytes(n, c, d)
+    roofline = roofline_of(k1_ms, b_alg, n, method, {
+        "kernel_share_of_step": k1_ms / (ms / args.steps),
+        "kernel_timing": f"CUDA events around each of {tim['step_kernel_launches']} launches "
+                         f"(both limiter variants are enqueued, one returns at once) in a second "
+                         f"run of {args.steps} steps, stream-launched variant of the same loop",
+        "rest_of_step_ms": ms / args.steps - k1_ms,
+        "note": "rest of the step = k_post + flag-driven Delaunay check + flip rounds + ring "
+                "rows + recomputation of touched vertices + statistics",
+    })
 
     line = {
-        "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps,
+        "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {
-            "workload": f"{method} omega={omega}, disk_mapped_grid({total_grid}): {n} vertices / "
-                        f"{c} cells ({n // world} vertices per GPU), fp64, step = point update + "
-                        f"limiter + flip-until-Delaunay",
+            "workload": f"{method} omega={omega} on a {mesh_name}: {n} vertices / {c} cells, "
+                        f"fp64, step = point update + limiter + flip-until-Delaunay",
             "method": method, "omega": omega, "n_vertices": n, "n_cells": c,
-            "parallelism": "1 GPU" if world == 1 else
-            f"{world} GPUs: vertex ranges of one mesh (topology replicated), update and every "
-            f"flip-check round sharded, band of coordinates + flagged-edge records exchanged "
-            f"over NCCL each step",
-            "l2": "inputs (points+cells+twins = %.0f MB) larger than the 126 MB L2"
-                  % ((16 * n + 32 * c) / 1e6),
+            "interior_vertices_with_more_than_8_cells": high_valence,
+            "mesh_generation_s": t_gen,
+            "parallelism": "1 GPU",
+            "l2": "inputs (points + ring rows = %.0f MB) larger than the 126 MB L2"
+                  % ((16 * n + 32 * n) / 1e6),
         },
         "steps_per_s": args.steps / (ms * 1e-3),
-        "flips_in_timed_region": flips, "flip_rounds_in_timed_region": rounds,
-        "limited_vertex_steps": limited,
+        "flips_per_step": tot["n_flips"] / args.steps,
+        "flip_rounds_per_step": tot["n_flip_rounds"] / args.steps,
+        "limited_vertices_per_step": tot["n_limited"] / args.steps,
+        "deferred_vertices_per_step": tot["n_deferred"] / args.steps,
+        "early_phase": {
+            "steps": early_steps, "ms_per_step": ms_early / early_steps,
+            "value": n * early_steps / (ms_early * 1e-3),
+            "flips_per_step": tot_early["n_flips"] / early_steps,
+            "flip_rounds_per_step": tot_early["n_flip_rounds"] / early_steps,
+            "limited_vertices_per_step": tot_early["n_limited"] / early_steps,
+            "deferred_vertices_per_step": tot_early["n_deferred"] / early_steps,
+            "note": "steps 1-5 on the fresh random mesh (exact-limiter kernel variant)",
+        },
+        "timed_steps": f"steps {early_steps + args.warmup + 1}-"
+                       f"{early_steps + args.warmup + args.steps} of the run",
         "roofline": roofline,
         "clocks": clocks,
         "gpu_launches": launches,
     }
-    if band is not None:
-        line["exchange"] = line_band
-
     dm.close()  # its device memory returns to the pool before the end-to-end calls
-    if rank == 0 and world == 1 and not args.no_e2e:
+    if not args.no_e2e:
         # end to end through the public API with HOST buffers: upload, setup, K steps,
-        # download -- all inside the timed region.  Five calls, the median is reported
-        # (a call that has to grow the driver's memory pool is several times slower, and
-        # host-side page faulting of the fresh 637 MB result arrays jitters).
+        # download -- all inside the timed region.  Five calls, the median is reported.
         e2e_steps = args.steps
-        cells64 = cells  # int64, as numpy produces it
         times = []
         p_out = c_out = None
         for _ in range(5):
@@ -365,21 +368,139 @@ def run_b200(args):
             "h2d_bytes_per_step": (pts.nbytes + cells64.nbytes) / e2e_steps,
             "d2h_bytes_per_step": (p_out.nbytes + c_out.nbytes) / e2e_steps,
             "call": f"optimize_points_cells(points, cells, {method!r}, 0.0, {e2e_steps}, "
-                    f"omega={omega}) on host numpy arrays",
+                    f"omega={omega}) on host numpy arrays (float64 points, int64 cells)",
             "seconds": dt, "seconds_all_calls": times, "steps": e2e_steps,
         }
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sample_grid = 600  # 360,000 vertices: ~10-30 s of single-core numpy
-        v, dt, ns, cs = cpu_step_rate(method, omega, sample_grid, 2, 0)
+    if not args.no_cpu_baseline:
+        v, dt, ns, cs, nb = cpu_step_rate(method, omega, 360000, 2, 0)
         line["cpu_baseline"] = {
             "value": v, "unit": METRIC, "cores": 1, "kind": "port",
-            "sample": f"disk_mapped_grid({sample_grid}): {ns} vertices / {cs} cells, 2 steps of "
-                      f"{method} incl. limiter and flip-until-Delaunay ({dt:.1f} s)",
+            "sample": f"random disk mesh disk({nb}) (Qhull): {ns} vertices / {cs} cells, 2 steps "
+                      f"of {method} incl. limiter and flip-until-Delaunay ({dt:.1f} s)",
             "host_cores_available": os.cpu_count(),
         }
+    print(json.dumps(line), flush=True)
+
+
+def run_multi(args, torch, dist, ob, world, rank, local, stream):
+    """N > 1: one mesh of N x (per-GPU size) vertices, vertex ranges of it updated per rank
+    (dist.py: band exchange of coordinates and round-wise flagged-edge records over NCCL)."""
+    from optimesh_b200 import generators as G
+    from optimesh_b200.dist import owned_range, partitioned_begin, partitioned_step
+
+    method, omega, grid = workload(args)
+    total_grid = int(round(grid * np.sqrt(world)))
+    tp, tc = G.disk_mapped_grid_torch(total_grid, 0.25, 0, device=f"cuda:{local}")
+    n, d = int(tp.shape[0]), int(tp.shape[1])
+    c = int(tc.shape[0])
+    dm = ob.DeviceMesh.from_torch(tp, tc, stream=stream)
+    del tp, tc
+    torch.cuda.empty_cache()
+    if args.rounds > 0:
+        dm.random_walk(args.rounds, 0)  # identical on every rank (hash of the vertex id)
+    dm.set_method(method, omega)
+    lo, hi = owned_range(n, rank, world)
+    band = partitioned_begin(dm)  # own ranges + the loop's initial flip pass (untimed)
+
+    def barrier():
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup + 5):  # the 5 early steps of the single-GPU line are warm-up here
+        partitioned_step(dm, band, 0.0)
+    dm.set_timing(True)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    l0 = dm.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    flips = rounds = limited = 0
+    e0.record()
+    for _ in range(args.steps):
+        st = partitioned_step(dm, band, 0.0)
+        flips += st["n_flips"]
+        rounds += st["n_flip_rounds"]
+        limited += st["n_limited"]
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    launches = dm.launch_count - l0
+    tim = dm.timing()
+    dm.set_timing(False)
+    from optimesh_b200 import dist as _d
+
+    if _d.PROFILE:
+        steps_p = max(_d.PROFILE.get("steps", 1), 1)
+        print(f"[rank {rank}] ms/step: " + " ".join(
+            f"{k}={1e3 * v / steps_p:.3f}" if isinstance(v, float) else f"{k}={v}"
+            for k, v in _d.PROFILE.items()), file=sys.stderr)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    cnt = torch.tensor([launches], dtype=torch.int64, device="cuda")
+    dist.all_reduce(cnt)
+    launches = int(cnt[0].item())
+    value = n * args.steps / (ms * 1e-3)  # n = vertices of the whole (sharded) mesh
+    k1_ms = tim["step_kernel_ms"] / max(tim["step_kernel_launches"], 1)
+    n_own = hi - lo
+    b_alg = alg_bytes(n_own, int(round(c * n_own / max(n, 1))), d)  # this rank's launch
+    roofline = roofline_of(k1_ms, b_alg, n, method, {
+        "kernel_share_of_step": tim["step_kernel_ms"] / ms,
+        "flip_pass_ms": tim["flip_pass_ms"] / max(tim["flip_passes"], 1),
+    })
+    line = {
+        "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {
+            "workload": f"{method} omega={omega} on a random disk mesh (disk_mapped_grid("
+                        f"{total_grid}) + {args.rounds} random-walk rounds): {n} vertices / {c} "
+                        f"cells ({n // world} vertices per GPU), fp64, step = point update + "
+                        f"limiter + flip-until-Delaunay",
+            "method": method, "omega": omega, "n_vertices": n, "n_cells": c,
+            "parallelism": f"{world} GPUs: vertex ranges of one mesh (topology replicated), "
+                           f"update and every flip-check round sharded, band of coordinates + "
+                           f"flagged-edge records exchanged over NCCL each step",
+            "l2": "inputs (points + ring rows = %.0f MB per GPU) larger than the 126 MB L2"
+                  % (48 * n_own / 1e6),
+        },
+        "steps_per_s": args.steps / (ms * 1e-3),
+        "flips_per_step": flips / args.steps, "flip_rounds_per_step": rounds / args.steps,
+        "limited_vertices_per_step": limited / args.steps,
+        "roofline": roofline,
+        "clocks": clocks,
+        "gpu_launches": launches,
+        "exchange": {"band_vertices_all_ranks": int(sum(band.counts or [0])),
+                     "fallback_full_gathers": band.full_gathers,
+                     "slow_flip_rounds": band.slow_rounds},
+    }
+    dm.close()
     if rank == 0:
         print(json.dumps(line), flush=True)
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
     if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import optimesh_b200 as ob
+    from optimesh_b200.dist import torch_stream_handle
+
+    stream = torch_stream_handle()
+    if world == 1:
+        run_single(args, torch, ob, local, stream)
+    else:
+        run_multi(args, torch, dist, ob, world, rank, local, stream)
         dist.destroy_process_group()
 
 

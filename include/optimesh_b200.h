@@ -119,6 +119,16 @@ int om_project(om_handle* h, int32_t* sweeps);
 /* The whole loop of optimize(mesh, method, tol, max_num_steps) on the device. */
 int om_run(om_handle* h, double tol, int64_t max_num_steps, int64_t* steps_done,
            om_step_stats* last);
+/* For the fixed-point methods on one GPU without a surface om_run launches ONE CUDA graph
+ * that holds the whole loop (update with the fused Delaunay check, flip rounds on a device
+ * condition, recomputation of the vertices whose star changed); om_run_prepare builds and
+ * caches that graph for the current method / omega / limiter settings without running it, so
+ * that a caller can keep the build out of a timed region.  om_get_run_totals: flips, flip
+ * rounds, limited vertices and vertices the ring kernel left to its list-driven companion
+ * (no ring row, or the lazy limiter bound failed), summed over the steps of the last om_run. */
+int om_run_prepare(om_handle* h);
+int om_get_run_totals(om_handle* h, int64_t* n_flips, int64_t* n_flip_rounds,
+                      int64_t* n_limited, int64_t* n_deferred);
 
 /* Synthetic workloads ("a randomly generated disk mesh", README.md:70-74): `rounds` times,
  * every free vertex moves by a random vector of length <= amplitude/2 x its smallest

@@ -58,6 +58,9 @@ SIGNATURES = {
     "om_update_points": (C.c_int, [_H, C.c_double, _P(StepStats)]),
     "om_project": (C.c_int, [_H, _P(C.c_int32)]),
     "om_run": (C.c_int, [_H, C.c_double, C.c_int64, _P(C.c_int64), _P(StepStats)]),
+    "om_run_prepare": (C.c_int, [_H]),
+    "om_get_run_totals": (C.c_int, [_H, _P(C.c_int64), _P(C.c_int64), _P(C.c_int64),
+                                    _P(C.c_int64)]),
     "om_random_walk": (C.c_int, [_H, C.c_int, C.c_uint64, C.c_double, _P(C.c_int64)]),
     "om_new_points": (C.c_int, [_H, C.c_void_p]),
     "om_solve_graph_laplacian": (C.c_int, [_H, C.c_double, C.c_int, _P(C.c_int32),

@@ -453,6 +453,7 @@ int om_destroy(om_handle* h) {
   om_free(h, h->v2c);
   om_free(h, h->bflag);
   om_free(h, h->ring);
+  om_free(h, h->ringc);
   om_free(h, h->dirty);
   om_free(h, h->dirty_epoch);
   om_free(h, h->diff2);
@@ -547,6 +548,7 @@ int om_update_points(om_handle* h, double tol, om_step_stats* out) {
 
 int om_project(om_handle* h, int32_t* sweeps) {
   OM_ENTER(h);
+  h->delaunay_clean = false;
   return om_project_impl(h, sweeps);
 }
 
@@ -581,11 +583,15 @@ int om_run(om_handle* h, double tol, int64_t max_num_steps, int64_t* steps_done,
   memset(&st, 0, sizeof(st));
   int64_t nf = 0;
   int32_t nr = 0, cap = 0;
-  OM_TRY(om_flip_impl(h, 0.0, 100, &nf, &nr, &cap));
+  if (!h->delaunay_clean) OM_TRY(om_flip_impl(h, 0.0, 100, &nf, &nr, &cap));
   int64_t k = 0;
+  h->run_flips = h->run_rounds = h->run_limited = h->run_deferred = 0;
   while (true) {
     k++;
     OM_TRY(om_step(h, tol, &st));
+    h->run_flips += st.n_flips;
+    h->run_rounds += st.n_flip_rounds;
+    h->run_limited += st.n_limited;
     if (st.is_final || k >= max_num_steps) break;
   }
   if (steps_done) *steps_done = k;
@@ -609,6 +615,22 @@ int om_random_walk(om_handle* h, int rounds, uint64_t seed, double amplitude, in
     total += nf;
   }
   if (n_flips) *n_flips = total;
+  return OM_OK;
+}
+
+int om_run_prepare(om_handle* h) {
+  OM_ENTER(h);
+  if (om_is_solve_method(h->method) || h->surf_kind != 0 || h->own_hi >= 0) return OM_OK;
+  return om_pl_prepare(h);
+}
+
+int om_get_run_totals(om_handle* h, int64_t* n_flips, int64_t* n_flip_rounds, int64_t* n_limited,
+                      int64_t* n_deferred) {
+  OM_ENTER(h);
+  if (n_deferred) *n_deferred = h->run_deferred;
+  if (n_flips) *n_flips = h->run_flips;
+  if (n_flip_rounds) *n_flip_rounds = h->run_rounds;
+  if (n_limited) *n_limited = h->run_limited;
   return OM_OK;
 }
 
@@ -642,6 +664,7 @@ int om_solve_graph_laplacian(om_handle* h, double rtol, int max_iter, int32_t* i
   OM_ENTER(h);
   OM_TRY(om_pcg_impl(h, rtol, max_iter, iters, rel_residual, h->xnew));
   std::swap(h->x, h->xnew);
+  h->delaunay_clean = false;
   return OM_OK;
 }
 
@@ -668,6 +691,7 @@ int om_get_points(om_handle* h, double* out_host) {
 int om_set_points(om_handle* h, const double* in_host) {
   OM_ENTER(h);
   if (h->N == 0) return OM_OK;
+  h->delaunay_clean = false;
   double* flat = nullptr;
   CUDA_TRY(om_malloc(h, &flat, sizeof(double) * h->N * h->D));
   {
@@ -723,6 +747,7 @@ int om_get_boundary_flags(om_handle* h, uint8_t* out_host) {
 int om_device_ptrs(om_handle* h, double** points, int32_t** cells4, int32_t** perm,
                    int32_t* point_stride) {
   OM_ENTER(h);
+  h->delaunay_clean = false;  // the caller may write through the pointer
   if (points) *points = h->x;
   if (cells4) *cells4 = (int32_t*)h->cells;
   if (perm) *perm = h->perm;
@@ -744,6 +769,7 @@ int om_pack_points(om_handle* h, const int32_t* idx_dev, int64_t n, double* buf_
 int om_unpack_points(om_handle* h, const int32_t* idx_dev, int64_t n, const double* buf_dev) {
   OM_ENTER(h);
   if (n == 0) return OM_OK;
+  h->delaunay_clean = false;
   if (h->D == 2)
     OM_LAUNCH(h, k_unpack<2>, om_grid(n, 256), 256, h->x, h->inv_perm, idx_dev, n, buf_dev);
   else
@@ -755,6 +781,16 @@ int om_unpack_points(om_handle* h, const int32_t* idx_dev, int64_t n, const doub
 int om_pin_vertices(om_handle* h, const int32_t* idx_host, int64_t n) {
   OM_ENTER(h);
   if (n == 0) return OM_OK;
+  if (n < 0 || !idx_host) {
+    om_set_error("om_pin_vertices: bad arguments");
+    return OM_ERR_ARG;
+  }
+  for (int64_t i = 0; i < n; i++)
+    if (idx_host[i] < 0 || idx_host[i] >= h->N) {
+      om_set_error("om_pin_vertices: vertex %d outside [0, %lld)", (int)idx_host[i],
+                   (long long)h->N);
+      return OM_ERR_INDEX;
+    }
   int* d = nullptr;
   CUDA_TRY(om_malloc(h, &d, sizeof(int) * n));
   cudaMemcpyAsync(d, idx_host, sizeof(int) * n, cudaMemcpyHostToDevice, h->stream);
@@ -906,6 +942,7 @@ int om_set_deferred_commit(om_handle* h, int on) {
 
 int om_commit_points(om_handle* h) {
   OM_ENTER(h);
+  h->delaunay_clean = false;
   return om_commit_points_impl(h);
 }
 
@@ -932,6 +969,7 @@ int om_set_owned_range(om_handle* h, int64_t lo, int64_t hi) {
 
 int om_points_device(om_handle* h, double** points, int64_t* n_alloc, int32_t* stride) {
   OM_ENTER(h);
+  h->delaunay_clean = false;  // the caller may write through the pointer
   if (points) *points = h->x;
   if (n_alloc) *n_alloc = h->N + OM_POINT_PAD;
   if (stride) *stride = h->PD;

@@ -117,7 +117,7 @@ struct Chain {
   double H[NH];
   // limiter
   double rn, rd;          // EXACT: 2A and perimeter of the cell with the smallest inradius
-  int minv4_hi, maxl_hi;  // lazy bound
+  int minq_hi;            // lazy bound: min over the cells of hi(V4) - hi(max L)
   // current spoke (the second spoke of the last cell) and what that cell leaves for it
   Vec<D> dq;
   double Lq, lenq;
@@ -137,8 +137,7 @@ struct Chain {
     for (int k = 0; k < NH; k++) H[k] = 0.0;
     rn = INFINITY;
     rd = 1.0;
-    minv4_hi = 0x7ff00000;
-    maxl_hi = 0;
+    minq_hi = 0x7fffffff;
     t1p = s1p = t2_0 = s2_0 = 0.0;
     lenq = 0.0;
     flags = 0u;
@@ -153,10 +152,7 @@ struct Chain {
   }
 
   // first spoke of the chain
-  __device__ __forceinline__ void start(const Vec<D>& P) {
-    spoke(P, dq, Lq, lenq);
-    if (!EXACT) maxl_hi = __double2hiint(Lq);
-  }
+  __device__ __forceinline__ void start(const Vec<D>& P) { spoke(P, dq, Lq, lenq); }
 
   // adds what the two cells next to spoke `d` leave for it
   __device__ __forceinline__ void finish_spoke(const Vec<D>& d, double L, double t2, double s2,
@@ -199,8 +195,8 @@ struct Chain {
   // spokes: (t2, s2) to the current one, (t1, s1) to dn.
   __device__ __forceinline__ void cell(const Vec<D>& dn, double Ln, double lenn, bool bary,
                                        double& t1, double& t2, double& s1, double& s2,
-                                       bool& masked) {
-    masked = false;
+                                       unsigned& mflags) {
+    mflags = 0u;
     const double c = vdot<D>(dq, dn);
     const double cc = c * c;
     const double V4 = fma(Lq, Ln, -cc);
@@ -218,12 +214,12 @@ struct Chain {
         rd = per;
       }
     } else {
-      // r_in^2 = V4 / (ee0 + ee1 + ee2 + 2 sum of products of lengths) >= V4 / (3 sum ee) and
-      // ee0 <= 2 (ee1 + ee2), so r_in^2 >= V4 / (18 max L): keep the smallest V4 and the
-      // largest spoke L of the star as high words (rounded the safe way in
-      // proves_unlimited()) -- two integer instructions per cell, nothing on the fp64 pipe
-      minv4_hi = min(minv4_hi, __double2hiint(V4));
-      maxl_hi = max(maxl_hi, __double2hiint(Ln));
+      // r_in^2 = V4 / (l0 + l1 + l2)^2 >= V4 / (3 sum ee) and ee0 <= 2 (ee1 + ee2), so
+      // r_in^2 >= V4 / (18 max(L_q, L_{q+1})) for this cell.  The smallest such quotient over
+      // the star is tracked as a DIFFERENCE OF HIGH WORDS (a fixed-point log2 with a known
+      // error, undone in proves_unlimited()): three integer instructions per cell, nothing on
+      // the fp64 pipe.
+      minq_hi = min(minq_hi, __double2hiint(V4) - max(__double2hiint(Lq), __double2hiint(Ln)));
     }
     if (NEED_T) {
       const double T1 = (c - Lq) * rs, T2 = (c - Ln) * rs;  // 2 t: angles at n_q, n_{q+1}
@@ -236,7 +232,13 @@ struct Chain {
         const long long one = 0x3ff0000000000000ll;
         const bool m0 = (__double2hiint(c) < 0) & (__double_as_longlong(cc) > __double_as_longlong(V4));
         const bool m1 = __double_as_longlong(T1) > one, m2 = __double_as_longlong(T2) > one;
-        masked = m0 | m1 | m2;
+        const bool masked = m0 | m1 | m2;
+        // Fused Delaunay check: an edge can only violate the criterion if one of its two
+        // opposite angles is obtuse.  A masked cell hides its t from the sums below, so it
+        // names the spoke opposite its > 135 deg angle itself (the angle at n_{q+1} faces the
+        // current spoke, the one at n_q faces dn); its two small angles (< 45 deg together)
+        // cannot make their edges violate it unless the cell across does the same.
+        mflags = (m2 ? 1u : 0u) | (m1 ? 2u : 0u);
         t1 = masked ? 0.0 : T1;
         t2 = masked ? 0.0 : T2;
         const double w1 = Ln * t1, w2 = Lq * t2;
@@ -281,10 +283,10 @@ struct Chain {
   __device__ __forceinline__ void first(const Vec<D>& P, bool bary, bool first_spoke_interior) {
     Vec<D> dn;
     double Ln, lenn = 0.0, t1, t2, s1, s2;
-    bool masked;
+    unsigned mflags;
     spoke(P, dn, Ln, lenn);
-    cell(dn, Ln, lenn, bary, t1, t2, s1, s2, masked);
-    if (CHECK && masked) flags |= 3u;  // both spokes of a masked cell are suspicious
+    cell(dn, Ln, lenn, bary, t1, t2, s1, s2, mflags);
+    if (CHECK) flags |= mflags;
     t2_0 = t2;
     s2_0 = s2;
     if (!first_spoke_interior) finish_spoke(dq, Lq, t2, s2, 0.0, 0.0, 0, false);
@@ -300,10 +302,10 @@ struct Chain {
   __device__ __forceinline__ void next(const Vec<D>& P, bool bary) {
     Vec<D> dn;
     double Ln, lenn = 0.0, t1, t2, s1, s2;
-    bool masked;
+    unsigned mflags;
     spoke(P, dn, Ln, lenn);
-    cell(dn, Ln, lenn, bary, t1, t2, s1, s2, masked);
-    if (CHECK && masked) flags |= 3u << q;
+    cell(dn, Ln, lenn, bary, t1, t2, s1, s2, mflags);
+    if (CHECK) flags |= mflags << q;
     finish_spoke(dq, Lq, t2, s2, t1p, s1p, q, true);
     t1p = t1;
     s1p = s1;
@@ -317,10 +319,10 @@ struct Chain {
   __device__ __forceinline__ void close(const Vec<D>& P, bool bary) {
     Vec<D> dn;
     double Ln, lenn = 0.0, t1, t2, s1, s2;
-    bool masked;
+    unsigned mflags;
     spoke(P, dn, Ln, lenn);
-    cell(dn, Ln, lenn, bary, t1, t2, s1, s2, masked);
-    if (CHECK && masked) flags |= (1u << q) | 1u;
+    cell(dn, Ln, lenn, bary, t1, t2, s1, s2, mflags);
+    if (CHECK) flags |= ((mflags & 1u) << q) | (mflags >> 1);
     finish_spoke(dq, Lq, t2, s2, t1p, s1p, q, true);
     finish_spoke(dn, Ln, t2_0, s2_0, t1, s1, 0, true);
     q++;
@@ -349,11 +351,14 @@ struct Chain {
 
   // lazy limiter: true if |d|^2 = diff2 provably stays below (r_in / 2)^2 for every cell
   __device__ __forceinline__ bool proves_unlimited(double diff2) const {
-    // |d|^2 <= r_in^2 / 4 follows from 72 |d|^2 max L <= min V4; high words rounded the safe
-    // way: V4 down, L up
-    const double v4 = __hiloint2double(minv4_hi, 0);
-    const double ml = __hiloint2double(maxl_hi + 1, 0);
-    return 72.0 * diff2 * ml <= v4;
+    // With h(x) the high word of x > 0, (h(a) - h(b) - 1) / 2^20 is a lower bound of
+    // log2(a / b) up to the error of the piecewise-linear log2 the exponent/mantissa layout
+    // amounts to: (1 + f) / 2^f lies in [1, 1.0615], so a / b >= D / 1.0615^2 with D the
+    // double whose high word is h(a) - h(b) - 1 + 0x3ff00000.  Hence r_in^2 >= D / (18 * 1.127)
+    // for every cell and |d|^2 <= r_in^2 / 4 follows from 81.2 |d|^2 <= D.
+    if (minq_hi < -0x3fe00000 || minq_hi > 0x3fe00000) return false;  // out of the double range
+    const double Dq = __hiloint2double(minq_hi - 1 + 0x3ff00000, 0);
+    return 81.2 * diff2 <= Dq;
   }
 
   // exact limiter: scales d if it is longer than half the smallest incident inradius

@@ -74,7 +74,8 @@ struct DevScalars {
   long long n_free;  // vertices the limiter statistics refer to
   long long pl_launches;  // kernels run by the pipelined loop (they are launched by the graph)
   int limiter_on;
-  int pad_pl;
+  int n_deferred;  // vertices the ring kernel left to k_post in the last update
+  long long total_deferred;
 };
 
 struct om_handle {
@@ -92,6 +93,7 @@ struct om_handle {
   int* v2c = nullptr;        // N: one incident cell (OM_NONE_CELL for orphans)
   uint8_t* bflag = nullptr;  // N: 1 = pinned (boundary / ghost)
   int* ring = nullptr;       // N x OM_RING_W: one-ring vertex ids of free interior vertices
+  int* ringc = nullptr;      // N x OM_RING_W: the cells between them (cell q = (v, n_q, n_q+1))
   int* dirty = nullptr;      // N: vertices touched by flips (ring rows to rebuild)
   int* dirty_epoch = nullptr;// N: dedupe stamps for `dirty`
   double* diff2 = nullptr;   // N: |diff|^2 of the last point update, sign bit = limited
@@ -156,6 +158,10 @@ struct om_handle {
   bool ev_pending = false;  // ev[0..1] recorded, elapsed time not read yet
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   void* pl = nullptr;  // cached graphs of the pipelined loop (loop.cu)
+  // the last whole-mesh flip pass ended without flagged edges and no coordinate has changed
+  // since: the flip pass that opens the loop has nothing to do
+  bool delaunay_clean = false;
+  int64_t run_flips = 0, run_rounds = 0, run_limited = 0, run_deferred = 0;  // last om_run
   double t_step_ms = 0.0, t_flip_ms = 0.0;
   int64_t n_step = 0, n_flip = 0;
 };
@@ -222,6 +228,7 @@ int om_launch_fixup(om_handle* h, double* out);
 // pipelined loop (loop.cu): one iteration = update (with the fused Delaunay check) from xin
 // into xout, flip pass on xin, recomputation of the vertices whose star changed
 int om_pl_launch_update(om_handle* h, const double* xin, double* xout, bool timed);
+int om_pl_launch_update_part(om_handle* h, const double* xin, double* xout, int what);
 int om_pl_launch_tail(om_handle* h, const double* xin, double* xout);
 int om_pl_launch_flags_check(om_handle* h, const double* xin);
 int om_pl_launch_flips(om_handle* h);
@@ -230,6 +237,7 @@ int om_pl_launch_round_end(om_handle* h, unsigned long long handle, int use_hand
 int om_run_pipelined(om_handle* h, double tol, int64_t max_num_steps, int64_t* steps_done,
                      om_step_stats* last);
 void om_pl_destroy(om_handle* h);
+int om_pl_prepare(om_handle* h);
 // pcg.cu
 int om_pcg_impl(om_handle* h, double rtol, int max_iter, int32_t* iters, double* relres,
                 double* out /* N*PD, may alias h->xnew */);

@@ -465,12 +465,14 @@ __global__ void k_reset_flip_scalars(DevScalars* ds, int new_pass) {
 // spoke of every vertex, twice the Delaunay indicator of that edge on the way (chain.cuh) and
 // leaves "spoke q may violate the criterion" bits in the vertex's flag word (bit 9: check all
 // my spokes -- vertices the ring kernel does not evaluate itself).  This kernel scans the flag
-// words, compacts the flagged vertices chunk by chunk, walks their stars in ring-row order to
-// name the half-edge of each flagged spoke and takes the decision on the exact s, like
-// k_suspect.  Flagged cells go to the candidate list through a list in shared memory: one
-// atomic on the global counter per chunk.
+// words warp by warp (runs of 256 words, compacted with a shuffle scan: no block barrier),
+// names the half-edge of each flagged spoke from the vertex's ring rows (neighbour ids + the
+// cells between them: no star walk) and takes the decision on the exact s, like k_suspect.
+// Flagged cells go to the candidate list through a small per-warp list in shared memory: one
+// atomic on the global counter per warp and run.
 constexpr unsigned VF_SPOKES = 0xffu, VF_DEFER = 0x100u, VF_CHECKALL = 0x200u;
-constexpr int FLG_BLOCK = 256, FLG_PER = 8, FLG_OUT = 4096;
+constexpr int FLG_BLOCK = 256, FLG_PER = 8, FLG_RUN = 32 * FLG_PER, FLG_OUT = 192, FLG_HE = 256;
+constexpr int RING_IDMASK = (1 << 29) - 1;
 
 template <int D>
 __device__ __forceinline__ void check_half_edge(const double* __restrict__ x,
@@ -507,29 +509,51 @@ __device__ __forceinline__ void check_half_edge(const double* __restrict__ x,
       if (pos < FLG_OUT)
         s_out[pos] = ids[i];
       else
-        cand[atomicAdd(&ds->n_cand, 1)] = ids[i];  // overflow of the block list (rare)
+        cand[atomicAdd(&ds->n_cand, 1)] = ids[i];  // overflow of the warp's list (rare)
     }
+}
+
+// appends a half-edge to the warp's work list (checked at once if the list is full)
+template <int D>
+__device__ __forceinline__ void push_half_edge(int he, int* s_he, int* s_nhe,
+                                               const double* __restrict__ x,
+                                               const int4* __restrict__ cells,
+                                               const int* __restrict__ adj, double tol,
+                                               double* __restrict__ sarr,
+                                               int* __restrict__ cand_epoch, int epoch, int* s_out,
+                                               int* s_nout, int* __restrict__ cand,
+                                               DevScalars* ds) {
+  const int pos = atomicAdd(s_nhe, 1);
+  if (pos < FLG_HE) {
+    s_he[pos] = he;
+  } else {
+    const int4 cl = __ldg(cells + (he >> 2));
+    check_half_edge<D>(x, cells, adj, he >> 2, he & 3, cl, tol, sarr, cand_epoch, epoch, s_out,
+                       s_nout, cand, ds);
+  }
 }
 
 template <int D>
 __global__ void __launch_bounds__(FLG_BLOCK)
     k_suspect_flags(const double* __restrict__ x, const int4* __restrict__ cells,
                     const int* __restrict__ adj, const int* __restrict__ v2c,
+                    const int* __restrict__ ring, const int* __restrict__ ringc,
                     unsigned short* __restrict__ vflags, int N, double tol,
                     double* __restrict__ sarr, int* __restrict__ cand,
                     int* __restrict__ cand_epoch, DevScalars* ds) {
   if (ds->halt) return;
-  constexpr int CHUNK = FLG_BLOCK * FLG_PER;
-  __shared__ int s_v[CHUNK];
-  __shared__ unsigned short s_f[CHUNK];
-  __shared__ int s_out[FLG_OUT];
-  __shared__ int s_warp[FLG_BLOCK / 32];
-  __shared__ int s_total, s_nout, s_base;
+  constexpr int NW = FLG_BLOCK / 32;
+  __shared__ int s_v[NW][FLG_RUN];
+  __shared__ unsigned short s_f[NW][FLG_RUN];
+  __shared__ int s_he[NW][FLG_HE];
+  __shared__ int s_out[NW][FLG_OUT];
+  __shared__ int s_nout[NW], s_nhe[NW];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gwarp = blockIdx.x * NW + warp, nwarps = gridDim.x * NW;
   const int epoch = ds->epoch;
-  const int nchunks = (N + CHUNK - 1) / CHUNK;
-  for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
-    const int vb = chunk * CHUNK + threadIdx.x * FLG_PER;
+  const int nruns = (N + FLG_RUN - 1) / FLG_RUN;
+  for (int run = gwarp; run < nruns; run += nwarps) {
+    const int vb = run * FLG_RUN + lane * FLG_PER;
     unsigned short w[FLG_PER];
     int cnt = 0;
     if (vb < N) {
@@ -548,39 +572,63 @@ __global__ void __launch_bounds__(FLG_BLOCK)
 #pragma unroll
       for (int i = 0; i < FLG_PER; i++) w[i] = 0;
     }
+    if (!__any_sync(0xffffffffu, cnt != 0)) continue;
     int incl = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int up = __shfl_up_sync(0xffffffffu, incl, o);
       if (lane >= o) incl += up;
     }
-    if (lane == 31) s_warp[warp] = incl;
-    if (threadIdx.x == 0) s_nout = 0;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      int tot = 0;
-      for (int q = 0; q < FLG_BLOCK / 32; q++) {
-        const int t = s_warp[q];
-        s_warp[q] = tot;
-        tot += t;
-      }
-      s_total = tot;
-    }
-    __syncthreads();
-    int pos = s_warp[warp] + incl - cnt;
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    int pos = incl - cnt;
 #pragma unroll
     for (int i = 0; i < FLG_PER; i++)
       if (w[i]) {
-        s_v[pos] = vb + i;
-        s_f[pos] = w[i];
+        s_v[warp][pos] = vb + i;
+        s_f[warp][pos] = w[i];
         pos++;
       }
-    __syncthreads();
-    const int total = s_total;
-    for (int it = threadIdx.x; it < total; it += FLG_BLOCK) {
-      const int v = s_v[it];
-      const unsigned f = s_f[it];
-      const bool all = (f & VF_CHECKALL) != 0;
+    if (lane == 0) {
+      s_nout[warp] = 0;
+      s_nhe[warp] = 0;
+    }
+    __syncwarp();
+    // phase 1, one lane per flagged vertex: name the half-edges of its flagged spokes
+    for (int it = lane; it < total; it += 32) {
+      const int v = s_v[warp][it];
+      const unsigned f = s_f[warp][it];
+      if (!(f & VF_CHECKALL)) {
+        // the vertex has ring rows: spoke q is the edge (v, n_q) of cell q = (v, n_q, n_{q+1})
+        const int4* rp = reinterpret_cast<const int4*>(ring + (size_t)OM_RING_W * v);
+        const int4* cp = reinterpret_cast<const int4*>(ringc + (size_t)OM_RING_W * v);
+        const int4 a0 = __ldg(rp), a1 = __ldg(rp + 1), b0 = __ldg(cp), b1 = __ldg(cp + 1);
+        const int e[OM_RING_W] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const int ec[OM_RING_W] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        const int k = 1 + ((e[0] >> 30) & 1) + ((e[1] >> 29) & 2) + ((e[2] >> 28) & 4);
+#pragma unroll
+        for (int q = 0; q < OM_RING_W; q++)
+          if (q < k && ((f >> q) & 1u)) {
+            int nn = e[0];  // n_{q+1}, cyclic
+#pragma unroll
+            for (int r2 = 1; r2 < OM_RING_W; r2++)
+              if (r2 == q + 1 && r2 < k) nn = e[r2];
+            nn &= RING_IDMASK;
+            const int c = ec[q];
+            if (c < 0) {
+              atomicOr(&ds->err, OM_DEV_WALK);
+              continue;
+            }
+            const int4 cl = __ldg(cells + c);
+            const int ks = slot_of(cl, nn);
+            if (ks < 0 || slot_of(cl, v) < 0)
+              atomicOr(&ds->err, OM_DEV_WALK);  // the rows do not match the cells
+            else
+              push_half_edge<D>(4 * c + ks, s_he[warp], &s_nhe[warp], x, cells, adj, tol, sarr,
+                                cand_epoch, epoch, s_out[warp], &s_nout[warp], cand, ds);
+          }
+        continue;
+      }
+      // no row (pinned vertex, or more than OM_RING_W cells): every spoke, by a star walk
       const int c0 = v2c[v];
       if (c0 == OM_NONE_CELL) continue;
       int4 cl = __ldg(cells + c0);
@@ -589,24 +637,21 @@ __global__ void __launch_bounds__(FLG_BLOCK)
         atomicOr(&ds->err, OM_DEV_WALK);
         continue;
       }
-      // spoke 0 is the edge of the start cell that the walk does NOT leave through
-      if (all || (f & 1u))
-        check_half_edge<D>(x, cells, adj, c0, (j + 2) % 3, cl, tol, sarr, cand_epoch, epoch, s_out,
-                           &s_nout, cand, ds);
-      int cur = c0, kexit = (j + 1) % 3, q = 1, hops = 0;
+      // the edge of the start cell that the walk does NOT leave through
+      push_half_edge<D>(4 * c0 + (j + 2) % 3, s_he[warp], &s_nhe[warp], x, cells, adj, tol, sarr,
+                        cand_epoch, epoch, s_out[warp], &s_nout[warp], cand, ds);
+      int cur = c0, kexit = (j + 1) % 3, hops = 0;
       bool open = false;
       while (true) {
-        // the walk leaves cell q-1 through spoke q
         const int t = __ldg(adj + 4 * (size_t)cur + kexit);
         if (t < 0) {
           open = true;
           break;
         }
         const int cn = t >> 2, kn = t & 3;
-        if (cn == c0) break;  // closed: this is spoke 0 again
-        if (all || (q < 8 && ((f >> q) & 1u)))
-          check_half_edge<D>(x, cells, adj, cur, kexit, cl, tol, sarr, cand_epoch, epoch, s_out,
-                             &s_nout, cand, ds);
+        if (cn == c0) break;  // closed: back at the first edge
+        push_half_edge<D>(4 * cur + kexit, s_he[warp], &s_nhe[warp], x, cells, adj, tol, sarr,
+                          cand_epoch, epoch, s_out[warp], &s_nout[warp], cand, ds);
         cl = __ldg(cells + cn);
         const int jn = slot_of(cl, v);
         if (jn < 0 || jn == kn || ++hops > 4096) {
@@ -615,13 +660,11 @@ __global__ void __launch_bounds__(FLG_BLOCK)
         }
         cur = cn;
         kexit = 3 - jn - kn;
-        q++;
       }
-      if (open && all) {
+      if (open) {
         // open fan (pinned boundary vertex): the spokes on the other side of the start cell
         cur = c0;
-        cl = __ldg(cells + c0);
-        kexit = (j + 2) % 3;  // spoke 0 was checked above
+        kexit = (j + 2) % 3;  // pushed above
         hops = 0;
         while (true) {
           const int t = __ldg(adj + 4 * (size_t)cur + kexit);
@@ -635,17 +678,27 @@ __global__ void __launch_bounds__(FLG_BLOCK)
           }
           cur = cn;
           kexit = 3 - jn - kn;
-          check_half_edge<D>(x, cells, adj, cur, kexit, cl, tol, sarr, cand_epoch, epoch, s_out,
-                             &s_nout, cand, ds);
+          push_half_edge<D>(4 * cur + kexit, s_he[warp], &s_nhe[warp], x, cells, adj, tol, sarr,
+                            cand_epoch, epoch, s_out[warp], &s_nout[warp], cand, ds);
         }
       }
     }
-    __syncthreads();
-    const int nout = min(s_nout, FLG_OUT);
-    if (threadIdx.x == 0) s_base = nout ? atomicAdd(&ds->n_cand, nout) : 0;
-    __syncthreads();
-    for (int i = threadIdx.x; i < nout; i += FLG_BLOCK) cand[s_base + i] = s_out[i];
-    __syncthreads();  // the shared lists are reused by the next chunk
+    __syncwarp();
+    // phase 2, one lane per half-edge: the decision on the exact s
+    const int nhe = min(s_nhe[warp], FLG_HE);
+    for (int i = lane; i < nhe; i += 32) {
+      const int he = s_he[warp][i];
+      const int4 cl = __ldg(cells + (he >> 2));
+      check_half_edge<D>(x, cells, adj, he >> 2, he & 3, cl, tol, sarr, cand_epoch, epoch,
+                         s_out[warp], &s_nout[warp], cand, ds);
+    }
+    __syncwarp();
+    const int nout = min(s_nout[warp], FLG_OUT);
+    int base = 0;
+    if (lane == 0 && nout) base = atomicAdd(&ds->n_cand, nout);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    for (int i = lane; i < nout; i += 32) cand[base + i] = s_out[warp][i];
+    __syncwarp();  // the shared lists are reused by the next run
   }
 }
 
@@ -978,6 +1031,7 @@ int om_flip_impl(om_handle* h, double tol, int max_rounds, int64_t* n_flips, int
   // ring rows of the vertices whose stars changed (hs->n_dirty is current: the last
   // readback of the pass came after the last flip)
   if (rc == OM_OK && n_flips && *n_flips > 0) rc = om_rebuild_rings(h, false);
+  h->delaunay_clean = rc == OM_OK && (!cap_hit || *cap_hit == 0) && tol == 0.0 && h->own_hi < 0;
   if (h->timing && rc == OM_OK) {
     cudaEventRecord(h->ev[3], h->stream);
     cudaEventSynchronize(h->ev[3]);
@@ -994,14 +1048,16 @@ int om_flip_impl(om_handle* h, double tol, int max_rounds, int64_t* n_flips, int
 // stamps on the device and returns at once when the loop has halted
 int om_pl_launch_flags_check(om_handle* h, const double* xin) {
   OM_LAUNCH(h, k_pl_pass_begin, 1, 1, h->ds);
-  const int chunks = om_grid(h->N, FLG_BLOCK * FLG_PER);
-  const int G = std::min(chunks, 148 * 4);
+  const int blocks = om_grid(h->N, FLG_BLOCK * FLG_PER);
+  const int G = std::min(blocks, 148 * 8);
   if (h->D == 2)
     OM_LAUNCH(h, k_suspect_flags<2>, G, FLG_BLOCK, xin, h->cells, (const int*)h->adj, h->v2c,
-              h->vflags, (int)h->N, 0.0, h->sarr, h->cand, h->cand_epoch, h->ds);
+              (const int*)h->ring, (const int*)h->ringc, h->vflags, (int)h->N, 0.0, h->sarr,
+              h->cand, h->cand_epoch, h->ds);
   else
     OM_LAUNCH(h, k_suspect_flags<3>, G, FLG_BLOCK, xin, h->cells, (const int*)h->adj, h->v2c,
-              h->vflags, (int)h->N, 0.0, h->sarr, h->cand, h->cand_epoch, h->ds);
+              (const int*)h->ring, (const int*)h->ringc, h->vflags, (int)h->N, 0.0, h->sarr,
+              h->cand, h->cand_epoch, h->ds);
   CUDA_TRY(cudaGetLastError());
   return OM_OK;
 }

@@ -45,6 +45,7 @@ __global__ void k_pl_init(DevScalars* ds, long long max_steps, double tol2, int 
   ds->cap_hit = 0;
   ds->pl_go = 0;
   ds->total_flips = ds->total_rounds = ds->total_limited = 0;
+  ds->total_deferred = 0;
   ds->pl_launches = 0;
 }
 
@@ -55,9 +56,18 @@ __global__ void k_pl_iter_end(DevScalars* ds, cudaGraphConditionalHandle handle,
     ds->total_flips += ds->n_flips;
     ds->total_rounds += ds->n_rounds;
     ds->total_limited += (long long)ds->n_limited;
-    // the lazy limiter pays off once few vertices are limited (the update just done tells)
-    ds->mode_exact =
-        (ds->limiter_on && 4ll * (long long)ds->n_limited > ds->n_free) ? 1 : 0;
+    // The lazy limiter pays off while it leaves few vertices to k_post (a deferred vertex
+    // costs about three times a vertex of the ring kernel, the exact variant about half a
+    // vertex more for everyone).  An exact update defers only the vertices without a row, so
+    // there the number of limited vertices decides (the bound fails for about twice as many).
+    // Either variant gives a vertex the same bits.
+    ds->total_deferred += ds->n_deferred;
+    if (!ds->limiter_on)
+      ds->mode_exact = 0;
+    else if (ds->mode_exact)
+      ds->mode_exact = 5ll * (long long)ds->n_limited > ds->n_free ? 1 : 0;
+    else
+      ds->mode_exact = 7ll * (long long)ds->n_deferred > ds->n_free ? 1 : 0;
     double md;
     memcpy(&md, &ds->max_diff2_bits, 8);
     if (ds->err)
@@ -66,6 +76,14 @@ __global__ void k_pl_iter_end(DevScalars* ds, cudaGraphConditionalHandle handle,
       ds->halt = 1;
   }
   if (use_handle) cudaGraphSetConditional(handle, ds->halt ? 0u : 1u);
+}
+
+// selects the limiter variant of the ring kernel for this iteration (two IF nodes)
+__global__ void k_pl_mode(const DevScalars* ds, cudaGraphConditionalHandle lazy,
+                          cudaGraphConditionalHandle exact) {
+  const bool run = !ds->halt;
+  cudaGraphSetConditional(lazy, run && !ds->mode_exact ? 1u : 0u);
+  cudaGraphSetConditional(exact, run && ds->mode_exact ? 1u : 0u);
 }
 
 struct PlGraph {
@@ -91,10 +109,10 @@ struct PlCache {
     }                                                                                 \
   } while (0)
 
-// the kernels of one iteration up to (and including) the first flip round
-int enqueue_head(om_handle* h, const double* xin, double* xout, bool timed,
-                 unsigned long long inner, int use_handle) {
-  OM_TRY(om_pl_launch_update(h, xin, xout, timed));
+// the kernels of one iteration after the ring kernel, up to (and including) the first flip round
+int enqueue_head_rest(om_handle* h, const double* xin, double* xout, unsigned long long inner,
+                      int use_handle) {
+  OM_TRY(om_pl_launch_update_part(h, xin, xout, 3));
   OM_TRY(om_pl_launch_flags_check(h, xin));
   OM_TRY(om_pl_launch_flips(h));
   OM_TRY(om_pl_launch_round_end(h, inner, use_handle));
@@ -162,6 +180,20 @@ int add_while(cudaGraph_t parent, const cudaGraphNode_t* deps, size_t ndeps,
   return OM_OK;
 }
 
+// an IF node after `dep` whose body is what `body` enqueues
+template <typename F>
+int add_if(om_handle* h, cudaStream_t cs, cudaGraph_t parent, cudaGraphConditionalHandle handle,
+           cudaGraphNode_t dep, cudaGraphNode_t* node, F&& body) {
+  cudaGraphNodeParams np = {cudaGraphNodeTypeConditional};
+  np.type = cudaGraphNodeTypeConditional;
+  np.conditional.handle = handle;
+  np.conditional.type = cudaGraphCondTypeIf;
+  np.conditional.size = 1;
+  CU_TRY(cudaGraphAddNode(node, parent, &dep, 1, &np));
+  cudaGraphNode_t unused;
+  return capture_into(h, cs, np.conditional.phGraph_out[0], nullptr, 0, &unused, body);
+}
+
 int build_graph(om_handle* h, PlCache* cache, PlGraph* g) {
   if (!cache->capture_stream)
     CU_TRY(cudaStreamCreateWithFlags(&cache->capture_stream, cudaStreamNonBlocking));
@@ -177,11 +209,26 @@ int build_graph(om_handle* h, PlCache* cache, PlGraph* g) {
   for (int half = 0; half < 2; half++) {
     const double* xin = half == 0 ? A : B;
     double* xout = half == 0 ? B : A;
-    // the handle of the inner loop has to exist before the kernels that set it are captured
-    cudaGraphConditionalHandle inner;
+    // the handles have to exist before the kernels that set them are captured
+    cudaGraphConditionalHandle inner, lazy, exact;
     CU_TRY(cudaGraphConditionalHandleCreate(&inner, body, 0u, cudaGraphCondAssignDefault));
-    OM_TRY(capture_into(h, cs, body, last ? &last : nullptr, last ? 1 : 0, &last, [&] {
-      return enqueue_head(h, xin, xout, false, (unsigned long long)inner, 1);
+    CU_TRY(cudaGraphConditionalHandleCreate(&lazy, body, 0u, cudaGraphCondAssignDefault));
+    CU_TRY(cudaGraphConditionalHandleCreate(&exact, body, 0u, cudaGraphCondAssignDefault));
+    OM_TRY(capture_into(h, cs, body, last ? &last : nullptr, last ? 1 : 0, &last, [&]() -> int {
+      OM_TRY(om_pl_launch_update_part(h, xin, xout, 0));
+      OM_LAUNCH(h, k_pl_mode, 1, 1, (const DevScalars*)h->ds, lazy, exact);
+      CUDA_TRY(cudaGetLastError());
+      return (int)OM_OK;
+    }));
+    // only the limiter variant the device selected runs (an empty 78k-block launch is 40 us)
+    cudaGraphNode_t if_lazy, if_exact;
+    OM_TRY(add_if(h, cs, body, lazy, last, &if_lazy,
+                  [&] { return om_pl_launch_update_part(h, xin, xout, 1); }));
+    OM_TRY(add_if(h, cs, body, exact, if_lazy, &if_exact,
+                  [&] { return om_pl_launch_update_part(h, xin, xout, 2); }));
+    last = if_exact;
+    OM_TRY(capture_into(h, cs, body, &last, 1, &last, [&] {
+      return enqueue_head_rest(h, xin, xout, (unsigned long long)inner, 1);
     }));
     cudaGraphNodeParams np = {cudaGraphNodeTypeConditional};
     np.type = cudaGraphNodeTypeConditional;
@@ -217,12 +264,16 @@ void free_graph(PlGraph& g) {
 }
 
 // the same loop driven from the stream: one scalar readback per flip round and per step
-int run_stream(om_handle* h, double* A, double* B) {
+int run_stream(om_handle* h, double* A, double* B, bool mode_exact) {
   const bool timed = h->timing;
   for (int64_t it = 0;; it++) {
     const double* xin = (it & 1) ? B : A;
     double* xout = (it & 1) ? A : B;
-    OM_TRY(enqueue_head(h, xin, xout, timed, 0ull, 0));
+    OM_TRY(om_pl_launch_update_part(h, xin, xout, 0));
+    if (timed) cudaEventRecord(h->ev[0], h->stream);
+    OM_TRY(om_pl_launch_update_part(h, xin, xout, mode_exact ? 2 : 1));
+    if (timed) cudaEventRecord(h->ev[1], h->stream);
+    OM_TRY(enqueue_head_rest(h, xin, xout, 0ull, 0));
     while (true) {
       OM_TRY(om_fetch_scalars(h));
       if (!h->hs->pl_go) break;
@@ -238,6 +289,7 @@ int run_stream(om_handle* h, double* A, double* B) {
     OM_TRY(enqueue_tail(h, xin, xout, 0ull, 0));
     OM_TRY(om_fetch_scalars(h));
     if (h->hs->halt) break;
+    mode_exact = h->hs->mode_exact != 0;
   }
   return OM_OK;
 }
@@ -253,6 +305,42 @@ void om_pl_destroy(om_handle* h) {
   h->pl = nullptr;
 }
 
+namespace {
+int get_graph(om_handle* h, PlGraph** out) {
+  PlCache* cache = (PlCache*)h->pl;
+  if (!cache) h->pl = cache = new PlCache();
+  for (auto& c : cache->graphs)
+    if (c.buf_a == h->x && c.method == h->method && c.limiter == h->limiter &&
+        c.odt_bary == h->odt_bary && c.use_rings == (h->use_rings ? 1 : 0) &&
+        c.omega == h->omega) {
+      *out = &c;
+      return OM_OK;
+    }
+  if (cache->graphs.size() >= 4) {
+    for (auto& c : cache->graphs) free_graph(c);
+    cache->graphs.clear();
+  }
+  cache->graphs.emplace_back();
+  PlGraph* g = &cache->graphs.back();
+  const int rc = build_graph(h, cache, g);
+  if (rc != OM_OK) {
+    free_graph(*g);
+    cache->graphs.pop_back();
+    return rc;
+  }
+  *out = g;
+  return OM_OK;
+}
+}  // namespace
+
+// builds (and caches) the graph om_run would launch now, without running it
+int om_pl_prepare(om_handle* h) {
+  static const bool no_graph = getenv("OM_NO_GRAPH") != nullptr;
+  if (no_graph || h->N == 0 || h->C == 0) return OM_OK;
+  PlGraph* g = nullptr;
+  return get_graph(h, &g);
+}
+
 // The whole loop for the fixed-point methods on one GPU without a surface.
 int om_run_pipelined(om_handle* h, double tol, int64_t max_num_steps, int64_t* steps_done,
                      om_step_stats* last) {
@@ -260,7 +348,8 @@ int om_run_pipelined(om_handle* h, double tol, int64_t max_num_steps, int64_t* s
   memset(&st, 0, sizeof(st));
   int64_t nf = 0;
   int32_t nr = 0, cap = 0;
-  OM_TRY(om_flip_impl(h, 0.0, 100, &nf, &nr, &cap));
+  if (!h->delaunay_clean) OM_TRY(om_flip_impl(h, 0.0, 100, &nf, &nr, &cap));
+  h->delaunay_clean = false;  // the points are about to move
   const int mode_exact = (h->limiter && h->limited_frac > 0.25) ? 1 : 0;
   OM_LAUNCH(h, k_pl_init, 1, 1, h->ds, (long long)max_num_steps, tol * tol, mode_exact,
             (long long)h->N, h->limiter, 100);
@@ -269,35 +358,19 @@ int om_run_pipelined(om_handle* h, double tol, int64_t max_num_steps, int64_t* s
   double* B = h->xnew;
   static const bool no_graph = getenv("OM_NO_GRAPH") != nullptr;
   if (no_graph || h->timing) {
-    OM_TRY(run_stream(h, A, B));
+    OM_TRY(run_stream(h, A, B, mode_exact != 0));
   } else {
-    PlCache* cache = (PlCache*)h->pl;
-    if (!cache) h->pl = cache = new PlCache();
     PlGraph* g = nullptr;
-    for (auto& c : cache->graphs)
-      if (c.buf_a == A && c.method == h->method && c.limiter == h->limiter &&
-          c.odt_bary == h->odt_bary && c.use_rings == (h->use_rings ? 1 : 0) &&
-          c.omega == h->omega)
-        g = &c;
-    if (!g) {
-      if (cache->graphs.size() >= 4) {
-        for (auto& c : cache->graphs) free_graph(c);
-        cache->graphs.clear();
-      }
-      cache->graphs.emplace_back();
-      g = &cache->graphs.back();
-      const int rc = build_graph(h, cache, g);
-      if (rc != OM_OK) {
-        free_graph(*g);
-        cache->graphs.pop_back();
-        return rc;
-      }
-    }
+    OM_TRY(get_graph(h, &g));
     CUDA_TRY(cudaGraphLaunch(g->exec, h->stream));
     OM_TRY(om_fetch_scalars(h));
   }
   h->launches += h->hs->pl_launches;
   const int64_t k = h->hs->k;
+  h->run_flips = h->hs->total_flips;
+  h->run_rounds = h->hs->total_rounds;
+  h->run_limited = h->hs->total_limited;
+  h->run_deferred = h->hs->total_deferred;
   // x_k is in A after an even number of updates
   h->x = (k & 1) ? B : A;
   h->xnew = (k & 1) ? A : B;
@@ -308,6 +381,9 @@ int om_run_pipelined(om_handle* h, double tol, int64_t max_num_steps, int64_t* s
   // the flip pass of the last step: nothing has looked at the last points yet
   OM_TRY(om_flip_impl(h, 0.0, 100, &st.n_flips, &st.n_flip_rounds, &st.flip_cap_hit));
   st.flip_cap_hit |= cap_before;
+  // totals: the flips of step j are found by iteration j+1, those of the last step just now
+  h->run_flips += st.n_flips;
+  h->run_rounds += st.n_flip_rounds;
   if (steps_done) *steps_done = k;
   if (last) *last = st;
   return OM_OK;

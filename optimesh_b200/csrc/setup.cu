@@ -360,6 +360,7 @@ int om_setup_mesh(om_handle* h, const double* points_dev, const void* cells_dev,
   if (C > 0) OM_LAUNCH(h, k_v2c, om_grid(C, B), B, h->cells, C, h->v2c);
   if (N > 0) {
     CUDA_TRY(om_malloc(h, &h->ring, sizeof(int) * OM_RING_W * N));
+    CUDA_TRY(om_malloc(h, &h->ringc, sizeof(int) * OM_RING_W * N));
     CUDA_TRY(om_malloc(h, &h->dirty, sizeof(int) * N));
     CUDA_TRY(om_malloc(h, &h->dirty_epoch, sizeof(int) * N));
     CUDA_TRY(om_malloc(h, &h->diff2, sizeof(double) * N));

@@ -75,15 +75,19 @@ __global__ void __launch_bounds__(256)
     k_build_rings(const int4* __restrict__ cells, const int* __restrict__ adj,
                   const int* __restrict__ v2c, const uint8_t* __restrict__ bflag, int n,
                   const int* __restrict__ list, const int* __restrict__ n_dev,
-                  int* __restrict__ ring, int lo, int hi, const int* __restrict__ halt) {
+                  int* __restrict__ ring, int* __restrict__ ringc, int lo, int hi,
+                  const int* __restrict__ halt) {
   if (halt && *halt) return;
   if (n_dev) n = *n_dev;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int v = LIST ? list[i] : i;
     if (v < lo || v >= hi) continue;  // partitioned run: only the own range's rows are read
-    int e[OM_RING_W];
+    int e[OM_RING_W], ec[OM_RING_W];  // neighbour ids and the cells between them
 #pragma unroll
-    for (int q = 0; q < OM_RING_W; q++) e[q] = v;
+    for (int q = 0; q < OM_RING_W; q++) {
+      e[q] = v;
+      ec[q] = -1;
+    }
     int marker = RING_ORPHAN;
     const int c0 = v2c[v];
     if (c0 != OM_NONE_CELL) {
@@ -101,11 +105,13 @@ __global__ void __launch_bounds__(256)
           while (true) {
             // twin row of cell k (`cur`): the exit edge, and whether it has a boundary edge
             const int4 ta = __ldg(reinterpret_cast<const int4*>(adj) + cur);
-            if (ta.x < 0 || ta.y < 0 || ta.z < 0) {
+            const bool bc = ta.x < 0 || ta.y < 0 || ta.z < 0;
 #pragma unroll
-              for (int q = 0; q < OM_RING_W; q++)
-                if (q == k) e[q] |= RING_BCELL;
-            }
+            for (int q = 0; q < OM_RING_W; q++)
+              if (q == k) {
+                if (bc) e[q] |= RING_BCELL;
+                ec[q] = cur;  // cell q = (v, n_q, n_{q+1})
+              }
             k++;
             const int t = cell_get(ta, kexit);
             if (t < 0) {  // open fan (cannot happen for a vertex that is not on the boundary)
@@ -145,6 +151,12 @@ __global__ void __launch_bounds__(256)
     int4* out = reinterpret_cast<int4*>(ring + (size_t)OM_RING_W * v);
     out[0] = make_int4(e[0], e[1], e[2], e[3]);
     out[1] = make_int4(e[4], e[5], e[6], e[7]);
+    if (ringc && !marker) {
+      // only read for vertices with a row and a flagged spoke (fused Delaunay check, flip.cu)
+      int4* outc = reinterpret_cast<int4*>(ringc + (size_t)OM_RING_W * v);
+      outc[0] = make_int4(ec[0], ec[1], ec[2], ec[3]);
+      outc[1] = make_int4(ec[4], ec[5], ec[6], ec[7]);
+    }
   }
 }
 
@@ -263,10 +275,22 @@ __global__ void __launch_bounds__(OM_K1_BLOCK, (D == 2 ? (EXACT ? OM_K1_MINB_EXA
     for (int i = 0; i < D; i++) d.v[i] *= p.omega;
     diff2 = vdot<D>(d, d);
     if (p.limiter) {
-      if (EXACT)
+      if (EXACT) {
         limited = ch.limit(d, diff2);
-      else
-        deferred = !ch.proves_unlimited(diff2);
+      } else if (!ch.proves_unlimited(diff2)) {
+        // The division-free bound cannot rule the limiter out (a few % of the vertices once
+        // the mesh has settled): the smallest incident inradius is evaluated exactly here,
+        // from the ring still staged in shared memory, by the limiter-only chain -- the
+        // same cell code, hence the same bits, as the exact variant of this kernel.
+        Chain<D, OM_CHAIN_LIMITER_ONLY, true, false> lim;
+        lim.init(P0);
+        lim.start(ld_ring(0));
+        lim.first(ld_ring(1), false, true);
+#pragma unroll 1
+        for (int j = 2; j < k; j++) lim.next(ld_ring(j), false);
+        lim.close(ld_ring(0), false);
+        limited = lim.limit(d, diff2);
+      }
     }
 #pragma unroll
     for (int i = 0; i < D; i++) out.v[i] = P0.v[i] + d.v[i];
@@ -404,6 +428,60 @@ __device__ __forceinline__ void walk_vertex(const StepParams& p, int v, int& err
   if (!TARGET) p.diff2[v] = limited ? -diff2 : diff2;
 }
 
+// One vertex from its ring row, outside the main kernel (vertices the lazy limiter left over,
+// vertices whose star was changed by flips): the ring coordinates are gathered straight into
+// registers, the chain is the main kernel's with the exact limiter -- the same bits as the
+// main kernel and as the star walk.  false: the vertex has no row (the caller walks its star).
+template <int D, int METHOD>
+__device__ __forceinline__ bool ring_vertex(const StepParams& p, int v, int& err) {
+  constexpr bool ODT = METHOD == OM_ODT_FIXED_POINT || METHOD == OM_ODT_DP_FP;
+  const int4* rp = reinterpret_cast<const int4*>(p.ring + (size_t)OM_RING_W * v);
+  const int4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+  if (r0.x < 0 || p.force_walk) return false;
+  const int e[OM_RING_W] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+  const int k = 1 + ((e[0] >> 30) & 1) + ((e[1] >> 29) & 2) + ((e[2] >> 28) & 4);
+  const Vec<D> P0 = ld_point<D>(p.x, v);
+  Vec<D> R[OM_RING_W];
+  unsigned bcells = 0u;
+#pragma unroll
+  for (int q = 0; q < OM_RING_W; q++) {
+    const int u = e[q] & RING_MASK;  // unused entries hold v itself: always a valid address
+    if (q < k && !p.valid(u)) p.ds->stale = 1;
+    if (ODT) bcells |= ((unsigned)(e[q] >> 29) & 1u) << q;
+    R[q] = ld_point<D>(p.x, u);
+  }
+  const bool odt_bary = ODT && p.odt_bary != 0;
+  Chain<D, METHOD, true, false> ch;
+  ch.init(P0);
+  ch.start(R[0]);
+  ch.first(R[1], odt_bary && (bcells & 1u), true);
+#pragma unroll
+  for (int j = 2; j < OM_RING_W; j++)
+    if (j < k) ch.next(R[j], odt_bary && ((bcells >> (j - 1)) & 1u));
+  ch.close(R[0], odt_bary && ((bcells >> (k - 1)) & 1u));
+  err |= ch.err;
+  Vec<D> d;
+  Vec<D> out = P0;
+  double diff2 = 0.0;
+  bool limited = false;
+  if (ch.target_offset(d)) {
+#pragma unroll
+    for (int i = 0; i < D; i++) d.v[i] *= p.omega;
+    diff2 = vdot<D>(d, d);
+    if (p.limiter) limited = ch.limit(d, diff2);
+#pragma unroll
+    for (int i = 0; i < D; i++) out.v[i] = P0.v[i] + d.v[i];
+  }
+  st_point<D>(p.xout, v, out);
+  p.diff2[v] = limited ? -diff2 : diff2;
+  return true;
+}
+
+template <int D, int METHOD>
+__device__ __forceinline__ void update_vertex(const StepParams& p, int v, int& err) {
+  if (!ring_vertex<D, METHOD>(p, v, err)) walk_vertex<D, METHOD, false>(p, v, err);
+}
+
 // get_new_points: every vertex by its star walk
 template <int D, int METHOD>
 __global__ void __launch_bounds__(128) k_target(StepParams p) {
@@ -414,24 +492,24 @@ __global__ void __launch_bounds__(128) k_target(StepParams p) {
   if (err) atomicOr(&p.ds->err, err);
 }
 
-// Vertices left by k_step_ring (flag bit VF_DEFER): the flag words of [lo, hi) are scanned in
-// chunks, the flagged vertices of a chunk are compacted into shared memory (no global
-// counter, no atomics: the order is the vertex order) and updated with all lanes busy.
+// Vertices left by k_step_ring (flag bit VF_DEFER).  Every WARP scans runs of 256 flag words
+// (one 16-byte load per lane), compacts the flagged vertices of its run into shared memory
+// with ballots and a shuffle scan -- no block barrier, no global counter, no atomics; the
+// order is the vertex order -- and updates them with its lanes.
 constexpr int POST_BLOCK = 256;
-constexpr int POST_PER = 8;  // flag words per thread and chunk (one 16-byte load)
+constexpr int POST_PER = 8;                  // flag words per lane (one 16-byte load)
+constexpr int POST_RUN = 32 * POST_PER;      // vertices per warp and trip
 template <int D, int METHOD>
 __global__ void __launch_bounds__(POST_BLOCK) k_post(StepParams p) {
-  constexpr int CHUNK = POST_BLOCK * POST_PER;
-  __shared__ int s_v[CHUNK];
-  __shared__ int s_warp[POST_BLOCK / 32];
-  __shared__ int s_total;
   if (p.gate && p.ds->halt) return;
+  __shared__ int s_v[POST_BLOCK / 32][POST_RUN];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gwarp = blockIdx.x * (POST_BLOCK / 32) + warp, nwarps = gridDim.x * (POST_BLOCK / 32);
   const int base0 = p.lo & ~(POST_PER - 1);  // 16-byte aligned start of the scan
-  const int nchunks = (p.hi - base0 + CHUNK - 1) / CHUNK;
+  const int nruns = (p.hi - base0 + POST_RUN - 1) / POST_RUN;
   int err = 0;
-  for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
-    const int vb = base0 + chunk * CHUNK + threadIdx.x * POST_PER;
+  for (int run = gwarp; run < nruns; run += nwarps) {
+    const int vb = base0 + run * POST_RUN + lane * POST_PER;
     unsigned hits = 0u;  // bit i: vertex vb + i is to be updated here
     if (vb < p.hi) {
       // (the flag array is padded to a multiple of POST_PER words beyond N)
@@ -451,6 +529,7 @@ __global__ void __launch_bounds__(POST_BLOCK) k_post(StepParams p) {
         *reinterpret_cast<uint4*>(p.vflags + vb) = raw;
       }
     }
+    if (!__any_sync(0xffffffffu, hits != 0u)) continue;
     const int cnt = __popc(hits);
     int incl = cnt;
 #pragma unroll
@@ -458,29 +537,17 @@ __global__ void __launch_bounds__(POST_BLOCK) k_post(StepParams p) {
       const int up = __shfl_up_sync(0xffffffffu, incl, o);
       if (lane >= o) incl += up;
     }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      int tot = 0;
-      for (int q = 0; q < POST_BLOCK / 32; q++) {
-        const int t = s_warp[q];
-        s_warp[q] = tot;
-        tot += t;
-      }
-      s_total = tot;
-    }
-    __syncthreads();
-    int pos = s_warp[warp] + incl - cnt;
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (lane == 0) atomicAdd(&p.ds->n_deferred, total);
+    int pos = incl - cnt;
     while (hits) {
       const int i = __ffs(hits) - 1;
       hits &= hits - 1;
-      s_v[pos++] = vb + i;
+      s_v[warp][pos++] = vb + i;
     }
-    __syncthreads();
-    const int total = s_total;
-    for (int i = threadIdx.x; i < total; i += POST_BLOCK)
-      walk_vertex<D, METHOD, false>(p, s_v[i], err);
-    __syncthreads();  // s_v / s_warp are reused by the next chunk
+    __syncwarp();
+    for (int i = lane; i < total; i += 32) update_vertex<D, METHOD>(p, s_v[warp][i], err);
+    __syncwarp();  // s_v is reused by the next run
   }
   if (err) atomicOr(&p.ds->err, err);
 }
@@ -494,7 +561,7 @@ __global__ void __launch_bounds__(128)
   int err = 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int v = list[i];
-    if (v >= p.lo && v < p.hi) walk_vertex<D, METHOD, false>(p, v, err);
+    if (v >= p.lo && v < p.hi) update_vertex<D, METHOD>(p, v, err);
   }
   if (err) atomicOr(&p.ds->err, err);
 }
@@ -559,8 +626,8 @@ int launch_method(om_handle* h, const StepParams& p, int what, bool exact, bool 
     case 1:
       return launch_ring<D, METHOD, true>(h, p, exact, part);
     case 2: {
-      const int chunks = om_grid(p.hi - (p.lo & ~(POST_PER - 1)), POST_BLOCK * POST_PER);
-      OM_LAUNCH(h, (k_post<D, METHOD>), std::min(chunks, 148 * 4), POST_BLOCK, p);
+      const int blocks = om_grid(p.hi - (p.lo & ~(POST_PER - 1)), POST_BLOCK * POST_PER);
+      OM_LAUNCH(h, (k_post<D, METHOD>), std::min(blocks, 148 * 8), POST_BLOCK, p);
       return OM_OK;
     }
     case 3:
@@ -759,6 +826,7 @@ __global__ void k_sphere_sweep(double* x, int N, double cx, double cy, double cz
 
 __global__ void k_reset_step_scalars(DevScalars* ds, int gate) {
   if (gate && ds->halt) return;
+  ds->n_deferred = 0;
   ds->n_over = 0;
   ds->stale = 0;
   ds->max_diff2_bits = 0ull;
@@ -878,6 +946,21 @@ int om_pl_launch_update(om_handle* h, const double* xin, double* xout, bool time
   return OM_OK;
 }
 
+// the same in three pieces, for a caller that runs only the variant the device selected
+// (conditional graph nodes): what = 0 reset, 1 lazy ring kernel, 2 exact ring kernel, 3 k_post
+int om_pl_launch_update_part(om_handle* h, const double* xin, double* xout, int what) {
+  StepParams p = make_params(h, xout);
+  p.x = xin;
+  p.gate = 1;
+  if (what == 0) {
+    OM_LAUNCH(h, k_reset_step_scalars, 1, 1, h->ds, 1);
+    CUDA_TRY(cudaGetLastError());
+    return OM_OK;
+  }
+  if (what == 3) return launch_step(h, p, 2);
+  return launch_step(h, p, 1, what == 2);
+}
+
 __global__ void k_pl_count(DevScalars* ds, int n) {
   if (!ds->halt) ds->pl_launches += n;
 }
@@ -886,7 +969,7 @@ __global__ void k_pl_count(DevScalars* ds, int n) {
 // from xin on the new topology, statistics of the whole update
 int om_pl_launch_tail(om_handle* h, const double* xin, double* xout) {
   OM_LAUNCH(h, (k_build_rings<true>), 148 * 4, 256, h->cells, (const int*)h->adj, h->v2c, h->bflag,
-            0, h->dirty, (const int*)&h->ds->n_dirty, h->ring, 0, (int)h->N,
+            0, h->dirty, (const int*)&h->ds->n_dirty, h->ring, h->ringc, 0, (int)h->N,
             (const int*)&h->ds->halt);
   StepParams p = make_params(h, xout);
   p.x = xin;
@@ -905,6 +988,7 @@ int om_pl_launch_tail(om_handle* h, const double* xin, double* xout) {
 int om_update_points_impl(om_handle* h, double tol, om_step_stats* out, bool target_only,
                           double* target_out, bool defer_fetch) {
   if (h->N == 0) return OM_OK;
+  if (!target_only) h->delaunay_clean = false;
   OM_LAUNCH(h, k_reset_step_scalars, 1, 1, h->ds, 0);
   int32_t iters = 0;
   if (om_is_solve_method(h->method)) {
@@ -987,6 +1071,7 @@ int om_random_move_impl(om_handle* h, uint64_t seed, int round, double amplitude
             (unsigned long long)seed, round, amplitude);
   CUDA_TRY(cudaGetLastError());
   std::swap(h->x, h->xnew);
+  h->delaunay_clean = false;
   return OM_OK;
 }
 
@@ -1022,8 +1107,8 @@ int om_rebuild_rings(om_handle* h, bool all, bool device) {
   const int B = 256;
   if (all) {
     OM_LAUNCH(h, (k_build_rings<false>), om_grid(h->N, B), B, h->cells, (const int*)h->adj, h->v2c,
-              h->bflag, (int)h->N, (const int*)nullptr, (const int*)nullptr, h->ring, 0, (int)h->N,
-              (const int*)nullptr);
+              h->bflag, (int)h->N, (const int*)nullptr, (const int*)nullptr, h->ring, h->ringc, 0,
+              (int)h->N, (const int*)nullptr);
     h->rings_partial = false;
   } else {
     // with an owned range only its rows are kept current (nothing else reads ring rows);
@@ -1033,13 +1118,14 @@ int om_rebuild_rings(om_handle* h, bool all, bool device) {
     const int lo = ranged ? (int)h->own_lo : 0, hi = ranged ? (int)h->own_hi : (int)h->N;
     if (device) {
       OM_LAUNCH(h, (k_build_rings<true>), 148 * 4, B, h->cells, (const int*)h->adj, h->v2c, h->bflag,
-                0, h->dirty, (const int*)&h->ds->n_dirty, h->ring, lo, hi, (const int*)nullptr);
+                0, h->dirty, (const int*)&h->ds->n_dirty, h->ring, h->ringc, lo, hi,
+                (const int*)nullptr);
     } else {
       const int n = h->hs->n_dirty;  // fetched by the flip pass
       if (n > 0)
         OM_LAUNCH(h, (k_build_rings<true>), std::min(om_grid(n, B), 148 * 8), B, h->cells,
                   (const int*)h->adj, h->v2c, h->bflag, n, h->dirty, (const int*)nullptr, h->ring,
-                  lo, hi, (const int*)nullptr);
+                  h->ringc, lo, hi, (const int*)nullptr);
     }
   }
   CUDA_TRY(cudaGetLastError());
@@ -1192,6 +1278,7 @@ int om_band_pack_impl(om_handle* h, const int* idx_dev, int64_t n, double* buf_d
 
 int om_band_unpack_impl(om_handle* h, const int* idx_dev, int64_t n, const double* buf_dev) {
   if (n <= 0) return OM_OK;
+  h->delaunay_clean = false;
   OM_TRY(om_band_alloc(h));
   if (h->PD == 2)
     OM_LAUNCH(h, k_band_unpack<2>, om_grid(n, 256), 256, h->x, idx_dev, (int)n, buf_dev,

@@ -185,3 +185,26 @@ def disk_mapped_grid_torch(n: int, jitter: float = 0.25, seed: int = 0, device="
     upper = torch.stack([a, d, c], dim=1)
     cells = torch.stack([lower, upper], dim=1).reshape(-1, 3).contiguous()
     return pts, cells
+
+
+def disk_gpu(n: int, rounds: int = 120, seed: int = 0, device: int = 0, stream=None,
+             jitter: float = 0.25):
+    """Random disk mesh for sizes Qhull cannot reach on the host ("a randomly generated disk
+    mesh", README.md:70-74): the mapped grid `disk_mapped_grid(n)` is
+    built on the device, then `rounds` random moves of every interior vertex, each bounded by
+    half the smallest incident inradius (no cell can invert) and followed by
+    flip-until-Delaunay, turn it into a random Delaunay triangulation of the unit disk
+    (`om_random_walk`).  120 rounds give the vertex-degree histogram of `disk()`: about 4 % of
+    the interior vertices have more than 8 cells.  Returns the resident `DeviceMesh`."""
+    import torch
+
+    from .mesh import DeviceMesh
+
+    with torch.cuda.device(device):
+        tp, tc = disk_mapped_grid_torch(n, jitter, seed, device=f"cuda:{device}")
+        torch.cuda.synchronize()
+        dm = DeviceMesh.from_torch(tp, tc, stream=stream)
+        del tp, tc
+        torch.cuda.empty_cache()
+    dm.random_walk(rounds, seed)
+    return dm

@@ -165,6 +165,18 @@ class DeviceMesh:
             warnings.warn("Maximum number of edge flips reached.")
         return steps.value, st.as_dict()
 
+    def run_prepare(self):
+        """Builds the CUDA graph `run` would launch (keeps the build out of a timed region)."""
+        check(self._lib.om_run_prepare(self._h))
+
+    def run_totals(self) -> dict:
+        """Flips, flip rounds and limited vertices summed over the steps of the last `run`."""
+        a, b, c, d = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+        check(self._lib.om_get_run_totals(self._h, C.byref(a), C.byref(b), C.byref(c),
+                                          C.byref(d)))
+        return dict(n_flips=a.value, n_flip_rounds=b.value, n_limited=c.value,
+                    n_deferred=d.value)
+
     def random_walk(self, rounds: int, seed: int = 0, amplitude: float = 1.0) -> int:
         """Synthetic workloads: `rounds` random moves bounded by half the smallest incident
         inradius, each followed by flip-until-Delaunay (om_random_walk).  Returns the flips."""

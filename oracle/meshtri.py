@@ -241,6 +241,71 @@ class MeshTri:
         used[self._cells.reshape(-1)] = True
         return used & ~self.is_boundary_point
 
+    def flip_round_survey(self, tol=0.0):
+        """One flip round with the selection rule of SURVEY.md A.7 AS WRITTEN: flag all
+        non-Delaunay interior edges; while some cell touches two or more flagged edges, every
+        such cell keeps only its most negative one (an edge dropped by either of its cells is
+        unflagged); flip what remains.  Returns the number of flips.
+
+        `flip_round` below implements this build's own single-pass rule instead (the upstream
+        rule cannot be pinned, see oracle/__init__.py).  Both rules only ever flip
+        non-Delaunay edges, one per cell and round, so they walk to the same fixed point --
+        the Delaunay triangulation, unique for points in general position -- possibly in a
+        different number of rounds and with different cell rows; `tests/test_oracle.py`
+        checks that the canonical cells agree."""
+        twin = self.twins
+        C = self._cells.shape[0]
+        ceh = self.ce_ratios.T.reshape(-1)
+        interior = twin >= 0
+        s = np.full(3 * C, np.inf)
+        s[interior] = ceh[interior] + ceh[twin[interior]]
+        flagged = s < -tol
+        if not flagged.any():
+            return 0
+        while True:
+            per_cell = flagged.reshape(C, 3).sum(axis=1)
+            crit = np.nonzero(per_cell > 1)[0]
+            if crit.size == 0:
+                break
+            sv = np.where(flagged, s, np.inf).reshape(C, 3)
+            for c in crit:
+                keep = int(np.argmin(sv[c]))
+                for k in range(3):
+                    if k != keep and flagged[3 * c + k]:
+                        flagged[3 * c + k] = False
+                        flagged[twin[3 * c + k]] = False
+        h0 = np.nonzero(flagged)[0]
+        h1 = twin[h0]
+        sel = h0 < h1
+        h0, h1 = h0[sel], h1[sel]
+        if h0.size == 0:
+            return 0
+        self._apply_flips(h0, h1)
+        return int(h0.size)
+
+    def _apply_flips(self, h0, h1):
+        a0, k0 = h0 // 3, h0 % 3
+        a1, k1 = h1 // 3, h1 % 3
+        cells = self._cells
+        v0 = cells[a0, k0]
+        v1 = cells[a1, k1]
+        v2 = cells[a0, (k0 + 1) % 3]
+        v3 = cells[a0, (k0 + 2) % 3]
+        cells[a0] = np.stack([v0, v1, v2], axis=1)
+        cells[a1] = np.stack([v0, v1, v3], axis=1)
+        self._twin = None
+        self._geo = None
+
+    def flip_until_delaunay_survey(self, tol=0.0, max_steps=100):
+        total = rounds = 0
+        for _ in range(max_steps):
+            n = self.flip_round_survey(tol)
+            if n == 0:
+                return total, rounds
+            total += n
+            rounds += 1
+        return total, rounds
+
     def flip_round(self, tol=0.0):
         """One simultaneous flip round (A.7).  Returns the number of flips.
 

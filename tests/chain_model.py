@@ -17,6 +17,15 @@ from __future__ import annotations
 import numpy as np
 
 
+def _hi(x):
+    """High 32 bits of a positive double, as the kernel reads them (__double2hiint)."""
+    return int(np.float64(x).view(np.int64) >> 32)
+
+
+def _from_hi(h):
+    return float(np.int64(int(h) << 32).view(np.float64))
+
+
 def vertex_rings(cells, n):
     """Ordered one-rings: for every vertex with a CLOSED fan the neighbour ids in walk order."""
     star = [[] for _ in range(n)]
@@ -52,7 +61,7 @@ def chain_vertex(P0, R, method, omega=1.0, bary=None):
     """One vertex: P0 (d,), ring coordinates R (k, d) in walk order.
 
     Returns dict(d=offset of the relaxed, unlimited update, rmin=smallest incident inradius,
-    min_v4, max_l (lazy limiter bound), flags=[suspicious spoke q], degenerate)."""
+    min_q (lazy limiter bound, a difference of high words), flags=[suspicious spoke q], degenerate)."""
     k = R.shape[0]
     d = R - P0
     L = np.einsum("ij,ij->i", d, d)
@@ -67,8 +76,9 @@ def chain_vertex(P0, R, method, omega=1.0, bary=None):
     t1raw = np.zeros(k)
     t2raw = np.zeros(k)
     masked = np.zeros(k, dtype=bool)
+    mflag = set()
     rmin_num, rmin_den = np.inf, 1.0
-    min_v4, max_l = np.inf, 0.0
+    min_q = 0x7fffffff
     lens = np.sqrt(L)
     for q in range(k):
         r = (q + 1) % k
@@ -78,8 +88,7 @@ def chain_vertex(P0, R, method, omega=1.0, bary=None):
             return dict(degenerate=True)
         rs = 1.0 / np.sqrt(V4)
         # limiter
-        min_v4 = min(min_v4, V4)
-        max_l = max(max_l, L[q], L[r])
+        min_q = min(min_q, _hi(V4) - max(_hi(L[q]), _hi(L[r])))
         A2 = V4 * rs
         per = lens[q] + lens[r] + np.sqrt(L[q] + L[r] - 2.0 * c)
         if A2 * rmin_den < rmin_num * per:
@@ -90,6 +99,11 @@ def chain_vertex(P0, R, method, omega=1.0, bary=None):
         if method in ("lloyd", "cvt-block-diagonal"):
             if max(T0, T1, T2) > 1.0:
                 masked[q] = True
+                # the masked cell names the spoke opposite its > 135 deg angle itself
+                if T2 > 1.0:
+                    mflag.add(q)
+                if T1 > 1.0:
+                    mflag.add(r)
                 continue
             w1, w2 = L[r] * T1, L[q] * T2
             uu = rs * (w1 + w2)
@@ -119,8 +133,8 @@ def chain_vertex(P0, R, method, omega=1.0, bary=None):
             W += L[q] * cH
             H += cH * np.outer(d[q], d[q])
         NUM += cN * d[q]
-        raw = t2raw[q] + t1raw[p]
-        if masked[q] or masked[p] or raw > -1e-9 * (abs(t2raw[q]) + abs(t1raw[p])):
+        # the kernel sees the masked (zeroed) t: conservative by the argument in chain.cuh
+        if q in mflag or cH > -1e-9 * (abs(t2[q]) + abs(t1[p])):
             flags.append(q)
     if W == 0.0:
         off = np.zeros(dim)
@@ -131,7 +145,7 @@ def chain_vertex(P0, R, method, omega=1.0, bary=None):
         off = np.linalg.solve(M, NUM / 6.0) if np.linalg.det(M) != 0.0 else np.zeros(dim)
     else:
         off = NUM / (3.0 * W)
-    return dict(d=omega * off, rmin=rmin_num / rmin_den, min_v4=min_v4, max_l=max_l,
+    return dict(d=omega * off, rmin=rmin_num / rmin_den, min_q=min_q,
                 flags=flags, degenerate=False)
 
 
@@ -163,7 +177,8 @@ def step_model(points, cells, method, omega=1.0, is_boundary=None, boundary_cell
         max_diff2 = max(max_diff2, diff2)
         limited = np.sqrt(diff2) > 0.5 * out["rmin"]
         # the lazy bound must never declare a limited vertex "not limited"
-        proves_free = 72.0 * diff2 * out["max_l"] * (1.0 + 1e-12) <= out["min_v4"]
+        dq = _from_hi(out["min_q"] - 1 + 0x3FF00000)
+        proves_free = 81.2 * diff2 <= dq
         if proves_free and limited:
             lazy_ok = False
         if limited:

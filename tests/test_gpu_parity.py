@@ -826,3 +826,105 @@ def test_random_walk_gives_a_random_delaunay_mesh(ob, G):
     assert np.array_equal(canonical_cells(c), canonical_cells(qh))
     val = np.bincount(c.reshape(-1), minlength=len(p))[~bnd]
     assert (val > 8).mean() > 0.01 and val.max() >= 9
+
+
+# ------------------------------------------------------------------ oracle parity at BASELINE sizes
+def _avail_gb():
+    try:
+        import psutil
+
+        return psutil.virtual_memory().available / 2**30
+    except Exception:
+        return 0.0
+
+
+@pytest.mark.parametrize("method", METHODS)
+def test_single_step_1m_random_mesh(ob, G, method):
+    """SURVEY.md section 4 tier 2 at 1M vertices: one update (pin, omega, exact limiter) from
+    an identical state on a RANDOM disk mesh (device generator, valence up to 12) against
+    the oracle, then the flip pass: same flips, same rounds, same cell rows."""
+    dm0 = G.disk_gpu(1000, rounds=40, seed=method.__hash__() % 7)
+    pts, cells = dm0.points, dm0.cells(np.int64)
+    dm0.close()
+    om = OMesh(pts, cells)
+    md2, nlim = oracle.driver.step(om, method, omega=1.0)
+    with ob.DeviceMesh(pts, cells) as dm:
+        dm.set_method(method, 1.0)
+        st = dm.update_points(0.0)
+        got = dm.points
+        assert rel_err(got, om.points) <= STEP_TOL
+        assert st["n_limited"] == nlim
+        assert abs(st["max_diff2"] - md2) <= 1e-9 * md2
+        of = om.flip_until_delaunay()
+        gf = dm.flip_until_delaunay()
+        assert gf == of and of[0] > 1000
+        assert np.array_equal(dm.cells(np.int64), om.cells("points"))
+
+
+def test_config2_single_step_10m(ob, G):
+    """configs[1] at full size: one cvt-block-diagonal update of the 9.95M-vertex random disk
+    mesh the bench runs on, from an identical state, against the oracle (the numpy step needs
+    about 45 GB and a minute or two)."""
+    if _avail_gb() < 100:
+        pytest.skip("needs ~100 GB of host memory for the numpy oracle at 10M vertices")
+    dm0 = G.disk_gpu(3154, rounds=120, seed=0)
+    pts, cells = dm0.points, dm0.cells(np.int64)
+    dm0.set_method("cvt-block-diagonal", 1.0)
+    st = dm0.update_points(0.0)
+    got = dm0.points
+    dm0.close()
+    assert pts.shape[0] == 9947716
+    om = OMesh(pts, cells)
+    md2, nlim = oracle.driver.step(om, "cvt-block-diagonal", omega=1.0)
+    assert rel_err(got, om.points) <= STEP_TOL
+    assert st["n_limited"] == nlim
+    assert abs(st["max_diff2"] - md2) <= 1e-9 * md2
+
+
+def test_config4_single_step_2m_sphere(ob, G):
+    """configs[3] at full size: one odt-fixed-point update + sphere projection of the
+    2M-vertex tetra-sphere (vertices perturbed on the sphere so that the update is not
+    trivial) against the oracle."""
+    pts, cells = G.tetra_sphere(1000)
+    rs = np.random.RandomState(0)
+    pts = pts + rs.normal(scale=1.0e-4, size=pts.shape)
+    pts /= np.linalg.norm(pts, axis=1)[:, None]
+    om = OMesh(pts, cells)
+    c0 = cells
+    sphere = ob.Sphere()
+    md2, nlim = oracle.driver.step(om, "odt-fixed-point", implicit_surface=sphere)
+    with ob.DeviceMesh(pts, c0) as dm:
+        dm.set_method("odt-fixed-point")
+        dm.set_sphere()
+        st = dm.update_points(0.0)
+        dm.project()
+        got = dm.points
+    assert rel_err(got, om.points) <= STEP_TOL
+    assert st["n_limited"] == nlim
+
+
+def test_cli_subdomains_on_gpu(ob, G, tmp_path):
+    """`optimesh in out -s NAME` (README.md:17 "preserves submeshes") through the device:
+    every subdomain is optimized on its own, interface vertices stay put, cell data survive."""
+    from optimesh_b200 import cli, io
+
+    pts, cells = G.disk(40, 1)
+    bary = pts[cells].mean(axis=1)
+    tag = (bary[:, 0] > 0.05).astype(np.int64) + 2 * (bary[:, 1] > 0.1).astype(np.int64)
+    src, dst = tmp_path / "in.vtk", tmp_path / "out.vtk"
+    io.write(str(src), pts, cells, cell_data={"region": tag})
+    assert cli.main([str(src), str(dst), "-m", "cvt-block-diagonal", "-n", "8", "-q", "-s", "region"]) in (0, None)
+    p2, c2, cd = io.read(str(dst), with_cell_data=True)
+    assert p2.shape == pts.shape and c2.shape == cells.shape
+    # the submeshes are preserved: same multiset of tags, and every interface vertex (one
+    # that touches cells of two regions) has not moved
+    assert np.array_equal(np.sort(cd["region"]), np.sort(tag))
+    touch = [set() for _ in range(len(pts))]
+    for row, t in zip(cells, tag):
+        for v in row:
+            touch[v].add(int(t))
+    interface = np.array([len(t) > 1 for t in touch])
+    assert interface.sum() > 10
+    assert np.array_equal(p2[interface], pts[interface])
+    moved = np.abs(p2 - pts).max(axis=1) > 0
+    assert moved.sum() > 0.5 * (~interface).sum()

@@ -356,3 +356,51 @@ def test_config1_trajectory_golden():
     assert np.allclose(norms(p), gold["norms"], rtol=1e-12)
     ah, qh, s = oracle.stats(MeshTri(p, c))
     assert ah.tolist() == gold["angle_hist"] and qh.tolist() == gold["q_hist"]
+
+
+def test_survey_flip_rule_reaches_the_same_triangulation():
+    """The per-round flip selection is this build's own rule ("an edge flips iff it is the most
+    negative flagged edge of BOTH its cells"); SURVEY.md A.7 words the upstream rule differently
+    ("while a cell touches two flagged edges it keeps its most negative one").  Neither can be
+    pinned against the reference, so row-for-row cell equality between the GPU and this oracle
+    is agreement on OUR rule.  What is independent of the rule is the fixed point: both rules
+    end in the same (canonical) triangulation -- Qhull's."""
+    import scipy.spatial
+
+    from oracle.meshtri import MeshTri, canonical_cells
+    from optimesh_b200 import generators as G
+
+    rs = np.random.RandomState(11)
+    done = 0
+    for trial in range(8):
+        pts, cells = G.disk(int(rs.randint(20, 70)), int(rs.randint(0, 100)))
+        m0 = MeshTri(pts, cells)
+        bnd = m0.is_boundary_point
+        # random moves bounded by 0.45 x the smallest incident inradius (no cell can invert),
+        # a few of them in a row so that plenty of edges stop being Delaunay
+        moved = pts.copy()
+        for _ in range(4):
+            mm = MeshTri(moved, cells)
+            rmin = np.full(len(pts), np.inf)
+            np.minimum.at(rmin, cells.reshape(-1), np.repeat(mm.cell_inradius, 3))
+            ang = rs.rand(len(pts)) * 2 * np.pi
+            step = 0.45 * rmin[:, None] * np.stack([np.cos(ang), np.sin(ang)], axis=1)
+            step[bnd] = 0.0
+            moved = moved + step
+        a, b = MeshTri(moved, cells), MeshTri(moved, cells)
+        if np.any(_signed_areas(moved, cells) * _signed_areas(pts, cells) <= 0):
+            continue  # the random move inverted a cell: not a valid mesh
+        done += 1
+        fa, ra = a.flip_until_delaunay()
+        fb, rb = b.flip_until_delaunay_survey()
+        assert fa > 0 and fb > 0
+        assert a.num_delaunay_violations() == 0 and b.num_delaunay_violations() == 0
+        ca, cb = canonical_cells(a.cells("points")), canonical_cells(b.cells("points"))
+        assert np.array_equal(ca, cb)
+        assert np.array_equal(ca, canonical_cells(scipy.spatial.Delaunay(moved).simplices))
+    assert done >= 4
+
+
+def _signed_areas(pts, cells):
+    p0, p1, p2 = pts[cells[:, 0]], pts[cells[:, 1]], pts[cells[:, 2]]
+    return (p1[:, 0] - p0[:, 0]) * (p2[:, 1] - p0[:, 1]) - (p1[:, 1] - p0[:, 1]) * (p2[:, 0] - p0[:, 0])

@@ -6,7 +6,7 @@ run() {
   python bench.py --steps 20 --warmup 3 --no-e2e --no-cpu-baseline ${BENCH_ARGS} 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read()); r=d['roofline']
-print('$1'.ljust(44), 'step %.4f ms  K1 %.4f ms  frac %.3f  flip %.4f ms' % (d['ms_per_step'], r['kernel_ms'], r['frac'], r['flip_pass_ms']))"
+print('$1'.ljust(44), 'step %.4f ms  K1 %.4f ms  frac %.3f  rest %.4f ms  early %.4f ms/step' % (d['ms_per_step'], r['kernel_ms'], r['frac'], r['rest_of_step_ms'], d['early_phase']['ms_per_step']))"
 }
 for spec in "$@"; do
   if [[ "$spec" == NVCC:* ]]; then
