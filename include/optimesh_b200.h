@@ -257,6 +257,17 @@ int om_get_timing(om_handle* h, double* step_kernel_ms, int64_t* step_kernel_lau
  * next om_create is cheap; this returns it to the driver. */
 int om_release_cached_memory(int device);
 
+/* Result buffers in pinned host memory, cached for the life of the process: om_get_points /
+ * om_get_cells into such a block are one DMA at PCIe speed (cells are widened on the device)
+ * instead of a staged copy into fresh pageable pages.  *out == NULL: the cache is full (4 GB)
+ * or pinning failed -- use ordinary memory.  om_result_free hands a block back to the cache. */
+int om_result_alloc(int64_t bytes, void** out);
+int om_result_free(void* p, int64_t bytes);
+
+/* Touches every page of a host buffer the caller is about to receive results in (huge pages
+ * requested), from the library's host threads; meant to run while the device is busy. */
+int om_prefault_host(void* p, int64_t bytes);
+
 /* kernels launched by this handle so far (bench.py's gpu_launches) */
 int om_launch_count(om_handle* h, int64_t* n);
 int om_synchronize(om_handle* h);

@@ -103,6 +103,9 @@ SIGNATURES = {
     "om_get_timing": (C.c_int, [_H, _P(C.c_double), _P(C.c_int64), _P(C.c_double),
                                 _P(C.c_int64)]),
     "om_release_cached_memory": (C.c_int, [C.c_int]),
+    "om_result_alloc": (C.c_int, [C.c_int64, _P(C.c_void_p)]),
+    "om_result_free": (C.c_int, [C.c_void_p, C.c_int64]),
+    "om_prefault_host": (C.c_int, [C.c_void_p, C.c_int64]),
     "om_launch_count": (C.c_int, [_H, _P(C.c_int64)]),
     "om_synchronize": (C.c_int, [_H]),
     "om_stream": (C.c_int, [_H, _P(C.c_void_p)]),

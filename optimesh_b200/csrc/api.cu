@@ -5,9 +5,14 @@
 #include <algorithm>
 #include <atomic>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
 #include <mutex>
 #include <thread>
 #include <vector>
+
+#include <sys/mman.h>
+#include <unistd.h>
 
 #include "common.cuh"
 #include "geom.cuh"
@@ -47,6 +52,15 @@ int om_check_dev_err(om_handle* h) {
 }
 
 namespace {
+
+bool is_pinned_host(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
 
 struct DeviceGuard {
   int prev = -1;
@@ -100,20 +114,75 @@ struct Stage {
   }
 };
 
+// A small persistent pool of host threads (spawning 16 threads per 16 MB chunk cost more
+// than the copies they did: ~40 chunks x 16 threads x 30 us per call of the API).
+class HostPool {
+ public:
+  static HostPool& get() {
+    static HostPool* pool = new HostPool(stage_threads());  // never destroyed: threads may
+    return *pool;                                           // outlive static destruction order
+  }
+  // runs f(begin, end) over [0, n) split into one piece per thread; returns when all are done
+  template <typename F>
+  void run(size_t n, F f) {
+    if (n == 0) return;
+    const int T = (int)workers_.size() + 1;
+    if (n < (1u << 16) || T == 1) {
+      f((size_t)0, n);
+      return;
+    }
+    std::lock_guard<std::mutex> serial(serial_);  // one parallel region at a time
+    const size_t per = (n + T - 1) / T;
+    std::function<void(int)> job = [&](int t) {
+      const size_t b = std::min(n, (size_t)t * per), e = std::min(n, b + per);
+      if (b < e) f(b, e);
+    };
+    {
+      std::lock_guard<std::mutex> lock(m_);
+      job_ = &job;
+      pending_ = (int)workers_.size();
+      generation_++;
+    }
+    cv_.notify_all();
+    job(T - 1);  // the caller takes the last piece
+    std::unique_lock<std::mutex> lock(m_);
+    done_.wait(lock, [&] { return pending_ == 0; });
+    job_ = nullptr;
+  }
+
+ private:
+  explicit HostPool(int threads) {
+    for (int t = 0; t + 1 < threads; t++)
+      workers_.emplace_back([this, t] {
+        uint64_t seen = 0;
+        while (true) {
+          std::function<void(int)>* job;
+          {
+            std::unique_lock<std::mutex> lock(m_);
+            cv_.wait(lock, [&] { return generation_ != seen; });
+            seen = generation_;
+            job = job_;
+          }
+          (*job)(t);
+          {
+            std::lock_guard<std::mutex> lock(m_);
+            if (--pending_ == 0) done_.notify_one();
+          }
+        }
+      });
+    for (auto& w : workers_) w.detach();
+  }
+  std::vector<std::thread> workers_;
+  std::mutex m_, serial_;
+  std::condition_variable cv_, done_;
+  std::function<void(int)>* job_ = nullptr;
+  int pending_ = 0;
+  uint64_t generation_ = 0;
+};
+
 template <typename F>
-void parallel_chunks(size_t n, F f) {  // f(begin, end) on stage_threads() host threads
-  const int T = n < (1u << 16) ? 1 : stage_threads();
-  if (T == 1) {
-    f((size_t)0, n);
-    return;
-  }
-  std::vector<std::thread> th;
-  const size_t per = (n + T - 1) / T;
-  for (int t = 0; t < T; t++) {
-    const size_t b = std::min(n, t * per), e = std::min(n, b + per);
-    if (b < e) th.emplace_back([=] { f(b, e); });
-  }
-  for (auto& x : th) x.join();
+void parallel_chunks(size_t n, F f) {  // f(begin, end) on the pool's host threads
+  HostPool::get().run(n, f);
 }
 
 // Staging buffers are kept for the lifetime of the process and handed from handle to handle
@@ -683,7 +752,18 @@ int om_get_points(om_handle* h, double* out_host) {
     OM_LAUNCH(h, k_export_points<2>, G, B, h->x, h->perm, (int)h->N, flat);
   else
     OM_LAUNCH(h, k_export_points<3>, G, B, h->x, h->perm, (int)h->N, flat);
-  int rc = staged_d2h<double, double>(h, flat, out_host, (size_t)h->N * h->D);
+  int rc = OM_OK;
+  if (is_pinned_host(out_host)) {
+    // pinned destination (om_result_alloc): one DMA, no staging
+    if (cudaMemcpyAsync(out_host, flat, sizeof(double) * h->N * h->D, cudaMemcpyDeviceToHost,
+                        h->stream) != cudaSuccess ||
+        cudaStreamSynchronize(h->stream) != cudaSuccess) {
+      om_set_error("copy of points failed: %s", cudaGetErrorString(cudaGetLastError()));
+      rc = OM_ERR_CUDA;
+    }
+  } else {
+    rc = staged_d2h<double, double>(h, flat, out_host, (size_t)h->N * h->D);
+  }
   om_free(h, flat);
   return rc;
 }
@@ -719,10 +799,29 @@ int om_get_cells(om_handle* h, void* out_host, int itemsize) {
     return OM_ERR_ARG;
   }
   if (h->C == 0) return OM_OK;
-  int* flat = nullptr;
   const size_t n = (size_t)3 * h->C;
-  CUDA_TRY(om_malloc(h, &flat, sizeof(int) * n));
   const int B = 256, G = om_grid(h->C, B);
+  if (is_pinned_host(out_host)) {
+    // pinned destination (om_result_alloc): widened on the device, one DMA, no staging
+    void* wide = nullptr;
+    CUDA_TRY(om_malloc(h, &wide, (size_t)itemsize * n));
+    if (itemsize == 4)
+      OM_LAUNCH(h, k_export_cells<int>, G, B, h->cells, h->perm, (int)h->C, (int*)wide);
+    else
+      OM_LAUNCH(h, k_export_cells<long long>, G, B, h->cells, h->perm, (int)h->C,
+                (long long*)wide);
+    int rc = OM_OK;
+    if (cudaMemcpyAsync(out_host, wide, (size_t)itemsize * n, cudaMemcpyDeviceToHost,
+                        h->stream) != cudaSuccess ||
+        cudaStreamSynchronize(h->stream) != cudaSuccess) {
+      om_set_error("copy of cells failed: %s", cudaGetErrorString(cudaGetLastError()));
+      rc = OM_ERR_CUDA;
+    }
+    om_free(h, wide);
+    return rc;
+  }
+  int* flat = nullptr;
+  CUDA_TRY(om_malloc(h, &flat, sizeof(int) * n));
   OM_LAUNCH(h, k_export_cells<int>, G, B, h->cells, h->perm, (int)h->C, flat);
   // 4 bytes per index cross the bus; 64-bit output is widened by the host threads
   int rc = itemsize == 4 ? staged_d2h<int, int>(h, flat, (int*)out_host, n)
@@ -1012,6 +1111,77 @@ int om_release_cached_memory(int device) {
       }
     }
   }
+  return OM_OK;
+}
+
+// ---- result buffers in pinned host memory, kept for the life of the process.
+// A result copied into a fresh pageable array costs a pinned staging hop, a host copy and
+// one page fault per 4 KB; into a cached pinned block it is one DMA at PCIe speed.  The
+// Python layer wraps a block as the numpy array it returns and hands it back when that
+// array is garbage collected.
+namespace {
+std::mutex g_res_mutex;
+std::vector<std::pair<void*, size_t>> g_res_free;  // blocks not in use
+size_t g_res_total = 0;
+const size_t RES_LIMIT = (size_t)4 << 30;  // pinned bytes the cache may hold
+}  // namespace
+
+int om_result_alloc(int64_t bytes, void** out) {
+  if (!out) return OM_ERR_ARG;
+  *out = nullptr;
+  if (bytes <= 0) return OM_OK;
+  const size_t want = ((size_t)bytes + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+  {
+    std::lock_guard<std::mutex> lock(g_res_mutex);
+    for (size_t i = 0; i < g_res_free.size(); i++)
+      if (g_res_free[i].second == want) {
+        *out = g_res_free[i].first;
+        g_res_free.erase(g_res_free.begin() + i);
+        return OM_OK;
+      }
+    if (g_res_total + want > RES_LIMIT) return OM_OK;  // caller falls back to pageable memory
+    g_res_total += want;
+  }
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, want, cudaHostAllocPortable) != cudaSuccess) {
+    cudaGetLastError();
+    std::lock_guard<std::mutex> lock(g_res_mutex);
+    g_res_total -= want;
+    return OM_OK;
+  }
+  *out = p;
+  return OM_OK;
+}
+
+int om_result_free(void* p, int64_t bytes) {
+  if (!p) return OM_OK;
+  const size_t want = ((size_t)bytes + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+  std::lock_guard<std::mutex> lock(g_res_mutex);
+  g_res_free.emplace_back(p, want);
+  return OM_OK;
+}
+
+int om_prefault_host(void* p, int64_t bytes) {
+  // Fresh result arrays cost one page fault per 4 KB when they are first written (155k
+  // faults for the 637 MB of a 10M-vertex result): ask for huge pages and touch every page
+  // from all host threads, while the GPU is busy with the steps.
+  if (!p || bytes <= 0) return OM_OK;
+  const size_t page = (size_t)sysconf(_SC_PAGESIZE);
+  char* b = (char*)p;
+  char* e = b + bytes;
+  char* ab = (char*)(((uintptr_t)b + page - 1) & ~(uintptr_t)(page - 1));
+  char* ae = (char*)((uintptr_t)e & ~(uintptr_t)(page - 1));
+#ifdef MADV_HUGEPAGE
+  static const bool huge = getenv("OM_NO_HUGEPAGE") == nullptr;
+  if (huge && ae > ab) madvise(ab, (size_t)(ae - ab), MADV_HUGEPAGE);
+#endif
+  const size_t npages = ((size_t)bytes + page - 1) / page;
+  parallel_chunks(std::max<size_t>(npages, (size_t)1 << 16), [=](size_t lo, size_t hi) {
+    for (size_t i = lo; i < hi && i < npages; i++) {
+      volatile char* q = b + i * page;
+      if ((char*)q < e) *q = 0;
+    }
+  });
   return OM_OK;
 }
 

@@ -56,18 +56,13 @@ __global__ void k_pl_iter_end(DevScalars* ds, cudaGraphConditionalHandle handle,
     ds->total_flips += ds->n_flips;
     ds->total_rounds += ds->n_rounds;
     ds->total_limited += (long long)ds->n_limited;
-    // The lazy limiter pays off while it leaves few vertices to k_post (a deferred vertex
-    // costs about three times a vertex of the ring kernel, the exact variant about half a
-    // vertex more for everyone).  An exact update defers only the vertices without a row, so
-    // there the number of limited vertices decides (the bound fails for about twice as many).
-    // Either variant gives a vertex the same bits.
+    // The lazy variant evaluates the limiter exactly, in a second pass over the ring, for the
+    // lanes whose division-free bound fails -- about 1.3 x the limited vertices.  A warp pays
+    // for that pass (+70 %) as soon as one of its 32 lanes needs it; the exact variant costs
+    // every warp +45 %.  Break-even: one warp in two affected, i.e. 2 % of the vertices
+    // limited.  Either variant gives a vertex the same bits.
     ds->total_deferred += ds->n_deferred;
-    if (!ds->limiter_on)
-      ds->mode_exact = 0;
-    else if (ds->mode_exact)
-      ds->mode_exact = 5ll * (long long)ds->n_limited > ds->n_free ? 1 : 0;
-    else
-      ds->mode_exact = 7ll * (long long)ds->n_deferred > ds->n_free ? 1 : 0;
+    ds->mode_exact = (ds->limiter_on && 50ll * (long long)ds->n_limited > ds->n_free) ? 1 : 0;
     double md;
     memcpy(&md, &ds->max_diff2_bits, 8);
     if (ds->err)
@@ -350,7 +345,7 @@ int om_run_pipelined(om_handle* h, double tol, int64_t max_num_steps, int64_t* s
   int32_t nr = 0, cap = 0;
   if (!h->delaunay_clean) OM_TRY(om_flip_impl(h, 0.0, 100, &nf, &nr, &cap));
   h->delaunay_clean = false;  // the points are about to move
-  const int mode_exact = (h->limiter && h->limited_frac > 0.25) ? 1 : 0;
+  const int mode_exact = (h->limiter && h->limited_frac > 0.02) ? 1 : 0;
   OM_LAUNCH(h, k_pl_init, 1, 1, h->ds, (long long)max_num_steps, tol * tol, mode_exact,
             (long long)h->N, h->limiter, 100);
   CUDA_TRY(cudaGetLastError());

@@ -216,10 +216,8 @@ int sort_pairs(om_handle* h, const K* kin, K* kout, const V* vin, V* vout, int64
   CUDA_TRY(om_malloc(h, &tmp, bytes ? bytes : 1));
   cudaError_t e =
       cub::DeviceRadixSort::SortPairs(tmp, bytes, kin, kout, vin, vout, n, 0, end_bit, h->stream);
-  cudaError_t e2 = cudaStreamSynchronize(h->stream);
-  om_free(h, tmp);
+  om_free(h, tmp);  // stream ordered: released once the sort has run
   CUDA_TRY(e);
-  CUDA_TRY(e2);
   return OM_OK;
 }
 
@@ -327,8 +325,7 @@ int om_setup_mesh(om_handle* h, const double* points_dev, const void* cells_dev,
     if (sort_cells) OM_TRY(sort_pairs(h, ckeys, ckeys2, cvals, cperm, C, bits_for(N)));
     OM_LAUNCH(h, k_build_cells4, om_grid(C, B), B, tmp3, cperm, C, h->cells);
   }
-  CUDA_TRY(cudaStreamSynchronize(h->stream));
-  om_free(h, tmp3);
+  om_free(h, tmp3);  // (stream-ordered frees: no synchronisation needed)
   om_free(h, ckeys);
   om_free(h, ckeys2);
   om_free(h, cvals);
@@ -350,7 +347,6 @@ int om_setup_mesh(om_handle* h, const double* points_dev, const void* cells_dev,
     OM_TRY(sort_pairs(h, ek, ek2, ev, ev2, M, 2 * bits));
     OM_LAUNCH(h, k_pair_twins, om_grid(M, B), B, ek2, ev2, M, bits, (int*)h->adj, h->bflag,
               &h->ds->err);
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
     om_free(h, ek);
     om_free(h, ek2);
     om_free(h, ev);

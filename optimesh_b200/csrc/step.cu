@@ -902,8 +902,9 @@ int om_launch_point_update(om_handle* h, double* out, bool check) {
     p.lo = (int)h->own_lo;
     p.hi = (int)h->own_hi;
   }
-  // the lazy limiter pays off once few vertices are limited (the previous step tells)
-  const bool exact = h->limiter && h->limited_frac > 0.25;
+  // the lazy limiter pays off once few vertices are limited (the previous step tells; see
+  // k_pl_iter_end in loop.cu for the break-even)
+  const bool exact = h->limiter && h->limited_frac > 0.02;
   if (h->timing) cudaEventRecord(h->ev[0], h->stream);
   OM_TRY(launch_step(h, p, check ? 1 : 0, exact));
   if (h->timing) {

@@ -45,6 +45,35 @@ def method_id(name: str) -> int:
     return METHOD_IDS[key]
 
 
+class _PinnedBlock:
+    """A block of the library's pinned result cache, exposed through the array interface; it
+    goes back to the cache when the numpy array built on it is garbage collected."""
+
+    def __init__(self, lib, ptr, nbytes, shape, typestr):
+        self._lib, self._ptr, self._nbytes = lib, ptr, nbytes
+        self.__array_interface__ = {"shape": tuple(shape), "typestr": typestr,
+                                    "data": (ptr, False), "version": 3}
+
+    def __del__(self):
+        try:
+            self._lib.om_result_free(self._ptr, self._nbytes)
+        except Exception:
+            pass
+
+
+def result_array(shape, dtype):
+    """An uninitialised array for a result: backed by the pinned result cache when the result
+    is large and the cache has room (om_result_alloc), an ordinary numpy array otherwise."""
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dtype.itemsize
+    if nbytes >= (8 << 20):
+        lib = _lib.load()
+        p = C.c_void_p()
+        if lib.om_result_alloc(nbytes, C.byref(p)) == 0 and p.value:
+            return np.asarray(_PinnedBlock(lib, p.value, nbytes, shape, dtype.str))
+    return np.empty(shape, dtype=dtype)
+
+
 class DeviceMesh:
     """A triangular mesh resident on one GPU."""
 
@@ -208,7 +237,12 @@ class DeviceMesh:
     # -- data movement
     @property
     def points(self) -> np.ndarray:
-        out = np.empty((self.n, self.dim), dtype=np.float64)
+        return self.get_points()
+
+    def get_points(self, out=None) -> np.ndarray:
+        if out is None:
+            out = result_array((self.n, self.dim), np.float64)
+        assert out.shape == (self.n, self.dim) and out.dtype == np.float64 and out.flags.c_contiguous
         check(self._lib.om_get_points(self._h, out.ctypes.data))
         return out
 
@@ -219,10 +253,18 @@ class DeviceMesh:
             raise ValueError(f"points must have shape {(self.n, self.dim)}")
         check(self._lib.om_set_points(self._h, new.ctypes.data))
 
-    def cells(self, dtype=None) -> np.ndarray:
+    @staticmethod
+    def cells_wire_dtype(dtype):
+        """int32 or int64: what om_get_cells writes for a result of `dtype`."""
+        dtype = np.dtype(dtype)
+        return np.dtype(np.int32 if dtype.itemsize <= 4 and dtype != np.uint32 else np.int64)
+
+    def cells(self, dtype=None, out=None) -> np.ndarray:
         dtype = np.dtype(dtype or self.cells_dtype)
-        wire = np.int32 if dtype.itemsize <= 4 and dtype != np.uint32 else np.int64
-        out = np.empty((self.c, 3), dtype=wire)
+        wire = self.cells_wire_dtype(dtype)
+        if out is None:
+            out = result_array((self.c, 3), wire)
+        assert out.shape == (self.c, 3) and out.dtype == wire and out.flags.c_contiguous
         check(self._lib.om_get_cells(self._h, out.ctypes.data, out.dtype.itemsize))
         return out.astype(dtype, copy=False)
 
