@@ -40,6 +40,9 @@ def parse():
     ap.add_argument("--rounds", type=int, default=WALK_ROUNDS,
                     help="random-walk rounds of the mesh generator (0: jittered mapped grid)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-config5", action="store_true",
+                    help="skip the config-5 block (Lloyd omega=2, 100M vertices, strong scaling)")
+    ap.add_argument("--config5-grid", type=int, default=10000)
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
 
@@ -240,6 +243,63 @@ def roofline_of(k1_ms, b_alg, n, method, extra):
     return out
 
 
+def config5_block(args, torch, dist, ob, world, rank, local, stream):
+    """BASELINE.json configs[4]: Lloyd omega=2.0 on a FIXED 100M-vertex disk mesh at N GPUs
+    (strong scaling: the reader divides the N=1 time by N x this time).  Same measurement
+    rules as the main line; every rank builds the same mesh on its device."""
+    from optimesh_b200 import generators as G
+
+    grid, rounds, warm, steps = args.config5_grid, 40, 5, 10
+    t0 = time.perf_counter()
+    dm = G.disk_gpu(grid, rounds, 0, device=local, stream=stream)
+    torch.cuda.synchronize()
+    t_gen = time.perf_counter() - t0
+    n, c = dm.n, dm.c
+    dm.set_method("lloyd", 2.0)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world == 1:
+        dm.run_prepare()
+        dm.run(0.0, warm)
+        torch.cuda.synchronize()
+        e0.record()
+        dm.run(0.0, steps)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        tot = dm.run_totals()
+        flips = tot["n_flips"]
+    else:
+        from optimesh_b200.dist import partitioned_begin, partitioned_step
+
+        band = partitioned_begin(dm)
+        for _ in range(warm):
+            partitioned_step(dm, band, 0.0)
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        flips = 0
+        e0.record()
+        for _ in range(steps):
+            flips += partitioned_step(dm, band, 0.0)["n_flips"]
+        e1.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    free, total = torch.cuda.mem_get_info()
+    dm.close()
+    return {
+        "workload": f"lloyd omega=2.0 on disk_gpu({grid}, rounds={rounds}): {n} vertices / {c} "
+                    f"cells, FIXED size at every N (strong scaling)",
+        "n_gpus": world, "n_vertices": n, "steps": steps, "warmup": warm,
+        "ms_per_step": ms / steps, "value": n * steps / (ms * 1e-3), "unit": METRIC,
+        "flips_per_step": flips / steps, "mesh_generation_s": t_gen,
+        "resident_gb_this_rank": (total - free) / 1e9,
+        "strong_scaling": "efficiency at N GPUs = ms_per_step(N=1) / (N x ms_per_step(N))",
+    }
+
+
 def run_single(args, torch, ob, local, stream):
     """N = 1: BASELINE.json configs[1] through the public loop (DeviceMesh.run = om_run: one
     CUDA graph holds update + fused Delaunay check + flip rounds + fix-up for all K steps)."""
@@ -348,6 +408,10 @@ def run_single(args, torch, ob, local, stream):
         "gpu_launches": launches,
     }
     dm.close()  # its device memory returns to the pool before the end-to-end calls
+    if not args.no_config5:
+        ob._lib.load().om_release_cached_memory(local)
+        line["config5"] = config5_block(args, torch, None, ob, 1, 0, local, stream)
+        ob._lib.load().om_release_cached_memory(local)
     if not args.no_e2e:
         # end to end through the public API with HOST buffers: upload, setup, K steps,
         # download -- all inside the timed region.  Five calls, the median is reported.
@@ -477,6 +541,9 @@ def run_multi(args, torch, dist, ob, world, rank, local, stream):
                      "slow_flip_rounds": band.slow_rounds},
     }
     dm.close()
+    if not args.no_config5:
+        ob._lib.load().om_release_cached_memory(local)
+        line["config5"] = config5_block(args, torch, dist, ob, world, rank, local, stream)
     if rank == 0:
         print(json.dumps(line), flush=True)
 

@@ -246,6 +246,33 @@ int om_flip_round_apply_gathered(om_handle* h, const void* gathered_dev, int32_t
                                  int32_t* abort_bits, int64_t* max_records_of_any_rank);
 int om_flip_pass_end(om_handle* h, int64_t* n_flips, int32_t* n_rounds);
 
+/* ONE mesh in ONE address space over the GPUs of a box (one process per GPU; NVLink / NVSwitch
+ * peer memory through CUDA virtual memory management): every mesh array is cut into
+ * `world` chunks by vertex / cell id, chunk r is physical memory of rank r's GPU, and all
+ * chunks are mapped back to back into one virtual range on every rank -- memory per rank
+ * scales with 1/world, the kernels use the same global ids everywhere, what they touch across
+ * a chunk boundary is an ordinary access to peer memory.
+ *   om_shared_begin  from a complete handle (om_create + om_flip_until_delaunay, identical on
+ *                    every rank): allocates this rank's chunks, returns their POSIX file
+ *                    descriptors (at most 32) for the caller to pass to the other ranks
+ *                    (SCM_RIGHTS over a Unix socket);
+ *   om_shared_map    fds_all[r * n_fds + i] = descriptor i of rank r as received here: maps
+ *                    everything, copies this rank's share of the mesh.  Synchronise the ranks
+ *                    afterwards; the complete handle may then be destroyed;
+ *   om_shared_run    the optimize() loop, called by every rank with the same arguments: one
+ *                    CUDA graph per rank, the ranks meet on the device (barrier + all-reduce
+ *                    through peer memory, ~9 us); results through om_get_points / om_get_cells
+ *                    on any rank (after a host barrier);
+ *   om_shared_info   this rank's vertex range, the chunk size and its resident bytes.
+ * om_destroy of a shared handle: only after every rank has stopped using the mesh. */
+int om_shared_begin(om_handle* complete, int rank, int world, om_handle** out, int32_t* fds,
+                    int32_t* n_fds);
+int om_shared_map(om_handle* h, const int32_t* fds_all, int32_t n_fds);
+int om_shared_run(om_handle* h, double tol, int64_t max_num_steps, int64_t* steps_done,
+                  om_step_stats* last);
+int om_shared_info(om_handle* h, int64_t* vertex_lo, int64_t* vertex_hi, int64_t* chunk_vertices,
+                   int64_t* resident_bytes);
+
 /* Per-kernel timing with CUDA events on the handle's stream (bench.py's roofline line):
  * when on, the fused step kernel (K1) and each flip-until-Delaunay pass are bracketed by
  * events; om_get_timing returns the accumulated device times and counts. */

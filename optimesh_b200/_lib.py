@@ -99,6 +99,11 @@ SIGNATURES = {
     "om_flip_round_pack": (C.c_int, [_H, C.c_int32, C.c_void_p]),
     "om_flip_round_apply_gathered": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_int32, _P(C.c_int64),
                                                _P(C.c_int64), _P(C.c_int32), _P(C.c_int64)]),
+    "om_shared_begin": (C.c_int, [_H, C.c_int, C.c_int, _P(_H), _P(C.c_int32), _P(C.c_int32)]),
+    "om_shared_map": (C.c_int, [_H, _P(C.c_int32), C.c_int32]),
+    "om_shared_run": (C.c_int, [_H, C.c_double, C.c_int64, _P(C.c_int64), _P(StepStats)]),
+    "om_shared_info": (C.c_int, [_H, _P(C.c_int64), _P(C.c_int64), _P(C.c_int64),
+                                 _P(C.c_int64)]),
     "om_set_timing": (C.c_int, [_H, C.c_int]),
     "om_get_timing": (C.c_int, [_H, _P(C.c_double), _P(C.c_int64), _P(C.c_double),
                                 _P(C.c_int64)]),

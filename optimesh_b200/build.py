@@ -19,7 +19,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "liboptimesh_b200.so")
-SOURCES = ["api.cu", "setup.cu", "step.cu", "flip.cu", "stats.cu", "pcg.cu", "loop.cu"]
+SOURCES = ["api.cu", "setup.cu", "step.cu", "flip.cu", "stats.cu", "pcg.cu", "loop.cu", "shared.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

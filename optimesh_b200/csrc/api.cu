@@ -514,6 +514,7 @@ int om_destroy(om_handle* h) {
   DeviceGuard guard(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   om_pl_destroy(h);
+  om_shared_destroy(h);  // (a shared handle's mesh arrays are mappings, not allocations)
   om_free(h, h->x);
   om_free(h, h->xnew);
   om_free(h, h->cells);

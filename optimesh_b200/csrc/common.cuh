@@ -62,7 +62,8 @@ struct DevScalars {
   int not_delaunay;  // a pass ended with flagged edges but no mutual pair (exact ties)
   double dot[4];   // PCG dot products
   // ---- pipelined loop (loop.cu): everything the host would decide between two steps
-  int halt;        // 0 running, 1 final step reached, 3 device error
+  int halt;        // 0 running, 1 final step reached, 3 device error (odd: stopped);
+                   // 4 flush: only the flip pass of the last points is still to run (shared.cu)
   int mode_exact;  // the next point update tracks the exact inradius
   int pl_go;       // another flip round follows (set by k_pl_round_end)
   int cap_hit;     // a flip pass ran out of rounds with flagged edges left
@@ -76,6 +77,12 @@ struct DevScalars {
   int limiter_on;
   int n_deferred;  // vertices the ring kernel left to k_post in the last update
   long long total_deferred;
+  // ---- shared address space over several GPUs (shared.cu)
+  unsigned long long sync_seq;      // meetings of the ranks so far
+  unsigned long long g_sum[4], g_max[2];  // what the last meeting reduced over the ranks
+  unsigned long long g_flips_prev, g_flips;  // flips of the pass over all ranks
+  int sync_dead;                    // a meeting timed out
+  int pad_sh;
 };
 
 struct om_handle {
@@ -158,6 +165,8 @@ struct om_handle {
   bool ev_pending = false;  // ev[0..1] recorded, elapsed time not read yet
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   void* pl = nullptr;  // cached graphs of the pipelined loop (loop.cu)
+  void* sh = nullptr;  // shared address space over several GPUs (shared.cu); the mesh arrays
+                       // of such a handle are not its own allocations
   // the last whole-mesh flip pass ended without flagged edges and no coordinate has changed
   // since: the flip pass that opens the loop has nothing to do
   bool delaunay_clean = false;
@@ -232,11 +241,17 @@ int om_pl_launch_update_part(om_handle* h, const double* xin, double* xout, int 
 int om_pl_launch_tail(om_handle* h, const double* xin, double* xout);
 int om_pl_launch_flags_check(om_handle* h, const double* xin);
 int om_pl_launch_flips(om_handle* h);
+int om_pl_launch_flips_part(om_handle* h, int which);  // 0 select, 1 flip, 2 twin patch
+int om_pl_launch_round_check(om_handle* h, const double* xin);
 int om_pl_launch_round(om_handle* h, const double* xin);
 int om_pl_launch_round_end(om_handle* h, unsigned long long handle, int use_handle);
 int om_run_pipelined(om_handle* h, double tol, int64_t max_num_steps, int64_t* steps_done,
                      om_step_stats* last);
 void om_pl_destroy(om_handle* h);
+// shared.cu: the vertex range this rank updates when the mesh lives in the shared address space
+// of several GPUs (unchanged for an ordinary handle)
+void om_shared_vertex_range(om_handle* h, int* vlo, int* vhi);
+void om_shared_destroy(om_handle* h);
 int om_pl_prepare(om_handle* h);
 // pcg.cu
 int om_pcg_impl(om_handle* h, double rtol, int max_iter, int32_t* iters, double* relres,

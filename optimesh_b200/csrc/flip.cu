@@ -540,8 +540,8 @@ __global__ void __launch_bounds__(FLG_BLOCK)
                     const int* __restrict__ ring, const int* __restrict__ ringc,
                     unsigned short* __restrict__ vflags, int N, double tol,
                     double* __restrict__ sarr, int* __restrict__ cand,
-                    int* __restrict__ cand_epoch, DevScalars* ds) {
-  if (ds->halt) return;
+                    int* __restrict__ cand_epoch, DevScalars* ds, int vlo, int vhi) {
+  if (ds->halt & 1) return;
   constexpr int NW = FLG_BLOCK / 32;
   __shared__ int s_v[NW][FLG_RUN];
   __shared__ unsigned short s_f[NW][FLG_RUN];
@@ -551,9 +551,11 @@ __global__ void __launch_bounds__(FLG_BLOCK)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gwarp = blockIdx.x * NW + warp, nwarps = gridDim.x * NW;
   const int epoch = ds->epoch;
-  const int nruns = (N + FLG_RUN - 1) / FLG_RUN;
+  // the flag words of the vertices [vlo, vhi) (vlo a multiple of FLG_PER)
+  const int nruns = (vhi - vlo + FLG_RUN - 1) / FLG_RUN;
+  N = vhi;
   for (int run = gwarp; run < nruns; run += nwarps) {
-    const int vb = run * FLG_RUN + lane * FLG_PER;
+    const int vb = vlo + run * FLG_RUN + lane * FLG_PER;
     unsigned short w[FLG_PER];
     int cnt = 0;
     if (vb < N) {
@@ -705,7 +707,7 @@ __global__ void __launch_bounds__(FLG_BLOCK)
 // ---- control of the pipelined loop: what the host decides between the rounds of a pass
 // starts a flip pass (and its first check round)
 __global__ void k_pl_pass_begin(DevScalars* ds) {
-  if (ds->halt) return;
+  if (ds->halt & 1) return;
   ds->epoch++;
   ds->dirty_pass++;
   ds->n_dirty = 0;
@@ -723,7 +725,7 @@ __global__ void k_pl_pass_begin(DevScalars* ds) {
 
 // starts the check of a further round
 __global__ void k_pl_round_begin(DevScalars* ds) {
-  if (ds->halt) return;
+  if (ds->halt & 1) return;
   ds->epoch++;
   ds->n_cand = 0;
 }
@@ -731,7 +733,7 @@ __global__ void k_pl_round_begin(DevScalars* ds) {
 // ends a round (its flips are done): counts it and decides whether another one follows
 __global__ void k_pl_round_end(DevScalars* ds, cudaGraphConditionalHandle handle, int use_handle) {
   unsigned go = 0u;
-  if (!ds->halt) {
+  if (!(ds->halt & 1)) {
     const bool progress = ds->n_flips > ds->flips_prev;
     if (progress) {
       ds->n_rounds++;
@@ -1048,16 +1050,18 @@ int om_flip_impl(om_handle* h, double tol, int max_rounds, int64_t* n_flips, int
 // stamps on the device and returns at once when the loop has halted
 int om_pl_launch_flags_check(om_handle* h, const double* xin) {
   OM_LAUNCH(h, k_pl_pass_begin, 1, 1, h->ds);
-  const int blocks = om_grid(h->N, FLG_BLOCK * FLG_PER);
+  int vlo = 0, vhi = (int)h->N;
+  om_shared_vertex_range(h, &vlo, &vhi);
+  const int blocks = om_grid(vhi - vlo, FLG_BLOCK * FLG_PER);
   const int G = std::min(blocks, 148 * 8);
   if (h->D == 2)
     OM_LAUNCH(h, k_suspect_flags<2>, G, FLG_BLOCK, xin, h->cells, (const int*)h->adj, h->v2c,
               (const int*)h->ring, (const int*)h->ringc, h->vflags, (int)h->N, 0.0, h->sarr,
-              h->cand, h->cand_epoch, h->ds);
+              h->cand, h->cand_epoch, h->ds, vlo, vhi);
   else
     OM_LAUNCH(h, k_suspect_flags<3>, G, FLG_BLOCK, xin, h->cells, (const int*)h->adj, h->v2c,
               (const int*)h->ring, (const int*)h->ringc, h->vflags, (int)h->N, 0.0, h->sarr,
-              h->cand, h->cand_epoch, h->ds);
+              h->cand, h->cand_epoch, h->ds, vlo, vhi);
   CUDA_TRY(cudaGetLastError());
   return OM_OK;
 }
@@ -1074,6 +1078,39 @@ int om_pl_launch_flips(om_handle* h) {
             h->work_epoch, h->work, h->best, h->ds, nd, 0, 0x7fffffff);
   CUDA_TRY(cudaGetLastError());
   h->nbr_valid = false;
+  return OM_OK;
+}
+
+int om_pl_launch_flips_part(om_handle* h, int which) {
+  const int B = 256, G = 148 * 8;
+  const int* nd = &h->ds->n_cand;
+  if (which == 0)
+    OM_LAUNCH(h, k_select, G, B, h->sarr, h->cand, 0, h->best, h->ds, nd);
+  else if (which == 1)
+    OM_LAUNCH(h, k_flip1, G, B, h->cells, h->adj, h->best, h->cand, 0, h->flip_epoch, h->reloc,
+              h->adj_tmp, h->v2c, h->dirty, h->dirty_epoch, h->ds, nd, 0, 0x7fffffff);
+  else
+    OM_LAUNCH(h, k_flip2, G, B, (int*)h->adj, h->adj_tmp, h->flip_epoch, h->reloc, h->cand, 0,
+              h->work_epoch, h->work, h->best, h->ds, nd, 0, 0x7fffffff);
+  CUDA_TRY(cudaGetLastError());
+  h->nbr_valid = false;
+  return OM_OK;
+}
+
+// the check of a further round alone (its flips follow through om_pl_launch_flips_part)
+int om_pl_launch_round_check(om_handle* h, const double* xin) {
+  const int B = 256, G = 148 * 8;
+  OM_LAUNCH(h, k_pl_round_begin, 1, 1, h->ds);
+  const ShardInfo none{0, 0, 0, 0, nullptr, 0, nullptr};
+  if (h->D == 2)
+    OM_LAUNCH(h, (k_suspect<2, 1>), G, B, xin, h->cells, (const int*)h->adj, 0, 0, h->work, 0.0,
+              h->sarr, h->cand, h->cand_epoch, (FlipRec*)nullptr, h->ds,
+              (const int*)&h->ds->n_work, none);
+  else
+    OM_LAUNCH(h, (k_suspect<3, 1>), G, B, xin, h->cells, (const int*)h->adj, 0, 0, h->work, 0.0,
+              h->sarr, h->cand, h->cand_epoch, (FlipRec*)nullptr, h->ds,
+              (const int*)&h->ds->n_work, none);
+  CUDA_TRY(cudaGetLastError());
   return OM_OK;
 }
 

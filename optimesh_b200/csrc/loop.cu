@@ -76,7 +76,7 @@ __global__ void k_pl_iter_end(DevScalars* ds, cudaGraphConditionalHandle handle,
 // selects the limiter variant of the ring kernel for this iteration (two IF nodes)
 __global__ void k_pl_mode(const DevScalars* ds, cudaGraphConditionalHandle lazy,
                           cudaGraphConditionalHandle exact) {
-  const bool run = !ds->halt;
+  const bool run = !(ds->halt & 1);
   cudaGraphSetConditional(lazy, run && !ds->mode_exact ? 1u : 0u);
   cudaGraphSetConditional(exact, run && ds->mode_exact ? 1u : 0u);
 }

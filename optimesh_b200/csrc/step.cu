@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(256)
                   const int* __restrict__ list, const int* __restrict__ n_dev,
                   int* __restrict__ ring, int* __restrict__ ringc, int lo, int hi,
                   const int* __restrict__ halt) {
-  if (halt && *halt) return;
+  if (halt && (*halt & 1)) return;  // (a flush iteration still rebuilds rows)
   if (n_dev) n = *n_dev;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int v = LIST ? list[i] : i;
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(OM_K1_BLOCK, (D == 2 ? (EXACT ? OM_K1_MINB_EXA
   constexpr int PER = (D == 2) ? 1 : 2;  // 16-byte pieces per vertex
   constexpr bool ODT = METHOD == OM_ODT_FIXED_POINT || METHOD == OM_ODT_DP_FP;
   __shared__ double2 ring_sm[OM_RING_W * PER * BLOCK];
-  if (p.gate && (p.ds->halt || (p.ds->mode_exact != 0) != EXACT)) return;
+  if (p.gate && ((p.ds->halt & 1) || (p.ds->mode_exact != 0) != EXACT)) return;
   const int v = p.lo + (int)(blockIdx.x * BLOCK + threadIdx.x);
   if (v >= p.hi) return;
   const int4* rp = reinterpret_cast<const int4*>(p.ring + (size_t)OM_RING_W * v);
@@ -501,7 +501,7 @@ constexpr int POST_PER = 8;                  // flag words per lane (one 16-byte
 constexpr int POST_RUN = 32 * POST_PER;      // vertices per warp and trip
 template <int D, int METHOD>
 __global__ void __launch_bounds__(POST_BLOCK) k_post(StepParams p) {
-  if (p.gate && p.ds->halt) return;
+  if (p.gate && (p.ds->halt & 1)) return;
   __shared__ int s_v[POST_BLOCK / 32][POST_RUN];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gwarp = blockIdx.x * (POST_BLOCK / 32) + warp, nwarps = gridDim.x * (POST_BLOCK / 32);
@@ -916,11 +916,12 @@ int om_launch_point_update(om_handle* h, double* out, bool check) {
 }
 
 int om_launch_reduce_stats(om_handle* h) {
-  const int lo = h->own_hi >= 0 ? (int)h->own_lo : 0;
-  const int hi = h->own_hi >= 0 ? (int)h->own_hi : (int)h->N;
+  int lo = h->own_hi >= 0 ? (int)h->own_lo : 0;
+  int hi = h->own_hi >= 0 ? (int)h->own_hi : (int)h->N;
+  om_shared_vertex_range(h, &lo, &hi);
   if (hi > lo)
     OM_LAUNCH(h, k_reduce_stats, std::min(om_grid(hi - lo, 256 * 8), 148 * 8), 256, h->diff2, lo, hi,
-              h->ds, 0);
+              h->ds, h->sh ? 1 : 0);
   CUDA_TRY(cudaGetLastError());
   return OM_OK;
 }
@@ -953,6 +954,7 @@ int om_pl_launch_update_part(om_handle* h, const double* xin, double* xout, int 
   StepParams p = make_params(h, xout);
   p.x = xin;
   p.gate = 1;
+  om_shared_vertex_range(h, &p.lo, &p.hi);  // shared address space: this rank's vertices
   if (what == 0) {
     OM_LAUNCH(h, k_reset_step_scalars, 1, 1, h->ds, 1);
     CUDA_TRY(cudaGetLastError());
@@ -976,6 +978,7 @@ int om_pl_launch_tail(om_handle* h, const double* xin, double* xout) {
   p.x = xin;
   p.gate = 1;
   OM_TRY(launch_step(h, p, 4));
+  if (h->sh) return OM_OK;  // shared address space: the caller synchronises the GPUs first
   if (h->N > 0)
     OM_LAUNCH(h, k_reduce_stats, std::min(om_grid(h->N, 256 * 8), 148 * 8), 256, h->diff2, 0,
               (int)h->N, h->ds, 1);

@@ -154,7 +154,9 @@ class BandExchange:
         self.band_bytes = 0
         self.slow_rounds = 0
         self.age, self.force, self.refresh = 0, False, 8
-        self.caps = [65536, 4096]  # record-slot capacities: round 0 / later rounds
+        # record-slot capacities: round 0 / later rounds.  They follow the largest count seen;
+        # the first guess scales with the mesh (a fresh random mesh flags ~2 % of its cells)
+        self.caps = [max(65536, _pow2_at_least(dm.c // 32)), max(4096, _pow2_at_least(dm.c // 128))]
         self.buffers = {}
         # the cells that sit on this rank's vertices (must be asked before any flip)
         lo, hi = owned_range(dm.n, self.rank, self.world)
@@ -525,3 +527,142 @@ def optimize_points_cells_sharded(points, cells, method: str, tol: float, max_nu
         else:
             run_sharded(GpuShard(dm, group), method, tol, max_num_steps, omega, group, log)
         return dm.points, dm.cells(cells.dtype)
+
+
+# ---------------------------------------------------------------------------------------------
+# One mesh in one address space over the GPUs of a box (csrc/shared.cu): memory per rank ~ 1/N,
+# no halo buffers, no collective on the data path; the ranks meet on the device.
+class SharedMesh(DeviceMesh):
+    """A mesh whose arrays are cut into `world` chunks, chunk r resident on rank r's GPU and
+    all of them mapped into one virtual range on every rank (CUDA virtual memory management
+    over NVLink peer memory).  Built from a complete `DeviceMesh` that every rank holds (same
+    inputs everywhere); `run` is the optimize() loop, called by all ranks alike."""
+
+    @classmethod
+    def from_complete(cls, full: DeviceMesh, group=None, flip_first: bool = True):
+        import array
+        import ctypes as C
+        import socket
+        import struct
+
+        import torch.distributed as dist
+
+        from . import _lib
+        from ._lib import check
+
+        lib = _lib.load()
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        if flip_first:
+            full.flip_until_delaunay()  # the loop expects a Delaunay mesh (same on every rank)
+        h = C.c_void_p()
+        fds = (C.c_int32 * 32)()
+        n = C.c_int32()
+        check(lib.om_shared_begin(full._h, rank, world, C.byref(h), fds, C.byref(n)))
+        n = n.value
+        mine = [int(fds[i]) for i in range(n)]
+        # every rank passes its descriptors to every other rank (SCM_RIGHTS, Unix datagrams)
+        tag = os.environ.get("MASTER_PORT", "0")
+        path = lambda r: f"/tmp/om_shared_{tag}_{os.getuid()}_{r}"  # noqa: E731
+        sock = socket.socket(socket.AF_UNIX, socket.SOCK_DGRAM)
+        try:
+            os.unlink(path(rank))
+        except FileNotFoundError:
+            pass
+        sock.bind(path(rank))
+        got = {rank: mine}
+        try:
+            dist.barrier(group)  # every socket is bound
+            for r in range(world):
+                if r != rank:
+                    # (socket.send_fds ignores its address argument in CPython 3.12)
+                    sock.sendmsg([struct.pack("i", rank)],
+                                 [(socket.SOL_SOCKET, socket.SCM_RIGHTS, array.array("i", mine))],
+                                 0, path(r))
+            while len(got) < world:
+                msg, rfds, _, _ = socket.recv_fds(sock, 16, n)
+                got[struct.unpack("i", msg[:4])[0]] = list(rfds)
+            flat = (C.c_int32 * (world * n))()
+            for r in range(world):
+                for i in range(n):
+                    flat[r * n + i] = got[r][i]
+            check(lib.om_shared_map(h, flat, n))
+        finally:
+            for r, lst in got.items():
+                if r != rank:
+                    for fd in lst:
+                        os.close(fd)
+            sock.close()
+            try:
+                os.unlink(path(rank))
+            except FileNotFoundError:
+                pass
+        dist.barrier(group)  # every rank has copied its share: the complete handles may go
+        self = cls.__new__(cls)
+        self.n, self.dim, self.c = full.n, full.dim, full.c
+        self.cells_dtype = full.cells_dtype
+        self._h, self._lib, self._group = h, lib, group
+        return self
+
+    def run(self, tol: float, max_num_steps: int):
+        import ctypes as C
+
+        from . import _lib
+        from ._lib import check
+
+        steps = C.c_int64()
+        st = _lib.StepStats()
+        check(self._lib.om_shared_run(self._h, float(tol), int(max_num_steps), C.byref(steps),
+                                      C.byref(st)))
+        if st.flip_cap_hit:
+            import warnings
+
+            warnings.warn("Maximum number of edge flips reached.")
+        return steps.value, st.as_dict()
+
+    def info(self) -> dict:
+        import ctypes as C
+
+        from ._lib import check
+
+        a, b, c, d = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+        check(self._lib.om_shared_info(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return dict(vertex_lo=a.value, vertex_hi=b.value, chunk_vertices=c.value,
+                    resident_bytes=d.value)
+
+    def close(self):
+        """Collective: every rank must call it (the chunks are unmapped everywhere)."""
+        if getattr(self, "_h", None) is not None and self._h:
+            import torch
+            import torch.distributed as dist
+
+            torch.cuda.synchronize()
+            if dist.is_initialized():
+                dist.barrier(self._group)  # nobody reads this rank's chunks any more
+            self._lib.om_destroy(self._h)
+            self._h = None
+
+    def __del__(self):  # no implicit collective at garbage collection
+        pass
+
+
+def optimize_points_cells_shared(points, cells, method: str, tol: float, max_num_steps: int,
+                                 omega: float = 1.0, device=None, group=None):
+    """`optimize_points_cells` for a process group with the mesh in the shared address space:
+    every rank passes the same arrays and gets the same result back (README.md:124-126)."""
+    import torch
+    import torch.distributed as dist
+
+    if device is None:
+        device = torch.cuda.current_device()
+    cells = np.asarray(cells)
+    full = DeviceMesh(points, cells, device=device)
+    full.set_method(method, omega)
+    sm = SharedMesh.from_complete(full, group)
+    full.close()
+    try:
+        sm.run(tol, max_num_steps)
+        torch.cuda.synchronize()
+        dist.barrier(group)  # every rank's part of the result is final
+        return sm.points, sm.cells(cells.dtype)
+    finally:
+        sm.close()
