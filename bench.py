@@ -269,24 +269,25 @@ def config5_block(args, torch, dist, ob, world, rank, local, stream):
         tot = dm.run_totals()
         flips = tot["n_flips"]
     else:
-        from optimesh_b200.dist import partitioned_begin, partitioned_step
+        from optimesh_b200.dist import SharedMesh
 
-        band = partitioned_begin(dm)
-        for _ in range(warm):
-            partitioned_step(dm, band, 0.0)
+        sm = SharedMesh.from_complete(dm)
+        dm.close()
+        ob._lib.load().om_release_cached_memory(local)
+        dm = sm
+        dm.run_prepare()
+        dm.run(0.0, warm)
         torch.cuda.synchronize()
         dist.barrier()
-        torch.cuda.synchronize()
-        flips = 0
-        e0.record()
-        for _ in range(steps):
-            flips += partitioned_step(dm, band, 0.0)["n_flips"]
-        e1.record()
-        torch.cuda.synchronize()
-        dist.barrier()
-        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        t0 = time.perf_counter()
+        dm.run(0.0, steps)
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+        ms = float(t.item()) * 1e3
+        flips = dm.run_totals()["n_flips"]
+        torch.cuda.synchronize()
+        dist.barrier()
     free, total = torch.cuda.mem_get_info()
     dm.close()
     return {
@@ -295,7 +296,7 @@ def config5_block(args, torch, dist, ob, world, rank, local, stream):
         "n_gpus": world, "n_vertices": n, "steps": steps, "warmup": warm,
         "ms_per_step": ms / steps, "value": n * steps / (ms * 1e-3), "unit": METRIC,
         "flips_per_step": flips / steps, "mesh_generation_s": t_gen,
-        "resident_gb_this_rank": (total - free) / 1e9,
+        "device_memory_in_use_gb_this_rank": (total - free) / 1e9,
         "strong_scaling": "efficiency at N GPUs = ms_per_step(N=1) / (N x ms_per_step(N))",
     }
 
@@ -447,100 +448,106 @@ def run_single(args, torch, ob, local, stream):
 
 
 def run_multi(args, torch, dist, ob, world, rank, local, stream):
-    """N > 1: one mesh of N x (per-GPU size) vertices, vertex ranges of it updated per rank
-    (dist.py: band exchange of coordinates and round-wise flagged-edge records over NCCL)."""
+    """N > 1: ONE mesh of N x (per-GPU size) vertices in one address space over the GPUs
+    (dist.SharedMesh, csrc/shared.cu): chunk r of every array is resident on GPU r, all chunks
+    are mapped on every rank, each rank runs the single-GPU pipeline on its own vertex range
+    and work lists, what crosses a chunk boundary is peer memory over NVLink, the ranks meet
+    on the device.  The same K steps through the same public loop as at N = 1."""
     from optimesh_b200 import generators as G
-    from optimesh_b200.dist import owned_range, partitioned_begin, partitioned_step
+    from optimesh_b200.dist import SharedMesh
 
     method, omega, grid = workload(args)
     total_grid = int(round(grid * np.sqrt(world)))
-    tp, tc = G.disk_mapped_grid_torch(total_grid, 0.25, 0, device=f"cuda:{local}")
-    n, d = int(tp.shape[0]), int(tp.shape[1])
-    c = int(tc.shape[0])
-    dm = ob.DeviceMesh.from_torch(tp, tc, stream=stream)
-    del tp, tc
-    torch.cuda.empty_cache()
-    if args.rounds > 0:
-        dm.random_walk(args.rounds, 0)  # identical on every rank (hash of the vertex id)
-    dm.set_method(method, omega)
-    lo, hi = owned_range(n, rank, world)
-    band = partitioned_begin(dm)  # own ranges + the loop's initial flip pass (untimed)
+    t_gen = time.perf_counter()
+    full = G.disk_gpu(total_grid, args.rounds, 0, device=local) if args.rounds > 0 else None
+    if full is None:
+        tp, tc = G.disk_mapped_grid_torch(total_grid, 0.25, 0, device=f"cuda:{local}")
+        full = ob.DeviceMesh.from_torch(tp, tc)
+        del tp, tc
+    n, d, c = full.n, full.dim, full.c
+    full.set_method(method, omega)
+    sm = SharedMesh.from_complete(full)  # (identical complete mesh on every rank -> chunks)
+    full.close()
+    ob._lib.load().om_release_cached_memory(local)
+    torch.cuda.synchronize()
+    t_gen = time.perf_counter() - t_gen
+    sm.run_prepare()
+    info = sm.info()
 
     def barrier():
         torch.cuda.synchronize()
         dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup + 5):  # the 5 early steps of the single-GPU line are warm-up here
-        partitioned_step(dm, band, 0.0)
-    dm.set_timing(True)
-    sampler = ClockSampler(local)
-    barrier()
-    sampler.start()
-    l0 = dm.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    flips = rounds = limited = 0
-    e0.record()
-    for _ in range(args.steps):
-        st = partitioned_step(dm, band, 0.0)
-        flips += st["n_flips"]
-        rounds += st["n_flip_rounds"]
-        limited += st["n_limited"]
-    e1.record()
-    barrier()
-    clocks = sampler.stop()
-    ms = e0.elapsed_time(e1)
-    launches = dm.launch_count - l0
-    tim = dm.timing()
-    dm.set_timing(False)
-    from optimesh_b200 import dist as _d
+    ext = torch.cuda.ExternalStream(sm.stream)  # the stream the library launches on
 
-    if _d.PROFILE:
-        steps_p = max(_d.PROFILE.get("steps", 1), 1)
-        print(f"[rank {rank}] ms/step: " + " ".join(
-            f"{k}={1e3 * v / steps_p:.3f}" if isinstance(v, float) else f"{k}={v}"
-            for k, v in _d.PROFILE.items()), file=sys.stderr)
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    def timed_run(k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        steps, last = sm.run(0.0, k)  # one graph launch; returns when this rank has finished
+        e1.record(ext)
+        e1.synchronize()
+        assert steps == k
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), sm.run_totals()
+
+    early_steps = 5
+    ms_early, tot_early = timed_run(early_steps)
+    if args.warmup > 0:
+        timed_run(args.warmup)
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = sm.launch_count
+    ms, tot = timed_run(args.steps)
+    clocks = sampler.stop()
+    launches = sm.launch_count - l0
     cnt = torch.tensor([launches], dtype=torch.int64, device="cuda")
     dist.all_reduce(cnt)
     launches = int(cnt[0].item())
-    value = n * args.steps / (ms * 1e-3)  # n = vertices of the whole (sharded) mesh
-    k1_ms = tim["step_kernel_ms"] / max(tim["step_kernel_launches"], 1)
-    n_own = hi - lo
+    value = n * args.steps / (ms * 1e-3)  # n = vertices of the whole mesh
+    k1_ms = sm.time_update(5)
+    n_own = info["vertex_hi"] - info["vertex_lo"]
     b_alg = alg_bytes(n_own, int(round(c * n_own / max(n, 1))), d)  # this rank's launch
     roofline = roofline_of(k1_ms, b_alg, n, method, {
-        "kernel_share_of_step": tim["step_kernel_ms"] / ms,
-        "flip_pass_ms": tim["flip_pass_ms"] / max(tim["flip_passes"], 1),
+        "kernel_share_of_step": k1_ms / (ms / args.steps),
+        "kernel_timing": "CUDA events around 5 launches of rank 0's update kernel on its own "
+                         "vertex range (om_shared_time_update), after the timed region",
     })
+    barrier()
     line = {
         "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {
-            "workload": f"{method} omega={omega} on a random disk mesh (disk_mapped_grid("
-                        f"{total_grid}) + {args.rounds} random-walk rounds): {n} vertices / {c} "
-                        f"cells ({n // world} vertices per GPU), fp64, step = point update + "
-                        f"limiter + flip-until-Delaunay",
+            "workload": f"{method} omega={omega} on a random disk mesh disk_gpu({total_grid}, "
+                        f"rounds={args.rounds}): {n} vertices / {c} cells ({n // world} vertices "
+                        f"per GPU), fp64, step = point update + limiter + flip-until-Delaunay",
             "method": method, "omega": omega, "n_vertices": n, "n_cells": c,
-            "parallelism": f"{world} GPUs: vertex ranges of one mesh (topology replicated), "
-                           f"update and every flip-check round sharded, band of coordinates + "
-                           f"flagged-edge records exchanged over NCCL each step",
+            "parallelism": f"{world} GPUs, one mesh in one address space: chunk r of every array "
+                           f"resident on GPU r (CUDA VMM), all chunks mapped on every rank, "
+                           f"cross-chunk accesses are NVLink peer memory, device-side meetings "
+                           f"(barrier + all-reduce through peer atomics), one CUDA graph per rank",
+            "chunk_vertices": info["chunk_vertices"],
+            "resident_gb_rank0": info["resident_bytes"] / 1e9,
+            "mesh_generation_and_distribution_s": t_gen,
             "l2": "inputs (points + ring rows = %.0f MB per GPU) larger than the 126 MB L2"
                   % (48 * n_own / 1e6),
+            "timing": "CUDA events on the library's stream around the K-step call (one graph "
+                      "launch per rank), host barrier before, max over ranks",
         },
         "steps_per_s": args.steps / (ms * 1e-3),
-        "flips_per_step": flips / args.steps, "flip_rounds_per_step": rounds / args.steps,
-        "limited_vertices_per_step": limited / args.steps,
+        "flips_per_step": tot["n_flips"] / args.steps,
+        "flip_rounds_per_step": tot["n_flip_rounds"] / args.steps,
+        "limited_vertices_per_step": tot["n_limited"] / args.steps,
+        "early_phase": {"steps": early_steps, "ms_per_step": ms_early / early_steps,
+                        "flips_per_step": tot_early["n_flips"] / early_steps},
         "roofline": roofline,
         "clocks": clocks,
         "gpu_launches": launches,
-        "exchange": {"band_vertices_all_ranks": int(sum(band.counts or [0])),
-                     "fallback_full_gathers": band.full_gathers,
-                     "slow_flip_rounds": band.slow_rounds},
     }
-    dm.close()
+    sm.close()
     if not args.no_config5:
         ob._lib.load().om_release_cached_memory(local)
         line["config5"] = config5_block(args, torch, dist, ob, world, rank, local, stream)

@@ -272,6 +272,11 @@ int om_shared_run(om_handle* h, double tol, int64_t max_num_steps, int64_t* step
                   om_step_stats* last);
 int om_shared_info(om_handle* h, int64_t* vertex_lo, int64_t* vertex_hi, int64_t* chunk_vertices,
                    int64_t* resident_bytes);
+/* om_shared_prepare builds the loop's CUDA graphs now (keeps the build out of a timed region);
+ * om_shared_time_update times this rank's update kernel on its own vertex range with CUDA
+ * events (`reps` launches into the spare buffer; the mesh is left as it was). */
+int om_shared_prepare(om_handle* h);
+int om_shared_time_update(om_handle* h, int reps, double* ms_per_launch);
 
 /* Per-kernel timing with CUDA events on the handle's stream (bench.py's roofline line):
  * when on, the fused step kernel (K1) and each flip-until-Delaunay pass are bracketed by

@@ -102,6 +102,8 @@ SIGNATURES = {
     "om_shared_begin": (C.c_int, [_H, C.c_int, C.c_int, _P(_H), _P(C.c_int32), _P(C.c_int32)]),
     "om_shared_map": (C.c_int, [_H, _P(C.c_int32), C.c_int32]),
     "om_shared_run": (C.c_int, [_H, C.c_double, C.c_int64, _P(C.c_int64), _P(StepStats)]),
+    "om_shared_prepare": (C.c_int, [_H]),
+    "om_shared_time_update": (C.c_int, [_H, C.c_int, _P(C.c_double)]),
     "om_shared_info": (C.c_int, [_H, _P(C.c_int64), _P(C.c_int64), _P(C.c_int64),
                                  _P(C.c_int64)]),
     "om_set_timing": (C.c_int, [_H, C.c_int]),

@@ -450,12 +450,10 @@ int add_cond(cudaGraph_t parent, cudaGraphConditionalHandle handle, cudaGraphCon
   return OM_OK;
 }
 
-int build_graph(om_handle* h, om_shared* sh, int which) {
+int build_graph(om_handle* h, om_shared* sh, int which, double* A, double* B) {
   if (!sh->capture_stream)
     CU_TRY2(cudaStreamCreateWithFlags(&sh->capture_stream, cudaStreamNonBlocking));
   cudaStream_t cs = sh->capture_stream;
-  double* A = h->x;
-  double* B = h->xnew;
   CU_TRY2(cudaGraphCreate(&sh->graph[which], 0));
   cudaGraph_t g = sh->graph[which];
   cudaGraphConditionalHandle outer;
@@ -522,6 +520,8 @@ int build_graph(om_handle* h, om_shared* sh, int which) {
   return OM_OK;
 }
 
+int graph_for(om_handle* h, om_shared* sh, double* A, double* B, int* which_out);
+
 void free_graphs(om_shared* sh) {
   for (int i = 0; i < 2; i++) {
     if (sh->exec[i]) cudaGraphExecDestroy(sh->exec[i]);
@@ -530,6 +530,39 @@ void free_graphs(om_shared* sh) {
     sh->graph[i] = nullptr;
     sh->graph_a[i] = nullptr;
   }
+}
+
+// the graph that starts from the buffer A (built and cached on demand; settings checked)
+int graph_for(om_handle* h, om_shared* sh, double* A, double* B, int* which_out) {
+  if (sh->g_method != h->method || sh->g_omega != h->omega || sh->g_limiter != h->limiter ||
+      sh->g_odt != h->odt_bary) {
+    free_graphs(sh);
+    sh->g_method = h->method;
+    sh->g_omega = h->omega;
+    sh->g_limiter = h->limiter;
+    sh->g_odt = h->odt_bary;
+  }
+  int which = -1;
+  for (int i = 0; i < 2; i++)
+    if (sh->graph_a[i] == A) which = i;
+  if (which < 0) {
+    which = sh->graph_a[0] ? 1 : 0;
+    if (sh->exec[which]) {
+      cudaGraphExecDestroy(sh->exec[which]);
+      cudaGraphDestroy(sh->graph[which]);
+      sh->exec[which] = nullptr;
+      sh->graph[which] = nullptr;
+      sh->graph_a[which] = nullptr;
+    }
+    OM_TRY(build_graph(h, sh, which, A, B));
+  }
+  *which_out = which;
+  return OM_OK;
+}
+
+__global__ void k_clear_flags(unsigned short* f, int lo, int hi) {
+  const int v = lo + blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < hi) f[v] = 0;
 }
 
 }  // namespace
@@ -750,27 +783,8 @@ int om_shared_run(om_handle* h, double tol, int64_t max_num_steps, int64_t* step
     return OM_ERR_ARG;
   }
   cudaSetDevice(h->device);
-  if (sh->g_method != h->method || sh->g_omega != h->omega || sh->g_limiter != h->limiter ||
-      sh->g_odt != h->odt_bary) {
-    free_graphs(sh);
-    sh->g_method = h->method;
-    sh->g_omega = h->omega;
-    sh->g_limiter = h->limiter;
-    sh->g_odt = h->odt_bary;
-  }
   int which = -1;
-  for (int i = 0; i < 2; i++)
-    if (sh->graph_a[i] == h->x) which = i;
-  if (which < 0) {
-    which = sh->graph_a[0] ? 1 : 0;
-    if (sh->exec[which]) {
-      cudaGraphExecDestroy(sh->exec[which]);
-      cudaGraphDestroy(sh->graph[which]);
-      sh->exec[which] = nullptr;
-      sh->graph[which] = nullptr;
-    }
-    OM_TRY(build_graph(h, sh, which));
-  }
+  OM_TRY(graph_for(h, sh, h->x, h->xnew, &which));
   const int mode_exact = (h->limiter && h->limited_frac > 0.02) ? 1 : 0;
   OM_LAUNCH(h, k_sh_init, 1, 1, h->ds, (long long)max_num_steps, tol * tol, mode_exact,
             (long long)h->N, h->limiter, 100);
@@ -800,6 +814,49 @@ int om_shared_run(om_handle* h, double tol, int64_t max_num_steps, int64_t* step
   st.flip_cap_hit = h->hs->cap_hit | (h->hs->not_delaunay ? 2 : 0);
   if (steps_done) *steps_done = k;
   if (last) *last = st;
+  return OM_OK;
+}
+
+// builds the graphs of both buffer parities now (keeps the build out of a timed region)
+int om_shared_prepare(om_handle* h) {
+  om_shared* sh = h ? shared_of(h) : nullptr;
+  if (!sh || !sh->mapped) {
+    om_set_error("om_shared_prepare: not a mapped shared handle");
+    return OM_ERR_ARG;
+  }
+  cudaSetDevice(h->device);
+  int which = 0;
+  OM_TRY(graph_for(h, sh, h->x, h->xnew, &which));
+  OM_TRY(graph_for(h, sh, h->xnew, h->x, &which));
+  return OM_OK;
+}
+
+// Times this rank's update kernel (the ring kernel with the fused check, lazy limiter) on its
+// own vertex range with CUDA events, `reps` launches into the spare point buffer; the mesh is
+// left as it was.  For the roofline line of a multi-GPU run (no collective, no meeting).
+int om_shared_time_update(om_handle* h, int reps, double* ms_per_launch) {
+  om_shared* sh = h ? shared_of(h) : nullptr;
+  if (!sh || !sh->mapped || reps < 1 || !ms_per_launch) {
+    om_set_error("om_shared_time_update: bad arguments");
+    return OM_ERR_ARG;
+  }
+  cudaSetDevice(h->device);
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  OM_LAUNCH(h, k_sh_init, 1, 1, h->ds, 1ll, 0.0, 0, (long long)h->N, h->limiter, 100);
+  OM_TRY(om_pl_launch_update_part(h, h->x, h->xnew, 1));  // warm-up
+  CUDA_TRY(cudaEventRecord(e0, h->stream));
+  for (int i = 0; i < reps; i++) OM_TRY(om_pl_launch_update_part(h, h->x, h->xnew, 1));
+  CUDA_TRY(cudaEventRecord(e1, h->stream));
+  if (sh->vhi > sh->vlo)
+    OM_LAUNCH(h, k_clear_flags, om_grid(sh->vhi - sh->vlo, 256), 256, h->vflags, sh->vlo, sh->vhi);
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  float ms = 0.f;
+  CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ms_per_launch = ms / reps;
   return OM_OK;
 }
 

@@ -619,6 +619,21 @@ class SharedMesh(DeviceMesh):
             warnings.warn("Maximum number of edge flips reached.")
         return steps.value, st.as_dict()
 
+    def run_prepare(self):
+        from ._lib import check
+
+        check(self._lib.om_shared_prepare(self._h))
+
+    def time_update(self, reps: int = 5) -> float:
+        """ms per launch of this rank's update kernel on its own vertex range (CUDA events)."""
+        import ctypes as C
+
+        from ._lib import check
+
+        ms = C.c_double()
+        check(self._lib.om_shared_time_update(self._h, int(reps), C.byref(ms)))
+        return ms.value
+
     def info(self) -> dict:
         import ctypes as C
 
