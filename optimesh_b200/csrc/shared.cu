@@ -162,7 +162,8 @@ enum { SYNC_BARRIER = 0, SYNC_ROUND = 1, SYNC_STATS = 2 };
 // this rank's earlier kernels, the system-scope fences order its peer writes before the
 // arrival is visible.
 __global__ void k_sync(ShView sv, DevScalars* ds, int kind) {
-  if (threadIdx.x != 0) return;
+  // one warp: lane r talks to rank r, so the peer round trips overlap instead of adding up
+  const int lane = threadIdx.x;
   if (ds->halt == 3 && ds->sync_dead) return;  // a meeting already timed out: do not wait again
   const unsigned long long s = ds->sync_seq + 1ull;
   const int slot = (int)(s % SH_SLOTS);
@@ -179,7 +180,7 @@ __global__ void k_sync(ShView sv, DevScalars* ds, int kind) {
     mx[1] = (unsigned long long)ds->err;
   }
   __threadfence_system();
-  for (int r = 0; r < sv.world; r++) {
+  for (int r = lane; r < sv.world; r += 32) {
     ShCtrl* c = sv.of(r);
     if (kind != SYNC_BARRIER) {
 #pragma unroll
@@ -188,10 +189,12 @@ __global__ void k_sync(ShView sv, DevScalars* ds, int kind) {
 #pragma unroll
       for (int i = 0; i < 2; i++)
         if (mx[i]) atomicMax_system(&c->slots[slot].mx[i], mx[i]);
+      __threadfence_system();  // the values are in place before the arrival is
     }
+    atomicAdd_system(&c->arrive, 1ull);
   }
-  __threadfence_system();
-  for (int r = 0; r < sv.world; r++) atomicAdd_system(&sv.of(r)->arrive, 1ull);
+  __syncwarp();
+  if (lane != 0) return;
   ShCtrl* mine = sv.of(sv.me);
   const unsigned long long target = (unsigned long long)sv.world * s;
   volatile unsigned long long* arrive = &mine->arrive;

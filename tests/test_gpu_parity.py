@@ -928,3 +928,49 @@ def test_cli_subdomains_on_gpu(ob, G, tmp_path):
     assert np.array_equal(p2[interface], pts[interface])
     moved = np.abs(p2 - pts).max(axis=1) > 0
     assert moved.sum() > 0.5 * (~interface).sum()
+
+
+def test_shared_address_space_loop_world_of_one(ob, G):
+    """csrc/shared.cu with a single rank: the mesh arrays are CUDA-VMM chunks mapped into one
+    virtual range, the loop is the graph with the device-side meetings (trivial at world 1).
+    Must equal the ordinary pipelined loop bit for bit.  The N-GPU check of the same path is
+    tests/run_shared_gpu.py (bit-identical to one GPU on 2 and 4 B200s)."""
+    import torch
+    import torch.distributed as dist
+
+    from optimesh_b200.dist import SharedMesh
+
+    created = False
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", str(29600 + os.getpid() % 300))
+        dist.init_process_group("gloo", rank=0, world_size=1)
+        created = True
+    try:
+        for method, omega in (("cvt-block-diagonal", 1.0), ("lloyd", 2.0)):
+            pts, cells = G.disk(90, 4)
+            with ob.DeviceMesh(pts, cells) as ref:
+                ref.set_method(method, omega)
+                k_ref, last_ref = ref.run(0.0, 6)
+                p_ref, c_ref = ref.points, ref.cells()
+            full = ob.DeviceMesh(pts, cells)
+            full.set_method(method, omega)
+            sm = SharedMesh.from_complete(full)
+            full.close()
+            try:
+                k, last = sm.run(0.0, 6)
+                torch.cuda.synchronize()
+                info = sm.info()
+                assert k == k_ref
+                assert np.array_equal(sm.points, p_ref) and np.array_equal(sm.cells(), c_ref)
+                for key in ("max_diff2", "n_limited", "n_flips", "n_flip_rounds"):
+                    assert last[key] == last_ref[key], key
+                assert (info["vertex_lo"], info["vertex_hi"]) == (0, len(pts))
+                assert sm.time_update(2) > 0.0
+                k2, _ = sm.run(1.0e-3, 500)  # stops on the tolerance, like the plain loop
+                assert 1 <= k2 < 500
+            finally:
+                sm.close()
+    finally:
+        if created:
+            dist.destroy_process_group()
