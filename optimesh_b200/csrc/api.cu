@@ -539,7 +539,6 @@ int om_destroy(om_handle* h) {
   om_free(h, h->cand_epoch);
   om_free(h, h->sarr);
   om_free(h, h->recs);
-  om_free(h, h->best);
   om_free(h, h->flip_epoch);
   om_free(h, h->reloc);
   om_free(h, h->nbr_ptr);

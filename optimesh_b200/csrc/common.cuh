@@ -82,8 +82,35 @@ struct DevScalars {
   unsigned long long g_sum[4], g_max[2];  // what the last meeting reduced over the ranks
   unsigned long long g_flips_prev, g_flips;  // flips of the pass over all ranks
   int sync_dead;                    // a meeting timed out
-  int pad_sh;
+  int pl_round;                     // flip rounds executed in the current pass (loop.cu)
 };
+
+// After the check of a flip round: do its flips run?  `cand` = edges the check flagged,
+// `flips` = flips of the pass so far (both over all GPUs when there are several).  A round
+// that flagged edges but flipped none (exact ties of s around a cycle of cells) ends the pass
+// with not_delaunay set; the round cap ends it with cap_hit when edges are still flagged.
+__device__ __forceinline__ unsigned om_flip_decide(DevScalars* ds, unsigned long long cand,
+                                                   unsigned long long flips) {
+  const bool progress = flips > ds->g_flips_prev;
+  if (progress) {
+    ds->n_rounds++;
+    ds->g_flips_prev = flips;
+  }
+  ds->g_flips = flips;
+  unsigned go = 0u;
+  if (ds->pl_round > 0 && !progress) {
+    ds->not_delaunay = 1;
+  } else if (cand > 0) {
+    if (ds->n_rounds >= ds->max_rounds) {
+      ds->cap_hit = 1;
+    } else {
+      go = 1u;
+      ds->pl_round++;
+    }
+  }
+  ds->pl_go = (int)go;
+  return go;
+}
 
 struct om_handle {
   int device = 0;
@@ -115,7 +142,6 @@ struct om_handle {
   int* cand_epoch = nullptr; // C: dedupe stamps for the candidate list
   double* sarr = nullptr;    // 4C: s of flagged half-edges (+inf when not flagged)
   FlipRec* recs = nullptr;   // C: records of the sharded check (allocated on first use)
-  int8_t* best = nullptr;    // C: locally most negative flagged edge or -1
   int* flip_epoch = nullptr; // C
   int* reloc = nullptr;      // 4C
   int4* adj_tmp = nullptr;   // C

@@ -7,9 +7,8 @@
 //             angles is obtuse, and a triangle has at most one obtuse angle -- so each cell
 //             examines at most one edge, and only then touches its neighbour (whose term is
 //             recomputed from the opposite vertex; no per-cell intermediate array).
-//   k_select  flagged cells only: most negative flagged edge of the cell (ties: lowest
-//             local index).
-//   k_flip1   candidates only: an edge kept by BOTH adjacent cells is flipped (an
+//   k_flip1   candidates only: every flagged cell keeps its most negative flagged edge (ties:
+//             lowest local index); an edge kept by BOTH adjacent cells is flipped (an
 //             independent set: every cell takes part in at most one flip); rewrites the two
 //             cells and records where the four outer half-edges move.
 //   k_flip2   candidates only: patches the twin table from the relocation records
@@ -290,17 +289,12 @@ __global__ void __launch_bounds__(256)
   block_append<2>(&ds->n_cand, cand, vals, preds);
 }
 
-// candidates: most negative flagged edge (ties: lowest local index); clears the s slots
-__global__ void __launch_bounds__(256)
-    k_select(double* __restrict__ sarr, const int* __restrict__ cand, int n,
-             int8_t* __restrict__ best, DevScalars* ds, const int* __restrict__ n_dev) {
-  if (ds->abort) return;  // gathered round rejected (uniform over the grid)
-  if (n_dev) n = *n_dev;
-  // the work list was consumed by the check of this round
-  if (blockIdx.x == 0 && threadIdx.x == 0) ds->n_work = 0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-  const int c = cand[i];
-  double2* p = reinterpret_cast<double2*>(sarr + 4 * (size_t)c);
+// the choice of a cell: its most negative flagged edge (ties: lowest local index), -1 if none.
+// Evaluated where it is needed (k_flip1, for the candidate and for the cell across its edge)
+// instead of in a kernel of its own: one launch -- and, with several GPUs, one meeting --
+// less per round.  The s slots are cleared by k_flip2, when nobody reads them any more.
+__device__ __forceinline__ int best_edge(const double* __restrict__ sarr, int c) {
+  const double2* p = reinterpret_cast<const double2*>(sarr + 4 * (size_t)c);
   const double2 s01 = p[0], s2 = p[1];
   const double sv[3] = {s01.x, s01.y, s2.x};
   int b = -1;
@@ -311,14 +305,11 @@ __global__ void __launch_bounds__(256)
       b = k;
       sb = sv[k];
     }
-  best[c] = (int8_t)b;
-  p[0] = make_double2(INFINITY, INFINITY);
-  p[1] = make_double2(INFINITY, INFINITY);
-  }
+  return b;
 }
 
 __global__ void __launch_bounds__(256)
-    k_flip1(int4* __restrict__ cells, const int4* __restrict__ adj, const int8_t* __restrict__ best,
+    k_flip1(int4* __restrict__ cells, const int4* __restrict__ adj, const double* __restrict__ sarr,
             const int* __restrict__ cand, int n, int* __restrict__ flip_epoch,
             int* __restrict__ reloc, int4* __restrict__ adj_tmp, int* __restrict__ v2c,
             int* __restrict__ dirty, int* __restrict__ dirty_epoch,
@@ -326,17 +317,19 @@ __global__ void __launch_bounds__(256)
   if (ds->abort) return;
   if (n_dev) n = *n_dev;
   const int epoch = ds->epoch, dirty_pass = ds->dirty_pass;
+  // the work list was consumed by the check of this round
+  if (blockIdx.x == 0 && threadIdx.x == 0) ds->n_work = 0;
   for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
   const int i = base + threadIdx.x;
   int nf = 0;
   int dv[4] = {0, 0, 0, 0};  // the four vertices of the flip this thread applied
   if (i < n) {
     const int a0 = cand[i];
-    const int k0 = best[a0];
+    const int k0 = best_edge(sarr, a0);  // a candidate has at least one flagged edge
     const int4 adjA = adj[a0];
-    const int t = cell_get(adjA, k0);
+    const int t = k0 >= 0 ? cell_get(adjA, k0) : -1;
     const int a1 = t >> 2, k1 = t & 3;
-    if (best[a1] == k1) {
+    if (t >= 0 && best_edge(sarr, a1) == k1) {
       const int4 A = cells[a0];
       const int4 Bc = cells[a1];
       // the half-edge with the smaller caller-numbering id owns the flip
@@ -394,7 +387,7 @@ __global__ void __launch_bounds__(256)
     k_flip2(int* __restrict__ adj, const int4* __restrict__ adj_tmp,
             const int* __restrict__ flip_epoch, const int* __restrict__ reloc,
             const int* __restrict__ cand, int n, int* __restrict__ work_epoch,
-            int* __restrict__ work, int8_t* __restrict__ best, DevScalars* ds,
+            int* __restrict__ work, double* __restrict__ sarr, DevScalars* ds,
             const int* __restrict__ n_dev, int clo, int chi) {
   if (ds->abort) return;
   if (n_dev) n = *n_dev;
@@ -406,7 +399,10 @@ __global__ void __launch_bounds__(256)
   int add[4] = {-1, -1, -1, -1};
   if (i < n) {
     const int c = cand[i];
-    best[c] = -1;  // k_flip1 is done with it; non-candidates must read "no flagged edge"
+    // k_flip1 is done with the s slots; non-candidates must read "no flagged edge"
+    double2* p = reinterpret_cast<double2*>(sarr + 4 * (size_t)c);
+    p[0] = make_double2(INFINITY, INFINITY);
+    p[1] = make_double2(INFINITY, INFINITY);
     add[0] = c;
     if (flip_epoch[c] == epoch) {
       const int4 t = adj_tmp[c];
@@ -721,6 +717,8 @@ __global__ void k_pl_pass_begin(DevScalars* ds) {
   ds->n_rounds = 0;
   ds->flips_prev = 0;
   ds->not_delaunay = 0;
+  ds->pl_round = 0;
+  ds->g_flips_prev = 0;
 }
 
 // starts the check of a further round
@@ -730,26 +728,17 @@ __global__ void k_pl_round_begin(DevScalars* ds) {
   ds->n_cand = 0;
 }
 
-// ends a round (its flips are done): counts it and decides whether another one follows
+// Decides, after a check, whether its flips run.  The check before knows the candidates of the
+// round to come, n_flips what the round before achieved: a round whose check flags nothing is
+// never launched (with several GPUs that is three meetings saved per pass).
 __global__ void k_pl_round_end(DevScalars* ds, cudaGraphConditionalHandle handle, int use_handle) {
   unsigned go = 0u;
   if (!(ds->halt & 1)) {
-    const bool progress = ds->n_flips > ds->flips_prev;
-    if (progress) {
-      ds->n_rounds++;
-      ds->flips_prev = ds->n_flips;
-    }
-    if (ds->n_cand > 0) {
-      if (!progress)
-        ds->not_delaunay = 1;  // flagged but no mutual pair (exact ties): leave it at that
-      else if (ds->n_rounds >= ds->max_rounds)
-        ds->cap_hit = 1;
-      else
-        go = 1u;
-    }
+    // first decision of a pass: pass begin, flag check, this; later: flip1, flip2, round begin,
+    // check, this
+    ds->pl_launches += ds->pl_round > 0 ? 5 : 3;
+    go = om_flip_decide(ds, (unsigned long long)ds->n_cand, (unsigned long long)ds->n_flips);
   }
-  ds->pl_go = (int)go;
-  ds->pl_launches += 6;  // begin, check, select, flip1, flip2, end
   if (use_handle) cudaGraphSetConditional(handle, go);
 }
 
@@ -771,12 +760,11 @@ int flip_rounds(om_handle* h, double tol, int max_rounds, int64_t* n_flips, int3
   };
   auto launch_flips = [&](int n_host, const int* n_dev, long long bound) {
     const int G = grid_for(bound);
-    OM_LAUNCH(h, k_select, G, B, h->sarr, h->cand, n_host, h->best, h->ds, n_dev);
-    OM_LAUNCH(h, k_flip1, G, B, h->cells, h->adj, h->best, h->cand, n_host,
+    OM_LAUNCH(h, k_flip1, G, B, h->cells, h->adj, h->sarr, h->cand, n_host,
               h->flip_epoch, h->reloc, h->adj_tmp, h->v2c, h->dirty, h->dirty_epoch,
               h->ds, n_dev, h->flt_vlo, h->flt_vhi);
     OM_LAUNCH(h, k_flip2, G, B, (int*)h->adj, h->adj_tmp, h->flip_epoch, h->reloc, h->cand,
-              n_host, h->work_epoch, h->work, h->best, h->ds, n_dev, h->flt_clo, h->flt_chi);
+              n_host, h->work_epoch, h->work, h->sarr, h->ds, n_dev, h->flt_clo, h->flt_chi);
     h->nbr_valid = false;
   };
   int rounds = 0, cap = 0;
@@ -936,12 +924,11 @@ int om_flip_round_apply_gathered_impl(om_handle* h, const void* gathered, int P,
             h->cand_epoch, h->ds);
   const int bound = (int)std::min<int64_t>(2ll * P * cap, h->C);
   const int* nd = &h->ds->n_cand;
-  OM_LAUNCH(h, k_select, om_grid(bound, B), B, h->sarr, h->cand, 0, h->best, h->ds, nd);
-  OM_LAUNCH(h, k_flip1, om_grid(bound, B), B, h->cells, h->adj, h->best, h->cand, 0,
+  OM_LAUNCH(h, k_flip1, om_grid(bound, B), B, h->cells, h->adj, h->sarr, h->cand, 0,
             h->flip_epoch, h->reloc, h->adj_tmp, h->v2c, h->dirty, h->dirty_epoch,
             h->ds, nd, h->flt_vlo, h->flt_vhi);
   OM_LAUNCH(h, k_flip2, om_grid(bound, B), B, (int*)h->adj, h->adj_tmp, h->flip_epoch, h->reloc,
-            h->cand, 0, h->work_epoch, h->work, h->best, h->ds, nd, h->flt_clo, h->flt_chi);
+            h->cand, 0, h->work_epoch, h->work, h->sarr, h->ds, nd, h->flt_clo, h->flt_chi);
   h->nbr_valid = false;
   OM_TRY(om_fetch_scalars(h));
   OM_TRY(om_check_dev_err(h));
@@ -960,12 +947,11 @@ int om_flip_round_apply_impl(om_handle* h, int64_t total_records, int64_t* n_can
   const int bound = (int)std::min<int64_t>(2 * total_records, h->C);
   if (bound > 0) {
     const int* nd = &h->ds->n_cand;
-    OM_LAUNCH(h, k_select, om_grid(bound, B), B, h->sarr, h->cand, 0, h->best, h->ds, nd);
-    OM_LAUNCH(h, k_flip1, om_grid(bound, B), B, h->cells, h->adj, h->best, h->cand, 0,
+    OM_LAUNCH(h, k_flip1, om_grid(bound, B), B, h->cells, h->adj, h->sarr, h->cand, 0,
               h->flip_epoch, h->reloc, h->adj_tmp, h->v2c, h->dirty, h->dirty_epoch,
               h->ds, nd, h->flt_vlo, h->flt_vhi);
     OM_LAUNCH(h, k_flip2, om_grid(bound, B), B, (int*)h->adj, h->adj_tmp, h->flip_epoch, h->reloc,
-              h->cand, 0, h->work_epoch, h->work, h->best, h->ds, nd, h->flt_clo, h->flt_chi);
+              h->cand, 0, h->work_epoch, h->work, h->sarr, h->ds, nd, h->flt_clo, h->flt_chi);
     h->nbr_valid = false;
   }
   OM_TRY(om_fetch_scalars(h));
@@ -1066,16 +1052,15 @@ int om_pl_launch_flags_check(om_handle* h, const double* xin) {
   return OM_OK;
 }
 
-// select + flip + twin patch on the candidate list (k_select and the flip kernels return at
+// flip + twin patch on the candidate list (the flip kernels return at
 // once on an empty list; ds->abort is 0 in the pipelined loop)
 int om_pl_launch_flips(om_handle* h) {
   const int B = 256, G = 148 * 8;
   const int* nd = &h->ds->n_cand;
-  OM_LAUNCH(h, k_select, G, B, h->sarr, h->cand, 0, h->best, h->ds, nd);
-  OM_LAUNCH(h, k_flip1, G, B, h->cells, h->adj, h->best, h->cand, 0, h->flip_epoch, h->reloc,
+  OM_LAUNCH(h, k_flip1, G, B, h->cells, h->adj, h->sarr, h->cand, 0, h->flip_epoch, h->reloc,
             h->adj_tmp, h->v2c, h->dirty, h->dirty_epoch, h->ds, nd, 0, 0x7fffffff);
   OM_LAUNCH(h, k_flip2, G, B, (int*)h->adj, h->adj_tmp, h->flip_epoch, h->reloc, h->cand, 0,
-            h->work_epoch, h->work, h->best, h->ds, nd, 0, 0x7fffffff);
+            h->work_epoch, h->work, h->sarr, h->ds, nd, 0, 0x7fffffff);
   CUDA_TRY(cudaGetLastError());
   h->nbr_valid = false;
   return OM_OK;
@@ -1084,14 +1069,12 @@ int om_pl_launch_flips(om_handle* h) {
 int om_pl_launch_flips_part(om_handle* h, int which) {
   const int B = 256, G = 148 * 8;
   const int* nd = &h->ds->n_cand;
-  if (which == 0)
-    OM_LAUNCH(h, k_select, G, B, h->sarr, h->cand, 0, h->best, h->ds, nd);
-  else if (which == 1)
-    OM_LAUNCH(h, k_flip1, G, B, h->cells, h->adj, h->best, h->cand, 0, h->flip_epoch, h->reloc,
+  if (which == 1)
+    OM_LAUNCH(h, k_flip1, G, B, h->cells, h->adj, h->sarr, h->cand, 0, h->flip_epoch, h->reloc,
               h->adj_tmp, h->v2c, h->dirty, h->dirty_epoch, h->ds, nd, 0, 0x7fffffff);
   else
     OM_LAUNCH(h, k_flip2, G, B, (int*)h->adj, h->adj_tmp, h->flip_epoch, h->reloc, h->cand, 0,
-              h->work_epoch, h->work, h->best, h->ds, nd, 0, 0x7fffffff);
+              h->work_epoch, h->work, h->sarr, h->ds, nd, 0, 0x7fffffff);
   CUDA_TRY(cudaGetLastError());
   h->nbr_valid = false;
   return OM_OK;
@@ -1114,20 +1097,10 @@ int om_pl_launch_round_check(om_handle* h, const double* xin) {
   return OM_OK;
 }
 
-// a further round: exact check of the work list, then its flips
+// a further round: the flips of the last check, then the exact check of the cells they touched
 int om_pl_launch_round(om_handle* h, const double* xin) {
-  const int B = 256, G = 148 * 8;
-  OM_LAUNCH(h, k_pl_round_begin, 1, 1, h->ds);
-  const ShardInfo none{0, 0, 0, 0, nullptr, 0, nullptr};
-  if (h->D == 2)
-    OM_LAUNCH(h, (k_suspect<2, 1>), G, B, xin, h->cells, (const int*)h->adj, 0, 0, h->work, 0.0,
-              h->sarr, h->cand, h->cand_epoch, (FlipRec*)nullptr, h->ds,
-              (const int*)&h->ds->n_work, none);
-  else
-    OM_LAUNCH(h, (k_suspect<3, 1>), G, B, xin, h->cells, (const int*)h->adj, 0, 0, h->work, 0.0,
-              h->sarr, h->cand, h->cand_epoch, (FlipRec*)nullptr, h->ds,
-              (const int*)&h->ds->n_work, none);
-  return om_pl_launch_flips(h);
+  OM_TRY(om_pl_launch_flips(h));
+  return om_pl_launch_round_check(h, xin);
 }
 
 int om_pl_launch_round_end(om_handle* h, unsigned long long handle, int use_handle) {

@@ -104,12 +104,12 @@ struct PlCache {
     }                                                                                 \
   } while (0)
 
-// the kernels of one iteration after the ring kernel, up to (and including) the first flip round
+// the kernels of one iteration after the ring kernel, up to the decision about the first flip
+// round (a pass whose check flags nothing launches no flip kernel at all)
 int enqueue_head_rest(om_handle* h, const double* xin, double* xout, unsigned long long inner,
                       int use_handle) {
   OM_TRY(om_pl_launch_update_part(h, xin, xout, 3));
   OM_TRY(om_pl_launch_flags_check(h, xin));
-  OM_TRY(om_pl_launch_flips(h));
   OM_TRY(om_pl_launch_round_end(h, inner, use_handle));
   return OM_OK;
 }

@@ -280,7 +280,6 @@ int om_setup_mesh(om_handle* h, const double* points_dev, const void* cells_dev,
   CUDA_TRY(om_malloc(h, &h->cand, sizeof(int) * std::max<int64_t>(C, 1)));
   CUDA_TRY(om_malloc(h, &h->work, sizeof(int) * std::max<int64_t>(C, 1)));
   CUDA_TRY(om_malloc(h, &h->work_epoch, sizeof(int) * std::max<int64_t>(C, 1)));
-  CUDA_TRY(om_malloc(h, &h->best, std::max<int64_t>(C, 1)));
   CUDA_TRY(om_malloc(h, &h->cand_epoch, sizeof(int) * std::max<int64_t>(C, 1)));
   CUDA_TRY(om_malloc(h, &h->sarr, sizeof(double) * 4 * std::max<int64_t>(C, 1)));
   CUDA_TRY(om_malloc(h, &h->flip_epoch, sizeof(int) * std::max<int64_t>(C, 1)));
@@ -292,7 +291,6 @@ int om_setup_mesh(om_handle* h, const double* points_dev, const void* cells_dev,
   CUDA_TRY(cudaMemsetAsync(h->flip_epoch, 0, sizeof(int) * std::max<int64_t>(C, 1), h->stream));
   CUDA_TRY(cudaMemsetAsync(h->work_epoch, 0, sizeof(int) * std::max<int64_t>(C, 1), h->stream));
   CUDA_TRY(cudaMemsetAsync(h->cand_epoch, 0, sizeof(int) * std::max<int64_t>(C, 1), h->stream));
-  CUDA_TRY(cudaMemsetAsync(h->best, 0xff, std::max<int64_t>(C, 1), h->stream));
   OM_LAUNCH(h, k_fill_double, om_grid(4 * std::max<int64_t>(C, 1), B), B, h->sarr,
             4 * std::max<int64_t>(C, 1), (double)INFINITY);
   CUDA_TRY(cudaMemsetAsync(h->bflag, 0, N, h->stream));

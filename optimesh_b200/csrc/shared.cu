@@ -161,10 +161,16 @@ enum { SYNC_BARRIER = 0, SYNC_ROUND = 1, SYNC_STATS = 2 };
 // a barrier on the arrival counters.  One thread; the kernel boundary before it has completed
 // this rank's earlier kernels, the system-scope fences order its peer writes before the
 // arrival is visible.
-__global__ void k_sync(ShView sv, DevScalars* ds, int kind) {
+__device__ void sh_iter_end(DevScalars* ds, cudaGraphConditionalHandle handle);
+
+__global__ void k_sync(ShView sv, DevScalars* ds, int kind, cudaGraphConditionalHandle handle) {
   // one warp: lane r talks to rank r, so the peer round trips overlap instead of adding up
   const int lane = threadIdx.x;
-  if (ds->halt == 3 && ds->sync_dead) return;  // a meeting already timed out: do not wait again
+  if (ds->halt == 3 && ds->sync_dead) {
+    // a meeting already timed out: do not wait again, and let the loops of the graph end
+    if (lane == 0 && kind != SYNC_BARRIER) cudaGraphSetConditional(handle, 0u);
+    return;
+  }
   const unsigned long long s = ds->sync_seq + 1ull;
   const int slot = (int)(s % SH_SLOTS);
   unsigned long long sum[4] = {0ull, 0ull, 0ull, 0ull}, mx[2] = {0ull, 0ull};
@@ -226,6 +232,20 @@ __global__ void k_sync(ShView sv, DevScalars* ds, int kind) {
   ahead->mx[0] = ahead->mx[1] = 0ull;
   ds->sync_seq = s;
   ds->pl_launches += 1;
+  if (kind == SYNC_ROUND) {
+    // ends the check of a flip round with the GLOBAL counts: the same decision on every rank
+    unsigned go = 0u;
+    if (!(ds->halt & 1)) {
+      if (ds->g_max[1]) ds->err |= (int)ds->g_max[1];
+      // kernels since the last decision (meetings count themselves): pass begin, flag check /
+      // flip1, flip2, round begin, check
+      ds->pl_launches += ds->pl_round > 0 ? 4 : 2;
+      go = om_flip_decide(ds, ds->g_sum[0], ds->g_sum[1]);
+    }
+    cudaGraphSetConditional(handle, go);
+  } else if (kind == SYNC_STATS) {
+    sh_iter_end(ds, handle);
+  }
 }
 
 __global__ void k_sh_init(DevScalars* ds, long long max_steps, double tol2, int mode_exact,
@@ -246,41 +266,8 @@ __global__ void k_sh_init(DevScalars* ds, long long max_steps, double tol2, int 
   ds->g_flips_prev = 0;
 }
 
-// starts the flip pass of an iteration on every rank alike
-__global__ void k_sh_pass_begin(DevScalars* ds) {
-  if (ds->halt & 1) return;
-  ds->g_flips_prev = 0;
-  ds->n_rounds = 0;
-}
-
-// ends a flip round with the GLOBAL counts of the meeting before it (same decision everywhere)
-__global__ void k_sh_round_end(DevScalars* ds, cudaGraphConditionalHandle handle) {
-  unsigned go = 0u;
-  if (!(ds->halt & 1)) {
-    const unsigned long long cand = ds->g_sum[0], flips = ds->g_sum[1];
-    if (ds->g_max[1]) ds->err |= (int)ds->g_max[1];
-    const bool progress = flips > ds->g_flips_prev;
-    if (progress) {
-      ds->n_rounds++;
-      ds->g_flips_prev = flips;
-    }
-    ds->g_flips = flips;
-    if (cand > 0) {
-      if (!progress)
-        ds->not_delaunay = 1;
-      else if (ds->n_rounds >= ds->max_rounds)
-        ds->cap_hit = 1;
-      else
-        go = 1u;
-    }
-  }
-  ds->pl_go = (int)go;
-  ds->pl_launches += 7;
-  cudaGraphSetConditional(handle, go);
-}
-
 // ends an iteration with the GLOBAL statistics of the update
-__global__ void k_sh_iter_end(DevScalars* ds, cudaGraphConditionalHandle handle) {
+__device__ void sh_iter_end(DevScalars* ds, cudaGraphConditionalHandle handle) {
   if (ds->halt == 4) {
     // the flush iteration: the flip pass of the last points is done
     ds->n_flips = (int)ds->g_flips;
@@ -304,7 +291,8 @@ __global__ void k_sh_iter_end(DevScalars* ds, cudaGraphConditionalHandle handle)
     else if (md < ds->tol2 || ds->k >= ds->max_steps)
       ds->halt = 4;  // one more pass of the loop body: only its flip pass runs
   }
-  ds->pl_launches += 12;
+  // reset, variant selection, ring kernel, post, ring rows, fix-up, reduce
+  ds->pl_launches += 7;
   cudaGraphSetConditional(handle, (ds->halt & 1) ? 0u : 1u);
 }
 
@@ -392,22 +380,22 @@ ShView view_of(om_shared* sh) {
   return v;
 }
 
-int sync_point(om_handle* h, int kind) {
-  OM_LAUNCH(h, k_sync, 1, 32, view_of(shared_of(h)), h->ds, kind);
+int sync_point(om_handle* h, int kind, cudaGraphConditionalHandle handle = 0) {
+  OM_LAUNCH(h, k_sync, 1, 32, view_of(shared_of(h)), h->ds, kind, handle);
   CUDA_TRY(cudaGetLastError());
   return OM_OK;
 }
 
-// select + flip + twin patch with the meetings the single-GPU order gets from kernel
-// boundaries; ends with the reduced counts of the round
-int flips_with_meetings(om_handle* h) {
-  OM_TRY(sync_point(h, SYNC_BARRIER));  // every mark of the check is written
-  OM_TRY(om_pl_launch_flips_part(h, 0));
-  OM_TRY(sync_point(h, SYNC_BARRIER));  // every cell has made its choice
+// One flip round over all GPUs: the flips of the last check, the twin patch and the check of
+// the cells they touched, with the meetings the single-GPU order gets from kernel boundaries.
+// Ends in the meeting that sums candidates and flips and decides about the next round.
+int round_with_meetings(om_handle* h, const double* xin, cudaGraphConditionalHandle inner) {
   OM_TRY(om_pl_launch_flips_part(h, 1));
   OM_TRY(sync_point(h, SYNC_BARRIER));  // every flip is recorded
   OM_TRY(om_pl_launch_flips_part(h, 2));
-  OM_TRY(sync_point(h, SYNC_ROUND));    // every twin is patched; candidates and flips summed
+  OM_TRY(sync_point(h, SYNC_BARRIER));  // every twin is patched
+  OM_TRY(om_pl_launch_round_check(h, xin));
+  OM_TRY(sync_point(h, SYNC_ROUND, inner));  // every mark of the check is written
   return OM_OK;
 }
 
@@ -461,9 +449,15 @@ int build_graph(om_handle* h, om_shared* sh, int which, double* A, double* B) {
   cudaGraph_t g = sh->graph[which];
   cudaGraphConditionalHandle outer;
   CU_TRY2(cudaGraphConditionalHandleCreate(&outer, g, 1u, cudaGraphCondAssignDefault));
+  // The ranks meet once before the loop: whatever they enqueued before (set-up, the flip pass
+  // of the start mesh) is complete everywhere.  Inside the loop the meeting that ends an
+  // iteration is also the one the next update waits for.
+  cudaGraphNode_t first;
+  OM_TRY(capture_into(h, cs, g, nullptr, 0, &first,
+                      [&]() -> int { return sync_point(h, SYNC_BARRIER); }));
   cudaGraphNode_t outer_node;
   cudaGraph_t body;
-  OM_TRY(add_cond(g, outer, cudaGraphCondTypeWhile, nullptr, 0, &outer_node, &body));
+  OM_TRY(add_cond(g, outer, cudaGraphCondTypeWhile, &first, 1, &outer_node, &body));
   cudaGraphNode_t last = nullptr;
   for (int half = 0; half < 2; half++) {
     const double* xin = half == 0 ? A : B;
@@ -472,9 +466,7 @@ int build_graph(om_handle* h, om_shared* sh, int which, double* A, double* B) {
     CU_TRY2(cudaGraphConditionalHandleCreate(&inner, body, 0u, cudaGraphCondAssignDefault));
     CU_TRY2(cudaGraphConditionalHandleCreate(&lazy, body, 0u, cudaGraphCondAssignDefault));
     CU_TRY2(cudaGraphConditionalHandleCreate(&exact, body, 0u, cudaGraphCondAssignDefault));
-    // the ranks meet before the update: the last iteration's points and rows are everywhere
     OM_TRY(capture_into(h, cs, body, last ? &last : nullptr, last ? 1 : 0, &last, [&]() -> int {
-      OM_TRY(sync_point(h, SYNC_BARRIER));
       OM_TRY(om_pl_launch_update_part(h, xin, xout, 0));
       OM_LAUNCH(h, k_sh_mode, 1, 1, (const DevScalars*)h->ds, lazy, exact);
       CUDA_TRY(cudaGetLastError());
@@ -491,30 +483,22 @@ int build_graph(om_handle* h, om_shared* sh, int which, double* A, double* B) {
     last = if_exact;
     OM_TRY(capture_into(h, cs, body, &last, 1, &last, [&]() -> int {
       OM_TRY(om_pl_launch_update_part(h, xin, xout, 3));  // k_post
-      OM_LAUNCH(h, k_sh_pass_begin, 1, 1, h->ds);
       OM_TRY(om_pl_launch_flags_check(h, xin));
-      OM_TRY(flips_with_meetings(h));
-      OM_LAUNCH(h, k_sh_round_end, 1, 1, h->ds, inner);
-      CUDA_TRY(cudaGetLastError());
+      OM_TRY(sync_point(h, SYNC_ROUND, inner));  // every mark of the check is written
       return (int)OM_OK;
     }));
     cudaGraphNode_t inner_node;
     cudaGraph_t rounds;
     OM_TRY(add_cond(body, inner, cudaGraphCondTypeWhile, &last, 1, &inner_node, &rounds));
-    OM_TRY(capture_into(h, cs, rounds, nullptr, 0, &unused, [&]() -> int {
-      OM_TRY(om_pl_launch_round_check(h, xin));
-      OM_TRY(flips_with_meetings(h));
-      OM_LAUNCH(h, k_sh_round_end, 1, 1, h->ds, inner);
-      CUDA_TRY(cudaGetLastError());
-      return (int)OM_OK;
-    }));
+    OM_TRY(capture_into(h, cs, rounds, nullptr, 0, &unused,
+                        [&]() -> int { return round_with_meetings(h, xin, inner); }));
     OM_TRY(capture_into(h, cs, body, &inner_node, 1, &last, [&]() -> int {
       OM_TRY(om_pl_launch_tail(h, xin, xout));  // ring rows + recomputation of touched vertices
-      OM_TRY(sync_point(h, SYNC_BARRIER));      // every new point and |diff|^2 is written
+      // the rank that flipped an edge recomputes its four vertices, whoever owns them: the
+      // owners reduce their |diff|^2 only after everybody is done
+      OM_TRY(sync_point(h, SYNC_BARRIER));
       OM_TRY(om_launch_reduce_stats(h));
-      OM_TRY(sync_point(h, SYNC_STATS));
-      OM_LAUNCH(h, k_sh_iter_end, 1, 1, h->ds, outer);
-      CUDA_TRY(cudaGetLastError());
+      OM_TRY(sync_point(h, SYNC_STATS, outer));
       return (int)OM_OK;
     }));
   }
@@ -661,7 +645,6 @@ int om_shared_begin(om_handle* full, int rank, int world, om_handle** out, int32
   add_array(sh, (void**)&h->cells, full->cells, 16, true);
   add_array(sh, (void**)&h->adj, full->adj, 16, true);
   add_array(sh, (void**)&h->adj_tmp, full->adj_tmp, 16, true);
-  add_array(sh, (void**)&h->best, full->best, 1, true);
   add_array(sh, (void**)&h->cand_epoch, full->cand_epoch, 4, true);
   add_array(sh, (void**)&h->work_epoch, full->work_epoch, 4, true);
   add_array(sh, (void**)&h->flip_epoch, full->flip_epoch, 4, true);
