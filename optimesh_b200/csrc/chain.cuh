@@ -118,6 +118,7 @@ struct Chain {
   // limiter
   double rn, rd;          // EXACT: 2A and perimeter of the cell with the smallest inradius
   int minq_hi;            // lazy bound: min over the cells of hi(V4) - hi(max L)
+  int min_v4_hi;          // smallest high word of V4 (degenerate cell: below that of 2^-1022)
   // current spoke (the second spoke of the last cell) and what that cell leaves for it
   Vec<D> dq;
   double Lq, lenq;
@@ -138,6 +139,7 @@ struct Chain {
     rn = INFINITY;
     rd = 1.0;
     minq_hi = 0x7fffffff;
+    min_v4_hi = 0x7fffffff;
     t1p = s1p = t2_0 = s2_0 = 0.0;
     lenq = 0.0;
     flags = 0u;
@@ -179,13 +181,12 @@ struct Chain {
         }
       }
       if (CHECK && interior) {
-        // s = ce + ce' < 0  <=>  cH > 0; everything within rounding of it is kept (sign bit
-        // clear also catches +0 and NaN); the flip pass decides on the exact s.
-        // cH >= 0, or so small against its two terms (2^-30) that rounding could hide a
-        // positive value: exponent fields compared as integers
-        const int hc = __double2hiint(cH);
-        const int em = max(__double2hiint(t2) & 0x7ff00000, __double2hiint(t1) & 0x7ff00000);
-        if (hc >= 0 || (hc & 0x7ff00000) + (30 << 20) < em) flags |= 1u << bit;
+        // s = ce + ce' < 0  <=>  cH > 0.  Everything above -2^-20 is kept: as an unsigned
+        // integer the high word of such a value (positive, +-0, or negative and tiny) is at
+        // most that of -2^-20 -- ONE compare.  The rounding error of the sum is below
+        // 2^-49 max|T|, far inside the margin for |T| < 2^29; cells beyond that have named
+        // their spokes in cell().  The flip pass decides on the exact s.
+        if ((unsigned)__double2hiint(cH) <= 0xBEB00000u) flags |= 1u << bit;
       }
     }
   }
@@ -195,14 +196,16 @@ struct Chain {
   // spokes: (t2, s2) to the current one, (t1, s1) to dn.
   __device__ __forceinline__ void cell(const Vec<D>& dn, double Ln, double lenn, bool bary,
                                        double& t1, double& t2, double& s1, double& s2,
-                                       unsigned& mflags) {
-    mflags = 0u;
+                                       int bit_cur, int bit_next) {
+    unsigned mflags = 0u;  // bit 0: the current spoke, bit 1: dn (set on the rare paths only)
     const double c = vdot<D>(dq, dn);
     const double cc = c * c;
     const double V4 = fma(Lq, Ln, -cc);
-    // a degenerate cell raises the error and the step is abandoned by the host: no need to
-    // keep its garbage (NaN at worst) out of the sums
-    if (!pos_normal(V4)) err |= OM_DEV_DEGENERATE;
+    // a degenerate cell (V4 negative, zero or subnormal) raises the error and the step is
+    // abandoned by the host: no need to keep its garbage out of the sums.  The smallest high
+    // word is tracked (one instruction) and looked at once per vertex, together with
+    // non-finite input, which shows up in |d|^2 (finite()).
+    min_v4_hi = min(min_v4_hi, __double2hiint(V4));
     const double rs = fast_rsqrt(V4);  // 1 / (2A)
     if (EXACT) {
       // inradius 2A / (l0 + l1 + l2), compared as fractions (no division per cell)
@@ -223,24 +226,41 @@ struct Chain {
     }
     if (NEED_T) {
       const double T1 = (c - Lq) * rs, T2 = (c - Ln) * rs;  // 2 t: angles at n_q, n_{q+1}
+      // Fused Delaunay check, part 1: cH = t2 + t1 of a spoke is compared with an ABSOLUTE
+      // threshold (finish_spoke), which covers the rounding of the sum as long as |T| < 2^29.
+      // A cell with a larger |T| (an angle below 4e-9 rad: T = -cot is hugely negative, its
+      // high word the largest as an unsigned integer) names both its spokes itself.
+      bool rare = false;
+      if (CHECK)
+        rare = max((unsigned)__double2hiint(T1), (unsigned)__double2hiint(T2)) >= 0xC1C00000u;
       if (LLOYD_LIKE) {
         // cell masked (an angle > 135 deg): some t > 1/2, i.e. some T > 1.  T0 = -c rs > 1
-        // <=> c < 0 and c^2 > V4; bit patterns of positive doubles order like integers, so all
-        // three tests run on the integer pipe.  A masked cell gives nothing to its spokes:
-        // with t1 = t2 = 0 every product below is 0 -- selects, no branch, so that the
-        // compiler can overlap the rsqrt chain of the next cell with the sums of this one.
-        const long long one = 0x3ff0000000000000ll;
-        const bool m0 = (__double2hiint(c) < 0) & (__double_as_longlong(cc) > __double_as_longlong(V4));
-        const bool m1 = __double_as_longlong(T1) > one, m2 = __double_as_longlong(T2) > one;
-        const bool masked = m0 | m1 | m2;
-        // Fused Delaunay check: an edge can only violate the criterion if one of its two
-        // opposite angles is obtuse.  A masked cell hides its t from the sums below, so it
-        // names the spoke opposite its > 135 deg angle itself (the angle at n_{q+1} faces the
-        // current spoke, the one at n_q faces dn); its two small angles (< 45 deg together)
-        // cannot make their edges violate it unless the cell across does the same.
-        mflags = (m2 ? 1u : 0u) | (m1 ? 2u : 0u);
-        t1 = masked ? 0.0 : T1;
-        t2 = masked ? 0.0 : T2;
+        // <=> c < 0 and c^2 > V4.  Masked cells are rare, the three exact tests are not cheap
+        // (64-bit integer compares: bit patterns of positive doubles order like integers), so
+        // they sit behind a pre-test on the high words that is false for almost every cell:
+        // 5 instructions instead of 17 on the issue-bound path.  A masked cell gives nothing
+        // to its spokes: with t1 = t2 = 0 every product below is 0.
+        rare |= max(__double2hiint(T1), __double2hiint(T2)) >= 0x3ff00000;
+        rare |= (__double2hiint(c) < 0) & (__double2hiint(cc) >= __double2hiint(V4));
+        t1 = T1;
+        t2 = T2;
+        if (rare) {
+          const long long one = 0x3ff0000000000000ll;
+          const bool m0 =
+              (__double2hiint(c) < 0) & (__double_as_longlong(cc) > __double_as_longlong(V4));
+          const bool m1 = __double_as_longlong(T1) > one, m2 = __double_as_longlong(T2) > one;
+          // Fused Delaunay check, part 2: an edge can only violate the criterion if one of
+          // its two opposite angles is obtuse.  A masked cell hides its t from the sums below,
+          // so it names the spoke opposite its > 135 deg angle itself (the angle at n_{q+1}
+          // faces the current spoke, the one at n_q faces dn); its two small angles (< 45 deg
+          // together) cannot make their edges violate it unless the cell across does the same.
+          mflags = (m2 ? 1u : 0u) | (m1 ? 2u : 0u);
+          if (CHECK &&
+              max((unsigned)__double2hiint(T1), (unsigned)__double2hiint(T2)) >= 0xC1C00000u)
+            mflags = 3u;
+          if (m0 | m1 | m2) t1 = t2 = 0.0;
+          if (CHECK) flags |= ((mflags & 1u) << bit_cur) | ((mflags >> 1) << bit_next);
+        }
         const double w1 = Ln * t1, w2 = Lq * t2;
         const double uu = rs * (w1 + w2);
         s2 = fma(-uu, w1, w2);
@@ -257,16 +277,19 @@ struct Chain {
         }
         t1 = T1;
         t2 = T2;
+        if (rare) flags |= (1u << bit_cur) | (1u << bit_next);
       } else if (CPT) {
         const double A2 = V4 * rs;
         W += A2;
         s1 = s2 = A2;
         t1 = T1;
         t2 = T2;
+        if (rare) flags |= (1u << bit_cur) | (1u << bit_next);
       } else {
         s1 = s2 = 0.0;
         t1 = T1;
         t2 = T2;
+        if (rare) flags |= (1u << bit_cur) | (1u << bit_next);
       }
     } else if (CPT) {
       const double A2 = V4 * rs;
@@ -283,10 +306,8 @@ struct Chain {
   __device__ __forceinline__ void first(const Vec<D>& P, bool bary, bool first_spoke_interior) {
     Vec<D> dn;
     double Ln, lenn = 0.0, t1, t2, s1, s2;
-    unsigned mflags;
     spoke(P, dn, Ln, lenn);
-    cell(dn, Ln, lenn, bary, t1, t2, s1, s2, mflags);
-    if (CHECK) flags |= mflags;
+    cell(dn, Ln, lenn, bary, t1, t2, s1, s2, 0, 1);
     t2_0 = t2;
     s2_0 = s2;
     if (!first_spoke_interior) finish_spoke(dq, Lq, t2, s2, 0.0, 0.0, 0, false);
@@ -302,10 +323,8 @@ struct Chain {
   __device__ __forceinline__ void next(const Vec<D>& P, bool bary) {
     Vec<D> dn;
     double Ln, lenn = 0.0, t1, t2, s1, s2;
-    unsigned mflags;
     spoke(P, dn, Ln, lenn);
-    cell(dn, Ln, lenn, bary, t1, t2, s1, s2, mflags);
-    if (CHECK) flags |= mflags << q;
+    cell(dn, Ln, lenn, bary, t1, t2, s1, s2, q, q + 1);
     finish_spoke(dq, Lq, t2, s2, t1p, s1p, q, true);
     t1p = t1;
     s1p = s1;
@@ -319,10 +338,8 @@ struct Chain {
   __device__ __forceinline__ void close(const Vec<D>& P, bool bary) {
     Vec<D> dn;
     double Ln, lenn = 0.0, t1, t2, s1, s2;
-    unsigned mflags;
     spoke(P, dn, Ln, lenn);
-    cell(dn, Ln, lenn, bary, t1, t2, s1, s2, mflags);
-    if (CHECK) flags |= ((mflags & 1u) << q) | (mflags >> 1);
+    cell(dn, Ln, lenn, bary, t1, t2, s1, s2, q, 0);
     finish_spoke(dq, Lq, t2, s2, t1p, s1p, q, true);
     finish_spoke(dn, Ln, t2_0, s2_0, t1, s1, 0, true);
     q++;
@@ -347,6 +364,15 @@ struct Chain {
 #pragma unroll
     for (int k = 0; k < D; k++) d.v[k] = NUM.v[k] * inv;
     return true;
+  }
+
+  // |d|^2 of the relaxed update must be a finite number (non-finite coordinates, overflow)
+  __device__ __forceinline__ void finite(double diff2) {
+    if ((__double2hiint(diff2) & 0x7ff00000) == 0x7ff00000) err |= OM_DEV_DEGENERATE;
+  }
+  // OM_DEV_* bits of the star (read once per vertex, after the last cell)
+  __device__ __forceinline__ int error() const {
+    return err | (min_v4_hi < 0x00100000 ? (int)OM_DEV_DEGENERATE : 0);
   }
 
   // lazy limiter: true if |d|^2 = diff2 provably stays below (r_in / 2)^2 for every cell

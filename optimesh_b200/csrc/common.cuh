@@ -64,7 +64,7 @@ struct DevScalars {
   // ---- pipelined loop (loop.cu): everything the host would decide between two steps
   int halt;        // 0 running, 1 final step reached, 3 device error (odd: stopped);
                    // 4 flush: only the flip pass of the last points is still to run (shared.cu)
-  int mode_exact;  // the next point update tracks the exact inradius
+  int mode_exact;  // limiter variant of the next point update (om_limiter_mode)
   int pl_go;       // another flip round follows (set by k_pl_round_end)
   int cap_hit;     // a flip pass ran out of rounds with flagged edges left
   int max_rounds;  // rounds a flip pass may take
@@ -84,6 +84,24 @@ struct DevScalars {
   int sync_dead;                    // a meeting timed out
   int pl_round;                     // flip rounds executed in the current pass (loop.cu)
 };
+
+// Limiter variant of the ring kernel, chosen from the share of vertices the PREVIOUS update
+// limited.  The lazy variant proves "not limited" with a division-free bound; about 1.3 x the
+// limited vertices fail it and need the exact smallest inradius.
+//   0 lazy, failures evaluated in the kernel (a second pass over the staged ring, +70 % for
+//     every warp with at least one such lane): best below 2 % -- fewer than half of the warps;
+//   2 lazy, failures handed to k_post (compacted, evaluated from their ring rows by full
+//     warps): best in between;
+//   1 exact everywhere (+45 % for every warp): best above 12 %, e.g. the first steps on a fresh
+//     mesh, where most vertices are limited.
+// Every variant gives a vertex the same bits.
+__host__ __device__ inline int om_limiter_mode(bool limiter_on, long long limited,
+                                               long long n_free) {
+  if (!limiter_on) return 0;
+  if (8ll * limited > n_free) return 1;
+  if (50ll * limited > n_free) return 2;
+  return 0;
+}
 
 // After the check of a flip round: do its flips run?  `cand` = edges the check flagged,
 // `flips` = flips of the pass so far (both over all GPUs when there are several).  A round

@@ -56,13 +56,8 @@ __global__ void k_pl_iter_end(DevScalars* ds, cudaGraphConditionalHandle handle,
     ds->total_flips += ds->n_flips;
     ds->total_rounds += ds->n_rounds;
     ds->total_limited += (long long)ds->n_limited;
-    // The lazy variant evaluates the limiter exactly, in a second pass over the ring, for the
-    // lanes whose division-free bound fails -- about 1.3 x the limited vertices.  A warp pays
-    // for that pass (+70 %) as soon as one of its 32 lanes needs it; the exact variant costs
-    // every warp +45 %.  Break-even: one warp in two affected, i.e. 2 % of the vertices
-    // limited.  Either variant gives a vertex the same bits.
     ds->total_deferred += ds->n_deferred;
-    ds->mode_exact = (ds->limiter_on && 50ll * (long long)ds->n_limited > ds->n_free) ? 1 : 0;
+    ds->mode_exact = om_limiter_mode(ds->limiter_on != 0, (long long)ds->n_limited, ds->n_free);
     double md;
     memcpy(&md, &ds->max_diff2_bits, 8);
     if (ds->err)
@@ -77,8 +72,8 @@ __global__ void k_pl_iter_end(DevScalars* ds, cudaGraphConditionalHandle handle,
 __global__ void k_pl_mode(const DevScalars* ds, cudaGraphConditionalHandle lazy,
                           cudaGraphConditionalHandle exact) {
   const bool run = !(ds->halt & 1);
-  cudaGraphSetConditional(lazy, run && !ds->mode_exact ? 1u : 0u);
-  cudaGraphSetConditional(exact, run && ds->mode_exact ? 1u : 0u);
+  cudaGraphSetConditional(lazy, run && ds->mode_exact != 1 ? 1u : 0u);
+  cudaGraphSetConditional(exact, run && ds->mode_exact == 1 ? 1u : 0u);
 }
 
 struct PlGraph {
@@ -259,14 +254,14 @@ void free_graph(PlGraph& g) {
 }
 
 // the same loop driven from the stream: one scalar readback per flip round and per step
-int run_stream(om_handle* h, double* A, double* B, bool mode_exact) {
+int run_stream(om_handle* h, double* A, double* B, int mode) {
   const bool timed = h->timing;
   for (int64_t it = 0;; it++) {
     const double* xin = (it & 1) ? B : A;
     double* xout = (it & 1) ? A : B;
     OM_TRY(om_pl_launch_update_part(h, xin, xout, 0));
     if (timed) cudaEventRecord(h->ev[0], h->stream);
-    OM_TRY(om_pl_launch_update_part(h, xin, xout, mode_exact ? 2 : 1));
+    OM_TRY(om_pl_launch_update_part(h, xin, xout, mode == 1 ? 2 : 1));
     if (timed) cudaEventRecord(h->ev[1], h->stream);
     OM_TRY(enqueue_head_rest(h, xin, xout, 0ull, 0));
     while (true) {
@@ -284,7 +279,7 @@ int run_stream(om_handle* h, double* A, double* B, bool mode_exact) {
     OM_TRY(enqueue_tail(h, xin, xout, 0ull, 0));
     OM_TRY(om_fetch_scalars(h));
     if (h->hs->halt) break;
-    mode_exact = h->hs->mode_exact != 0;
+    mode = h->hs->mode_exact;
   }
   return OM_OK;
 }
@@ -345,7 +340,7 @@ int om_run_pipelined(om_handle* h, double tol, int64_t max_num_steps, int64_t* s
   int32_t nr = 0, cap = 0;
   if (!h->delaunay_clean) OM_TRY(om_flip_impl(h, 0.0, 100, &nf, &nr, &cap));
   h->delaunay_clean = false;  // the points are about to move
-  const int mode_exact = (h->limiter && h->limited_frac > 0.02) ? 1 : 0;
+  const int mode_exact = om_limiter_mode(h->limiter != 0, (long long)(h->limited_frac * 1.0e6), 1000000);
   OM_LAUNCH(h, k_pl_init, 1, 1, h->ds, (long long)max_num_steps, tol * tol, mode_exact,
             (long long)h->N, h->limiter, 100);
   CUDA_TRY(cudaGetLastError());
@@ -353,7 +348,7 @@ int om_run_pipelined(om_handle* h, double tol, int64_t max_num_steps, int64_t* s
   double* B = h->xnew;
   static const bool no_graph = getenv("OM_NO_GRAPH") != nullptr;
   if (no_graph || h->timing) {
-    OM_TRY(run_stream(h, A, B, mode_exact != 0));
+    OM_TRY(run_stream(h, A, B, mode_exact));
   } else {
     PlGraph* g = nullptr;
     OM_TRY(get_graph(h, &g));

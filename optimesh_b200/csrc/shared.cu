@@ -283,7 +283,7 @@ __device__ void sh_iter_end(DevScalars* ds, cudaGraphConditionalHandle handle) {
     ds->total_deferred += (long long)ds->g_sum[1];
     ds->max_diff2_bits = ds->g_max[0];
     ds->n_limited = (unsigned long long)limited;
-    ds->mode_exact = (ds->limiter_on && 50ll * limited > ds->n_free) ? 1 : 0;
+    ds->mode_exact = om_limiter_mode(ds->limiter_on != 0, limited, ds->n_free);
     double md;
     memcpy(&md, &ds->g_max[0], 8);
     if (ds->err || ds->g_max[1])
@@ -299,8 +299,8 @@ __device__ void sh_iter_end(DevScalars* ds, cudaGraphConditionalHandle handle) {
 __global__ void k_sh_mode(const DevScalars* ds, cudaGraphConditionalHandle lazy,
                           cudaGraphConditionalHandle exact) {
   const bool run = !(ds->halt & 1);
-  cudaGraphSetConditional(lazy, run && !ds->mode_exact ? 1u : 0u);
-  cudaGraphSetConditional(exact, run && ds->mode_exact ? 1u : 0u);
+  cudaGraphSetConditional(lazy, run && ds->mode_exact != 1 ? 1u : 0u);
+  cudaGraphSetConditional(exact, run && ds->mode_exact == 1 ? 1u : 0u);
 }
 
 om_shared* shared_of(om_handle* h) { return (om_shared*)h->sh; }
@@ -771,7 +771,7 @@ int om_shared_run(om_handle* h, double tol, int64_t max_num_steps, int64_t* step
   cudaSetDevice(h->device);
   int which = -1;
   OM_TRY(graph_for(h, sh, h->x, h->xnew, &which));
-  const int mode_exact = (h->limiter && h->limited_frac > 0.02) ? 1 : 0;
+  const int mode_exact = om_limiter_mode(h->limiter != 0, (long long)(h->limited_frac * 1.0e6), 1000000);
   OM_LAUNCH(h, k_sh_init, 1, 1, h->ds, (long long)max_num_steps, tol * tol, mode_exact,
             (long long)h->N, h->limiter, 100);
   CUDA_TRY(cudaGetLastError());

@@ -186,6 +186,7 @@ struct StepParams {
   int force_walk;  // diagnostics (OM_NO_RINGS): every free vertex goes through k_post
   int prefetch_ahead;  // vertices between a block and the one that runs a wave later
   int gate;  // pipelined loop: return at once if the loop has halted / the other limiter mode is on
+  int mode;  // limiter variant (om_limiter_mode) when the host chose it (gate == 0)
   DevScalars* ds;
 };
 
@@ -201,7 +202,7 @@ __global__ void __launch_bounds__(OM_K1_BLOCK, (D == 2 ? (EXACT ? OM_K1_MINB_EXA
   constexpr int PER = (D == 2) ? 1 : 2;  // 16-byte pieces per vertex
   constexpr bool ODT = METHOD == OM_ODT_FIXED_POINT || METHOD == OM_ODT_DP_FP;
   __shared__ double2 ring_sm[OM_RING_W * PER * BLOCK];
-  if (p.gate && ((p.ds->halt & 1) || (p.ds->mode_exact != 0) != EXACT)) return;
+  if (p.gate && ((p.ds->halt & 1) || (p.ds->mode_exact == 1) != EXACT)) return;
   const int v = p.lo + (int)(blockIdx.x * BLOCK + threadIdx.x);
   if (v >= p.hi) return;
   const int4* rp = reinterpret_cast<const int4*>(p.ring + (size_t)OM_RING_W * v);
@@ -274,14 +275,19 @@ __global__ void __launch_bounds__(OM_K1_BLOCK, (D == 2 ? (EXACT ? OM_K1_MINB_EXA
 #pragma unroll
     for (int i = 0; i < D; i++) d.v[i] *= p.omega;
     diff2 = vdot<D>(d, d);
+    ch.finite(diff2);
     if (p.limiter) {
       if (EXACT) {
         limited = ch.limit(d, diff2);
       } else if (!ch.proves_unlimited(diff2)) {
-        // The division-free bound cannot rule the limiter out (a few % of the vertices once
-        // the mesh has settled): the smallest incident inradius is evaluated exactly here,
-        // from the ring still staged in shared memory, by the limiter-only chain -- the
-        // same cell code, hence the same bits, as the exact variant of this kernel.
+        // The division-free bound cannot rule the limiter out.  Many such vertices (mode 2):
+        // k_post takes them.  Few (a fraction of a percent once the mesh has settled): the
+        // smallest incident inradius is evaluated exactly here, from the ring still staged in
+        // shared memory, by the limiter-only chain -- the same cell code, hence the same bits,
+        // as the exact variant of this kernel.
+        if ((p.gate ? p.ds->mode_exact : p.mode) == 2) {
+          deferred = true;
+        } else {
         Chain<D, OM_CHAIN_LIMITER_ONLY, true, false> lim;
         lim.init(P0);
         lim.start(ld_ring(0));
@@ -290,6 +296,7 @@ __global__ void __launch_bounds__(OM_K1_BLOCK, (D == 2 ? (EXACT ? OM_K1_MINB_EXA
         for (int j = 2; j < k; j++) lim.next(ld_ring(j), false);
         lim.close(ld_ring(0), false);
         limited = lim.limit(d, diff2);
+        }
       }
     }
 #pragma unroll
@@ -301,7 +308,7 @@ __global__ void __launch_bounds__(OM_K1_BLOCK, (D == 2 ? (EXACT ? OM_K1_MINB_EXA
   }
   const unsigned f = (CHECK ? (ch.flags & VF_SPOKES) : 0u) | (deferred ? VF_DEFER : 0u);
   if (f) p.vflags[v] = (unsigned short)f;
-  if (ch.err) atomicOr(&p.ds->err, ch.err);
+  if (const int e2 = ch.error()) atomicOr(&p.ds->err, e2);
 }
 
 // ------------------------------------------------------------------ star walk
@@ -410,13 +417,15 @@ __device__ __forceinline__ void walk_vertex(const StepParams& p, int v, int& err
         ch.next(ld_point<D>(p.x, newid), bary);
         kexit = 3 - jn - kn;
       }
-      err |= ch.err;
+      err |= ch.error();
       Vec<D> d;
       if (ch.target_offset(d) && !(pinned && !TARGET)) {
         if (!TARGET) {
 #pragma unroll
           for (int i = 0; i < D; i++) d.v[i] *= p.omega;
           diff2 = vdot<D>(d, d);
+          ch.finite(diff2);
+          err |= ch.error();
           if (p.limiter) limited = ch.limit(d, diff2);
         }
 #pragma unroll
@@ -459,7 +468,7 @@ __device__ __forceinline__ bool ring_vertex(const StepParams& p, int v, int& err
   for (int j = 2; j < OM_RING_W; j++)
     if (j < k) ch.next(R[j], odt_bary && ((bcells >> (j - 1)) & 1u));
   ch.close(R[0], odt_bary && ((bcells >> (k - 1)) & 1u));
-  err |= ch.err;
+  err |= ch.error();
   Vec<D> d;
   Vec<D> out = P0;
   double diff2 = 0.0;
@@ -468,6 +477,8 @@ __device__ __forceinline__ bool ring_vertex(const StepParams& p, int v, int& err
 #pragma unroll
     for (int i = 0; i < D; i++) d.v[i] *= p.omega;
     diff2 = vdot<D>(d, d);
+    ch.finite(diff2);
+    err |= ch.error();
     if (p.limiter) limited = ch.limit(d, diff2);
 #pragma unroll
     for (int i = 0; i < D; i++) out.v[i] = P0.v[i] + d.v[i];
@@ -708,7 +719,7 @@ __device__ __forceinline__ void star_limiter(const StepParams& p, int v, int c0,
     cur = cn;
     kexit = 3 - jn - kn;
   }
-  err |= ch.err;
+  err |= ch.error();
 }
 
 // x <- x + omega (target - x), limited: the driver-loop tail for methods whose target
@@ -861,6 +872,7 @@ StepParams make_params(om_handle* h, double* out) {
     p.prefetch_ahead = waves * OM_K1_BLOCK;
   }
   p.gate = 0;
+  p.mode = 0;
   p.ds = h->ds;
   return p;
 }
@@ -904,9 +916,9 @@ int om_launch_point_update(om_handle* h, double* out, bool check) {
   }
   // the lazy limiter pays off once few vertices are limited (the previous step tells; see
   // k_pl_iter_end in loop.cu for the break-even)
-  const bool exact = h->limiter && h->limited_frac > 0.02;
+  p.mode = om_limiter_mode(h->limiter != 0, (long long)(h->limited_frac * 1.0e6), 1000000);
   if (h->timing) cudaEventRecord(h->ev[0], h->stream);
-  OM_TRY(launch_step(h, p, check ? 1 : 0, exact));
+  OM_TRY(launch_step(h, p, check ? 1 : 0, p.mode == 1));
   if (h->timing) {
     cudaEventRecord(h->ev[1], h->stream);
     h->ev_pending = true;

@@ -96,6 +96,11 @@ def chain_vertex(P0, R, method, omega=1.0, bary=None):
         m0, m1, m2 = -c, c - L[q], c - L[r]
         T0, T1, T2 = m0 * rs, m1 * rs, m2 * rs
         t1raw[q], t2raw[q] = T1, T2
+        # a cell with |T| >= 2^29 (T hugely negative: an angle below 4e-9 rad) names both its
+        # spokes: the absolute threshold of the check below does not cover its rounding
+        if min(T1, T2) <= -2.0 ** 29:
+            mflag.add(q)
+            mflag.add(r)
         if method in ("lloyd", "cvt-block-diagonal"):
             if max(T0, T1, T2) > 1.0:
                 masked[q] = True
@@ -133,8 +138,9 @@ def chain_vertex(P0, R, method, omega=1.0, bary=None):
             W += L[q] * cH
             H += cH * np.outer(d[q], d[q])
         NUM += cN * d[q]
-        # the kernel sees the masked (zeroed) t: conservative by the argument in chain.cuh
-        if q in mflag or cH > -1e-9 * (abs(t2[q]) + abs(t1[p])):
+        # the kernel sees the masked (zeroed) t: conservative by the argument in chain.cuh;
+        # kept: cH >= 0, or negative with a high word of at most that of -2^-20
+        if q in mflag or cH >= 0.0 or _hi(-cH) <= 0x3EB00000:
             flags.append(q)
     if W == 0.0:
         off = np.zeros(dim)
