@@ -529,6 +529,54 @@ def optimize_points_cells_sharded(points, cells, method: str, tol: float, max_nu
         return dm.points, dm.cells(cells.dtype)
 
 
+def exchange_fds(mine, group=None):
+    """All-to-all of file descriptors between the ranks of one box: every rank passes its list
+    `mine` (same length everywhere) to every other rank over Unix datagram sockets with
+    SCM_RIGHTS and gets {rank: [descriptors]} back (its own list under its own rank; the
+    received descriptors are new ones in this process: the caller closes them).  The host side
+    of SharedMesh: the descriptors are CUDA memory handles (cuMemExportToShareableHandle)."""
+    import array
+    import socket
+    import struct
+
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    mine = [int(fd) for fd in mine]
+    n = len(mine)
+    tag = os.environ.get("MASTER_PORT", "0")
+    path = lambda r: f"/tmp/om_shared_{tag}_{os.getuid()}_{r}"  # noqa: E731
+    sock = socket.socket(socket.AF_UNIX, socket.SOCK_DGRAM)
+    try:
+        os.unlink(path(rank))
+    except FileNotFoundError:
+        pass
+    sock.bind(path(rank))
+    got = {rank: mine}
+    try:
+        dist.barrier(group)  # every socket is bound
+        for r in range(world):
+            if r != rank:
+                # (socket.send_fds ignores its address argument in CPython 3.12)
+                sock.sendmsg([struct.pack("i", rank)],
+                             [(socket.SOL_SOCKET, socket.SCM_RIGHTS, array.array("i", mine))],
+                             0, path(r))
+        sock.settimeout(120.0)
+        while len(got) < world:
+            msg, rfds, _, _ = socket.recv_fds(sock, 16, max(n, 1))
+            if len(rfds) != n:
+                raise RuntimeError(f"expected {n} descriptors from a peer, got {len(rfds)}")
+            got[struct.unpack("i", msg[:4])[0]] = list(rfds)
+        dist.barrier(group)  # everybody has everything: the sockets may go
+    finally:
+        sock.close()
+        try:
+            os.unlink(path(rank))
+        except FileNotFoundError:
+            pass
+    return got
+
+
 # ---------------------------------------------------------------------------------------------
 # One mesh in one address space over the GPUs of a box (csrc/shared.cu): memory per rank ~ 1/N,
 # no halo buffers, no collective on the data path; the ranks meet on the device.
@@ -540,10 +588,7 @@ class SharedMesh(DeviceMesh):
 
     @classmethod
     def from_complete(cls, full: DeviceMesh, group=None, flip_first: bool = True):
-        import array
         import ctypes as C
-        import socket
-        import struct
 
         import torch.distributed as dist
 
@@ -560,27 +605,8 @@ class SharedMesh(DeviceMesh):
         check(lib.om_shared_begin(full._h, rank, world, C.byref(h), fds, C.byref(n)))
         n = n.value
         mine = [int(fds[i]) for i in range(n)]
-        # every rank passes its descriptors to every other rank (SCM_RIGHTS, Unix datagrams)
-        tag = os.environ.get("MASTER_PORT", "0")
-        path = lambda r: f"/tmp/om_shared_{tag}_{os.getuid()}_{r}"  # noqa: E731
-        sock = socket.socket(socket.AF_UNIX, socket.SOCK_DGRAM)
+        got = exchange_fds(mine, group)
         try:
-            os.unlink(path(rank))
-        except FileNotFoundError:
-            pass
-        sock.bind(path(rank))
-        got = {rank: mine}
-        try:
-            dist.barrier(group)  # every socket is bound
-            for r in range(world):
-                if r != rank:
-                    # (socket.send_fds ignores its address argument in CPython 3.12)
-                    sock.sendmsg([struct.pack("i", rank)],
-                                 [(socket.SOL_SOCKET, socket.SCM_RIGHTS, array.array("i", mine))],
-                                 0, path(r))
-            while len(got) < world:
-                msg, rfds, _, _ = socket.recv_fds(sock, 16, n)
-                got[struct.unpack("i", msg[:4])[0]] = list(rfds)
             flat = (C.c_int32 * (world * n))()
             for r in range(world):
                 for i in range(n):
@@ -591,11 +617,6 @@ class SharedMesh(DeviceMesh):
                 if r != rank:
                     for fd in lst:
                         os.close(fd)
-            sock.close()
-            try:
-                os.unlink(path(rank))
-            except FileNotFoundError:
-                pass
         dist.barrier(group)  # every rank has copied its share: the complete handles may go
         self = cls.__new__(cls)
         self.n, self.dim, self.c = full.n, full.dim, full.c

@@ -117,3 +117,42 @@ def test_ranges_cover_everything():
             assert r[0][0] == 0 and r[-1][1] == n
             assert all(r[k][1] == r[k + 1][0] for k in range(world - 1))
             assert chunk_of(n, world) * world <= n + world
+
+
+def _fd_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from optimesh_b200.dist import exchange_fds
+
+    # three "memory handles" per rank: anonymous files that name their owner and slot
+    mine = []
+    for i in range(3):
+        fd = os.memfd_create(f"om_test_{rank}_{i}")
+        os.write(fd, f"rank {rank} slot {i}".encode())
+        mine.append(fd)
+    got = exchange_fds(mine, None)
+    ok = sorted(got) == list(range(world)) and got[rank] == mine
+    for r, fds in got.items():
+        for i, fd in enumerate(fds):
+            ok = ok and os.pread(fd, 64, 0) == f"rank {r} slot {i}".encode()
+            if r != rank:
+                ok = ok and fd not in mine  # a new descriptor of this process
+                os.close(fd)
+    for fd in mine:
+        os.close(fd)
+    with open(os.path.join(out_dir, f"ok{rank}"), "w") as f:
+        f.write("1" if ok else "0")
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_shared_mesh_descriptor_exchange(tmp_path, world):
+    """Host side of the shared-address-space loop (dist.SharedMesh, what `bench.py --gpus N`
+    runs): every rank hands the descriptors of its memory chunks to every other rank.  The
+    device side needs GPUs: tests/run_shared_gpu.py (N ranks, bit-identity with one GPU) and
+    tests/test_gpu_parity.py::test_shared_address_space_loop_world_of_one."""
+    port = 29500 + ((os.getpid() + 7 * world) % 2000)
+    mp.spawn(_fd_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert (tmp_path / f"ok{r}").read_text() == "1"

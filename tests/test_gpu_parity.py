@@ -337,6 +337,30 @@ def test_cpt_linear_solve_vs_spsolve(ob, G):
     assert np.array_equal(got[bnd], pts[bnd])
 
 
+def test_cpt_linear_solve_multigrid_vs_spsolve(ob, G):
+    """Above 20,000 vertices the solve is preconditioned by aggregation multigrid (pcg.cu):
+    same answer as the sparse direct solve, a mesh-independent-ish iteration count, and the
+    same bits from run to run (integer-valued Galerkin weights, fixed summation orders)."""
+    pts, cells = G.disk(900, 5)  # random (Qhull)
+    assert pts.shape[0] > 60000
+    ref = oracle.get_new_points(OMesh(pts, cells), "cpt-linear-solve")
+    runs = []
+    for _ in range(2):
+        with ob.DeviceMesh(pts, cells) as dm:
+            its, res = dm.solve_graph_laplacian(1e-12, 2000)
+            runs.append((its, dm.points))
+    its, got = runs[0]
+    assert res <= 1e-12 and 0 < its <= 120, its
+    assert rel_err(got, ref) <= 1e-9
+    bnd = OMesh(pts, cells).is_boundary_point
+    assert np.array_equal(got[bnd], pts[bnd])
+    assert runs[1][0] == its and runs[1][1].tobytes() == got.tobytes()
+    # the loop with the solve as its update (flips change the matrix between steps)
+    rp, rc = oracle.optimize_points_cells(pts, cells, "cpt-linear-solve", 0.0, 2)
+    gp, gc = ob.optimize_points_cells(pts, cells, "cpt-linear-solve", 0.0, 2)
+    assert np.array_equal(gc, rc) and rel_err(gp, rp) <= 1e-8
+
+
 # ------------------------------------------------------------------ properties, edge cases
 def test_bitwise_deterministic(ob, G):
     pts, cells = G.disk(100, 4)
