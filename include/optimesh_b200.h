@@ -141,6 +141,22 @@ int om_random_walk(om_handle* h, int rounds, uint64_t seed, double amplitude, in
  * positions, N x dim, caller numbering. */
 int om_new_points(om_handle* h, double* out_host);
 
+/* Device side of the reference's per-step hooks (README.md:146-149 boundary_step, :157-162
+ * generic implicit surfaces): the caller's code works on device memory between the phases of a
+ * step, nothing goes through the host.
+ *   om_targets_device      un-relaxed targets of the current method (what om_new_points
+ *                          returns) in a device buffer owned by the handle: internal numbering
+ *                          and layout, like om_device_ptrs' points (N x point_stride doubles);
+ *                          the caller may overwrite entries (boundary_step moves the targets
+ *                          of the boundary vertices);
+ *   om_update_from_targets x <- x + limiter(omega (target - x)) for EVERY vertex, boundary
+ *                          vertices included (the loop's semantics when boundary_step is
+ *                          given), statistics like om_update_points.  The flip pass and the
+ *                          projection are the caller's next calls. */
+int om_targets_device(om_handle* h, double** targets_dev);
+int om_update_from_targets(om_handle* h, const double* targets_dev, double tol,
+                           om_step_stats* out);
+
 /* cpt-linear-solve alone: solve the Dirichlet graph Laplacian for all coordinates and
  * overwrite the interior points with the solution. */
 int om_solve_graph_laplacian(om_handle* h, double rtol, int max_iter, int32_t* iters,

@@ -63,6 +63,8 @@ SIGNATURES = {
                                     _P(C.c_int64)]),
     "om_random_walk": (C.c_int, [_H, C.c_int, C.c_uint64, C.c_double, _P(C.c_int64)]),
     "om_new_points": (C.c_int, [_H, C.c_void_p]),
+    "om_targets_device": (C.c_int, [_H, _P(C.c_void_p)]),
+    "om_update_from_targets": (C.c_int, [_H, C.c_void_p, C.c_double, _P(StepStats)]),
     "om_solve_graph_laplacian": (C.c_int, [_H, C.c_double, C.c_int, _P(C.c_int32),
                                            _P(C.c_double)]),
     "om_stats": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -545,6 +545,7 @@ int om_destroy(om_handle* h) {
   om_free(h, h->nbr_idx);
   om_free(h, h->nbr_w);
   om_free(h, h->pcg_buf);
+  om_free(h, h->target_buf);
   om_free(h, h->ds);
   om_free(h, h->partials);
   if (h->hs) cudaFreeHost(h->hs);
@@ -726,6 +727,32 @@ int om_new_points(om_handle* h, double* out_host) {
   om_free(h, target);
   om_free(h, flat);
   return rc;
+}
+
+int om_targets_device(om_handle* h, double** targets_dev) {
+  OM_ENTER(h);
+  if (!targets_dev) {
+    om_set_error("om_targets_device: null output pointer");
+    return OM_ERR_ARG;
+  }
+  *targets_dev = nullptr;
+  if (h->N == 0) return OM_OK;
+  if (!h->target_buf)
+    CUDA_TRY(om_malloc(h, &h->target_buf, sizeof(double) * (h->N + OM_POINT_PAD) * h->PD));
+  OM_TRY(om_update_points_impl(h, 0.0, nullptr, true, h->target_buf));
+  *targets_dev = h->target_buf;
+  return OM_OK;
+}
+
+int om_update_from_targets(om_handle* h, const double* targets_dev, double tol,
+                           om_step_stats* out) {
+  OM_ENTER(h);
+  if (out) memset(out, 0, sizeof(*out));
+  if (!targets_dev && h->N > 0) {
+    om_set_error("om_update_from_targets: null targets");
+    return OM_ERR_ARG;
+  }
+  return om_update_from_targets_impl(h, targets_dev, tol, out);
 }
 
 int om_solve_graph_laplacian(om_handle* h, double rtol, int max_iter, int32_t* iters,

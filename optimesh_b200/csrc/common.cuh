@@ -169,6 +169,7 @@ struct om_handle {
   float* nbr_w = nullptr;    // nnz edge multiplicities
   int64_t nnz = 0;
   double* pcg_buf = nullptr; // 4 vectors of N*PD
+  double* target_buf = nullptr;  // N*PD: targets handed to the caller (om_targets_device)
   bool nbr_valid = false;
   // scalars
   DevScalars* ds = nullptr;  // device
@@ -277,6 +278,8 @@ int om_commit_points_impl(om_handle* h);
 int om_rebuild_rings(om_handle* h, bool all, bool device = false);
 int om_launch_point_update(om_handle* h, double* out, bool check);
 int om_launch_reduce_stats(om_handle* h);
+int om_update_from_targets_impl(om_handle* h, const double* targets_dev, double tol,
+                                om_step_stats* out);
 int om_launch_fixup(om_handle* h, double* out);
 // pipelined loop (loop.cu): one iteration = update (with the fused Delaunay check) from xin
 // into xout, flip pass on xin, recomputation of the vertices whose star changed

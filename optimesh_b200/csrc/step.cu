@@ -1076,6 +1076,95 @@ int om_update_points_impl(om_handle* h, double tol, om_step_stats* out, bool tar
   return OM_OK;
 }
 
+// ---- the update from caller-supplied targets (device side of the boundary_step hook)
+namespace {
+// per vertex: smallest inradius over its cells, as the bits of a non-negative double
+template <int D>
+__global__ void __launch_bounds__(256)
+    k_cell_inradius_min(const double* __restrict__ x, const int4* __restrict__ cells, int C,
+                        unsigned long long* __restrict__ minr) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const int4 cl = __ldg(cells + c);
+  const Vec<D> P0 = ld_point<D>(x, cl.x), P1 = ld_point<D>(x, cl.y), P2 = ld_point<D>(x, cl.z);
+  const Vec<D> e0 = vsub<D>(P2, P1), e1 = vsub<D>(P0, P2), e2 = vsub<D>(P1, P0);
+  const double l0 = sqrt(vdot<D>(e0, e0)), l1 = sqrt(vdot<D>(e1, e1)), l2 = sqrt(vdot<D>(e2, e2));
+  const double d12 = vdot<D>(e1, e2);
+  // |e1 x e2|^2 = |e1|^2 |e2|^2 - (e1.e2)^2 in any embedding dimension
+  const double area = 0.5 * sqrt(fmax(l1 * l1 * l2 * l2 - d12 * d12, 0.0));
+  const double r = 2.0 * area / (l0 + l1 + l2);
+  const unsigned long long b = (unsigned long long)__double_as_longlong(r);
+  atomicMin(minr + cl.x, b);  // (integer min of the bit patterns: order independent)
+  atomicMin(minr + cl.y, b);
+  atomicMin(minr + cl.z, b);
+}
+
+// x <- x + omega (target - x), limited to half the smallest incident inradius, for EVERY
+// vertex with a target (boundary vertices included: their targets come from the caller)
+template <int D>
+__global__ void __launch_bounds__(256)
+    k_relax_all(StepParams p, const double* __restrict__ target,
+                const unsigned long long* __restrict__ minr) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= p.N) return;
+  const Vec<D> P0 = ld_point<D>(p.x, v), T = ld_point<D>(target, v);
+  Vec<D> d;
+#pragma unroll
+  for (int k = 0; k < D; k++) d.v[k] = p.omega * (T.v[k] - P0.v[k]);
+  const double diff2 = vdot<D>(d, d);
+  bool limited = false;
+  if (p.limiter) {
+    const double limit = 0.5 * __longlong_as_double((long long)minr[v]);
+    const double length = sqrt(diff2);
+    if (length > limit) {
+      const double f = limit / length;
+#pragma unroll
+      for (int k = 0; k < D; k++) d.v[k] *= f;
+      limited = true;
+    }
+  }
+  Vec<D> out;
+#pragma unroll
+  for (int k = 0; k < D; k++) out.v[k] = P0.v[k] + d.v[k];
+  st_point<D>(p.xout, v, out);
+  p.diff2[v] = limited ? -diff2 : diff2;
+}
+}  // namespace
+
+int om_update_from_targets_impl(om_handle* h, const double* targets_dev, double tol,
+                                om_step_stats* out) {
+  if (h->N == 0) return OM_OK;
+  h->delaunay_clean = false;
+  OM_LAUNCH(h, k_reset_step_scalars, 1, 1, h->ds, 0);
+  unsigned long long* minr = nullptr;
+  CUDA_TRY(om_malloc(h, &minr, sizeof(unsigned long long) * h->N));
+  // +inf for vertices without a cell (0x7ff0... as four identical 16-bit halves is not
+  // possible: fill with the byte 0x7f -> 0x7f7f..., a huge finite double)
+  CUDA_TRY(cudaMemsetAsync(minr, 0x7f, sizeof(unsigned long long) * h->N, h->stream));
+  StepParams p = make_params(h, h->xnew);
+  if (h->C > 0) {
+    if (h->D == 2)
+      OM_LAUNCH(h, k_cell_inradius_min<2>, om_grid(h->C, 256), 256, h->x, h->cells, (int)h->C,
+                minr);
+    else
+      OM_LAUNCH(h, k_cell_inradius_min<3>, om_grid(h->C, 256), 256, h->x, h->cells, (int)h->C,
+                minr);
+  }
+  if (h->D == 2)
+    OM_LAUNCH(h, k_relax_all<2>, om_grid(h->N, 256), 256, p, targets_dev, minr);
+  else
+    OM_LAUNCH(h, k_relax_all<3>, om_grid(h->N, 256), 256, p, targets_dev, minr);
+  CUDA_TRY(cudaGetLastError());
+  om_free(h, minr);
+  OM_LAUNCH(h, k_reduce_stats, std::min(om_grid(h->N, 256 * 8), 148 * 8), 256, h->diff2, 0,
+            (int)h->N, h->ds, 0);
+  OM_TRY(om_fetch_scalars(h));
+  OM_TRY(om_check_dev_err(h));
+  std::swap(h->x, h->xnew);
+  om_step_stats_from_scalars(h, tol, out);
+  return OM_OK;
+}
+
 int om_random_move_impl(om_handle* h, uint64_t seed, int round, double amplitude) {
   if (h->N == 0) return OM_OK;
   if (h->D != 2) {

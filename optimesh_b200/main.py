@@ -36,6 +36,80 @@ def _project_host(dm: DeviceMesh, surface, tol: float, max_iter: int = 100):
         dm.points = x.T
 
 
+class _DeviceHooks:
+    """The per-step hooks on DEVICE memory: the user's callables get torch
+    CUDA tensors that alias the library's arrays, so a generic implicit surface
+    (README.md:157-162: ``f(x)``, ``grad(x)`` on ``(3, n)``) and a ``boundary_step`` callback
+    (README.md:146-149: ``(d, n_boundary)`` targets in, moved targets out) run between the
+    device kernels without a host round trip.  Opt-in (``device_callables=True`` or an
+    ``on_device = True`` attribute on the object): the callables must be written for
+    array-API style arguments (``x[0] ** 2``, ``-2 * x``, ``torch.sqrt`` ...), numpy functions
+    do not accept CUDA tensors.  The boundary targets arrive in the caller's vertex order."""
+
+    def __init__(self, dm: DeviceMesh, device: int):
+        import torch
+
+        from .dist import _DevPtr
+
+        self.torch, self._DevPtr = torch, _DevPtr
+        self.dm, self.dev = dm, torch.device("cuda", device)
+        self.n, self.dim = dm.n, dm.dim
+        _, _, perm_ptr, self.stride = dm.device_ptrs()
+        bnd = np.nonzero(dm.is_boundary_point)[0]  # caller ids, ascending
+        ids = torch.as_tensor(bnd, device=self.dev, dtype=torch.int64)
+        if perm_ptr:
+            perm = torch.as_tensor(_DevPtr(perm_ptr, (self.n,), "<i4"), device=self.dev).long()
+            inv = torch.empty(self.n, dtype=torch.int64, device=self.dev)
+            inv[perm] = torch.arange(self.n, device=self.dev)
+            ids = inv[ids]
+        self.bidx = ids  # internal ids of the boundary vertices, in the caller's order
+
+    def _view(self, ptr):
+        t = self.torch.as_tensor(self._DevPtr(ptr, (self.n, self.stride), "<f8"), device=self.dev)
+        return t[:, : self.dim]
+
+    def _fence(self):
+        # the library runs on its own stream, torch on its current one
+        self.dm.synchronize()
+
+    def update(self, omega: float, tol: float, boundary_step) -> dict:
+        torch = self.torch
+        ptr = self.dm.targets_device()
+        if self.bidx.numel():
+            self._fence()
+            T = self._view(ptr)
+            moved = boundary_step(T[self.bidx].T.contiguous())
+            if not torch.is_tensor(moved):
+                moved = torch.as_tensor(np.asarray(moved), device=self.dev)
+            if tuple(moved.shape) != (self.dim, self.bidx.numel()):
+                raise ValueError("boundary_step must return an array of the shape it was given")
+            T[self.bidx] = moved.T.to(torch.float64)
+            torch.cuda.current_stream(self.dev).synchronize()
+        return self.dm.update_from_targets(ptr, tol)
+
+    def project(self, surface, tol: float, max_iter: int = 100) -> int:
+        torch = self.torch
+        self._fence()
+        ptr = self.dm.device_ptrs()[0]
+        X = self._view(ptr)
+        sweeps = 0
+        for _ in range(max_iter):
+            x = X.T
+            fval = surface.f(x)
+            if not bool((fval.abs() <= tol).all()):
+                grad = surface.grad(x)
+                X -= (grad * (fval / (grad * grad).sum(0))).T
+                sweeps += 1
+            else:
+                break
+        torch.cuda.current_stream(self.dev).synchronize()
+        return sweeps
+
+
+def _wants_device(obj, flag) -> bool:
+    return obj is not None and (bool(flag) or bool(getattr(obj, "on_device", False)))
+
+
 def _half_min_inradius(x: np.ndarray, cells: np.ndarray) -> np.ndarray:
     """Per vertex: half of the smallest inradius over its cells (the loop's step limit)."""
     p0, p1, p2 = x[cells[:, 0]], x[cells[:, 1]], x[cells[:, 2]]
@@ -80,7 +154,8 @@ def _host_update(dm: DeviceMesh, omega: float, tol: float, boundary_step) -> dic
 def _run_loop(dm: DeviceMesh, method: str, tol: float, max_num_steps: int, omega: float = 1.0,
               verbose: bool = False, callback=None, step_filename_format=None,
               implicit_surface=None, implicit_surface_tol: float = 1.0e-10, boundary_step=None,
-              cells_dtype=None, log=None, odt_boundary_barycenters: bool = True):
+              cells_dtype=None, log=None, odt_boundary_barycenters: bool = True,
+              device_callables: bool = False, device: int = 0):
     if boundary_step is not None and not callable(boundary_step):
         raise TypeError("boundary_step must be callable: (d, n) array -> (d, n) array")
     if max_num_steps < 1:
@@ -97,6 +172,9 @@ def _run_loop(dm: DeviceMesh, method: str, tol: float, max_num_steps: int, omega
             raise TypeError("implicit_surface must provide f(x) and grad(x)")
         dm.clear_surface()
         host_surface = implicit_surface
+    dev_surface = _wants_device(host_surface, device_callables)
+    dev_boundary = _wants_device(boundary_step, device_callables)
+    hooks_dev = _DeviceHooks(dm, device) if (dev_surface or dev_boundary) else None
 
     if verbose:
         print("Before:")
@@ -118,9 +196,13 @@ def _run_loop(dm: DeviceMesh, method: str, tol: float, max_num_steps: int, omega
             else:
                 if boundary_step is None:
                     st = dm.update_points(tol)
+                elif dev_boundary:
+                    st = hooks_dev.update(omega, tol, boundary_step)
                 else:
                     st = _host_update(dm, omega, tol, boundary_step)
-                if host_surface is not None:
+                if host_surface is not None and dev_surface:
+                    st["surface_sweeps"] = hooks_dev.project(host_surface, implicit_surface_tol)
+                elif host_surface is not None:
                     _project_host(dm, host_surface, implicit_surface_tol)
                 elif boundary_step is not None:
                     dm.project()  # the built-in surface, if one is set
@@ -152,7 +234,7 @@ def optimize_points_cells(points, cells, method: str, tol: float, max_num_steps:
                           step_filename_format=None, implicit_surface=None,
                           implicit_surface_tol: float = 1.0e-10, boundary_step=None,
                           method_name=None, device: int = 0, log=None,
-                          odt_boundary_barycenters: bool = True):
+                          odt_boundary_barycenters: bool = True, device_callables: bool = False):
     """Returns ``(points, cells)``; the inputs are not modified (README.md:124-126).
 
     ``device``, ``log`` (per-step statistics are appended to the list) and
@@ -163,7 +245,7 @@ def optimize_points_cells(points, cells, method: str, tol: float, max_num_steps:
     with DeviceMesh(points, cells, device=device) as dm:
         _run_loop(dm, method, tol, max_num_steps, omega, verbose, callback, step_filename_format,
                   implicit_surface, implicit_surface_tol, boundary_step, cells.dtype, log,
-                  odt_boundary_barycenters)
+                  odt_boundary_barycenters, device_callables, device)
         # large results come back in blocks of the library's pinned result cache: one DMA at
         # PCIe speed instead of a staged copy into 155k fresh pages (DeviceMesh.get_points)
         return dm.get_points(), dm.cells(cells.dtype)

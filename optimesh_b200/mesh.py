@@ -219,6 +219,29 @@ class DeviceMesh:
         check(self._lib.om_new_points(self._h, out.ctypes.data))
         return out
 
+    def targets_device(self) -> int:
+        """Device pointer of the un-relaxed targets of the current method (what `new_points`
+        returns), internal numbering and layout like `points_device`; owned by the handle,
+        valid until the next call.  The caller may overwrite entries."""
+        p = C.c_void_p()
+        check(self._lib.om_targets_device(self._h, C.byref(p)))
+        return p.value
+
+    def update_from_targets(self, targets_ptr: int, tol: float = 0.0) -> dict:
+        """x <- x + limiter(omega (target - x)) for every vertex, boundary vertices included,
+        from a device buffer laid out like `targets_device`."""
+        st = _lib.StepStats()
+        check(self._lib.om_update_from_targets(self._h, C.c_void_p(targets_ptr), float(tol),
+                                               C.byref(st)))
+        return st.as_dict()
+
+    def device_ptrs(self):
+        """(points, cells4, perm, point_stride): raw device pointers, internal numbering; perm
+        (internal -> caller vertex id) is None for the identity."""
+        a, b, c, s = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_int32()
+        check(self._lib.om_device_ptrs(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(s)))
+        return a.value, b.value, c.value, s.value
+
     def solve_graph_laplacian(self, rtol=1.0e-13, max_iter=100000):
         it, res = C.c_int32(), C.c_double()
         check(self._lib.om_solve_graph_laplacian(self._h, float(rtol), int(max_iter),

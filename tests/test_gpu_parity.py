@@ -324,6 +324,71 @@ def test_sphere_odt_with_projection(ob, G):
     assert np.array_equal(c2, rc) and rel_err(p2, rp) <= 1e-8
 
 
+def test_hooks_on_device_match_host_hooks(ob, G):
+    """a generic implicit surface (README.md:157-162) and a boundary_step
+    callback (README.md:146-149) given torch-style callables run on device memory
+    (`device_callables=True`): same trajectory as the host-hook path of the same library
+    (numpy callables between the device phases), which in turn follows the oracle."""
+    import torch
+
+    # 1. generic surface: the README's object works on numpy arrays and on CUDA tensors alike
+    class UserSphere:
+        def f(self, x):
+            return 1.0 - (x[0] ** 2 + x[1] ** 2 + x[2] ** 2)
+
+        def grad(self, x):
+            return -2 * x
+
+    pts, cells = G.tetra_sphere(16)
+    rp, rc = oracle.optimize_points_cells(pts, cells, "odt-fixed-point", 1e-4, 8,
+                                          implicit_surface=ob.Sphere())
+    hlog, dlog = [], []
+    hp, hc = ob.optimize_points_cells(pts, cells, "odt-fixed-point", 1e-4, 8,
+                                      implicit_surface=UserSphere(), log=hlog)
+    dp, dc = ob.optimize_points_cells(pts, cells, "odt-fixed-point", 1e-4, 8,
+                                      implicit_surface=UserSphere(), log=dlog,
+                                      device_callables=True)
+    assert np.array_equal(dc, hc) and np.array_equal(dc, rc)
+    assert rel_err(dp, hp) <= 1e-12 and rel_err(dp, rp) <= 1e-8
+    assert np.abs(np.linalg.norm(dp, axis=1) - 1.0).max() < 1e-10
+    assert [l["n_flips"] for l in dlog] == [l["n_flips"] for l in hlog]
+    assert any(l["surface_sweeps"] > 0 for l in dlog)
+
+    # 2. boundary_step: Lloyd proposes the control-volume centroid for boundary vertices too;
+    #    the callback puts it back onto the circle.  The device variant sees a CUDA tensor in
+    #    the caller's vertex order.
+    seen = {}
+
+    def to_circle_np(x):
+        return x / np.sqrt(np.einsum("ij,ij->j", x, x))
+
+    def to_circle_torch(x):
+        seen["cuda"] = x.is_cuda
+        seen["shape"] = tuple(x.shape)
+        return x / torch.sqrt((x * x).sum(0))
+
+    to_circle_torch.on_device = True  # (the attribute opts in, like device_callables=True)
+    pts, cells = G.disk(60, 3)
+    nb = int(OMesh(pts, cells).is_boundary_point.sum())
+    for method, omega in (("lloyd", 1.0), ("cvt-block-diagonal", 1.0), ("lloyd", 2.0)):
+        hlog, dlog = [], []
+        hp, hc = ob.optimize_points_cells(pts, cells, method, 0.0, 8, omega=omega,
+                                          boundary_step=to_circle_np, log=hlog)
+        dp, dc = ob.optimize_points_cells(pts, cells, method, 0.0, 8, omega=omega,
+                                          boundary_step=to_circle_torch, log=dlog)
+        assert seen == {"cuda": True, "shape": (2, nb)}
+        assert np.array_equal(dc, hc)
+        assert rel_err(dp, hp) <= 1e-11
+        assert [l["n_flips"] for l in dlog] == [l["n_flips"] for l in hlog]
+        assert [l["n_limited"] for l in dlog] == [l["n_limited"] for l in hlog]
+    bnd = OMesh(pts, cells).is_boundary_point
+    assert not np.allclose(dp[bnd], pts[bnd])  # the boundary vertices slid along the circle
+    assert np.abs(np.linalg.norm(dp[bnd], axis=1) - 1.0).max() < 0.02
+    with pytest.raises(ValueError):
+        ob.optimize_points_cells(pts, cells, "lloyd", 0.0, 1, boundary_step=lambda x: x[:, :-1],
+                                 device_callables=True)
+
+
 def test_cpt_linear_solve_vs_spsolve(ob, G):
     """Config 3 in miniature: Laplacian smoothing on a jittered square, boundary pinned."""
     pts, cells = G.square(60, 0.25, 0)
