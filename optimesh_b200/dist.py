@@ -289,6 +289,10 @@ def partitioned_flip(dm: DeviceMesh, band: BandExchange, group=None, tol: float 
         first = False
         if ncand == 0:
             break
+    else:
+        import warnings
+
+        warnings.warn("Maximum number of edge flips reached.")
     nf, nr = dm.flip_pass_end()
     if nf > 0:
         band.dirty = True

@@ -389,6 +389,27 @@ def test_hooks_on_device_match_host_hooks(ob, G):
                                  device_callables=True)
 
 
+def test_solver_failures_are_reported(ob, G):
+    """An iterative solve that does not reach its tolerance is an error, never a silent OK;
+    a closed surface (no fixed vertex: singular graph Laplacian) is refused."""
+    from optimesh_b200._lib import OptimeshError
+
+    pts, cells = G.square(60, 0.25, 0)
+    with ob.DeviceMesh(pts, cells) as dm:
+        with pytest.raises(OptimeshError, match="stopped after"):
+            dm.solve_graph_laplacian(1e-14, 5)
+    big, bc = G.disk(900, 5)  # above the multigrid threshold
+    with ob.DeviceMesh(big, bc) as dm:
+        with pytest.raises(OptimeshError, match="stopped after"):
+            dm.solve_graph_laplacian(1e-14, 3)
+    sp, sc = G.tetra_sphere(8)
+    with ob.DeviceMesh(sp, sc) as dm:
+        with pytest.raises(ValueError, match="needs a boundary"):
+            dm.solve_graph_laplacian(1e-10, 100)
+    with pytest.raises(ValueError, match="needs a boundary"):
+        ob.optimize_points_cells(sp, sc, "cpt-linear-solve", 1e-6, 2)
+
+
 def test_cpt_linear_solve_vs_spsolve(ob, G):
     """Config 3 in miniature: Laplacian smoothing on a jittered square, boundary pinned."""
     pts, cells = G.square(60, 0.25, 0)
