@@ -1,5 +1,6 @@
 // Shared declarations for the optimesh_b200 device library (sm_100a).
 #pragma once
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -83,24 +84,23 @@ struct DevScalars {
   unsigned long long g_flips_prev, g_flips;  // flips of the pass over all ranks
   int sync_dead;                    // a meeting timed out
   int pl_round;                     // flip rounds executed in the current pass (loop.cu)
+  int lim_div_exact;                // threshold of om_limiter_mode (set by k_pl_init)
 };
 
 // Limiter variant of the ring kernel, chosen from the share of vertices the PREVIOUS update
-// limited.  The lazy variant proves "not limited" with a division-free bound; about 1.3 x the
-// limited vertices fail it and need the exact smallest inradius.
-//   0 lazy, failures evaluated in the kernel (a second pass over the staged ring, +70 % for
-//     every warp with at least one such lane): best below 2 % -- fewer than half of the warps;
-//   2 lazy, failures handed to k_post (compacted, evaluated from their ring rows by full
-//     warps): best in between;
-//   1 exact everywhere (+45 % for every warp): best above 12 %, e.g. the first steps on a fresh
-//     mesh, where most vertices are limited.
-// Every variant gives a vertex the same bits.
+// limited.
+//   0 lazy: a division-free bound proves "not limited"; the vertices that fail it (about 1.3 x
+//     the limited ones) are handed to k_post, which evaluates them exactly from their ring rows;
+//   1 exact everywhere (+45 % for every warp): pays above 1/8 limited, e.g. in the first steps
+//     on a fresh mesh, where most vertices are limited.
+// Either variant gives a vertex the same bits.  OM_LIM_EXACT_DIV overrides the 8 (measurements).
 __host__ __device__ inline int om_limiter_mode(bool limiter_on, long long limited,
-                                               long long n_free) {
-  if (!limiter_on) return 0;
-  if (8ll * limited > n_free) return 1;
-  if (50ll * limited > n_free) return 2;
-  return 0;
+                                               long long n_free, int div_exact = 8) {
+  return (limiter_on && (long long)div_exact * limited > n_free) ? 1 : 0;
+}
+inline int om_lim_div() {
+  static const int de = getenv("OM_LIM_EXACT_DIV") ? atoi(getenv("OM_LIM_EXACT_DIV")) : 8;
+  return de;
 }
 
 // After the check of a flip round: do its flips run?  `cand` = edges the check flagged,

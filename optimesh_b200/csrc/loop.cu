@@ -33,8 +33,9 @@
 namespace {
 
 __global__ void k_pl_init(DevScalars* ds, long long max_steps, double tol2, int mode_exact,
-                          long long n_free, int limiter_on, int max_rounds) {
+                          long long n_free, int limiter_on, int max_rounds, int div_exact) {
   ds->halt = 0;
+  ds->lim_div_exact = div_exact;
   ds->k = 0;
   ds->max_steps = max_steps;
   ds->tol2 = tol2;
@@ -57,7 +58,8 @@ __global__ void k_pl_iter_end(DevScalars* ds, cudaGraphConditionalHandle handle,
     ds->total_rounds += ds->n_rounds;
     ds->total_limited += (long long)ds->n_limited;
     ds->total_deferred += ds->n_deferred;
-    ds->mode_exact = om_limiter_mode(ds->limiter_on != 0, (long long)ds->n_limited, ds->n_free);
+    ds->mode_exact = om_limiter_mode(ds->limiter_on != 0, (long long)ds->n_limited, ds->n_free,
+                                     ds->lim_div_exact);
     double md;
     memcpy(&md, &ds->max_diff2_bits, 8);
     if (ds->err)
@@ -340,9 +342,10 @@ int om_run_pipelined(om_handle* h, double tol, int64_t max_num_steps, int64_t* s
   int32_t nr = 0, cap = 0;
   if (!h->delaunay_clean) OM_TRY(om_flip_impl(h, 0.0, 100, &nf, &nr, &cap));
   h->delaunay_clean = false;  // the points are about to move
-  const int mode_exact = om_limiter_mode(h->limiter != 0, (long long)(h->limited_frac * 1.0e6), 1000000);
+  const int mode_exact = om_limiter_mode(h->limiter != 0, (long long)(h->limited_frac * 1.0e6), 1000000,
+                                         om_lim_div());
   OM_LAUNCH(h, k_pl_init, 1, 1, h->ds, (long long)max_num_steps, tol * tol, mode_exact,
-            (long long)h->N, h->limiter, 100);
+            (long long)h->N, h->limiter, 100, om_lim_div());
   CUDA_TRY(cudaGetLastError());
   double* A = h->x;
   double* B = h->xnew;

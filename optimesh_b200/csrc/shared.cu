@@ -249,8 +249,9 @@ __global__ void k_sync(ShView sv, DevScalars* ds, int kind, cudaGraphConditional
 }
 
 __global__ void k_sh_init(DevScalars* ds, long long max_steps, double tol2, int mode_exact,
-                          long long n_free, int limiter_on, int max_rounds) {
+                          long long n_free, int limiter_on, int max_rounds, int div_exact) {
   ds->halt = 0;
+  ds->lim_div_exact = div_exact;
   ds->k = 0;
   ds->max_steps = max_steps;
   ds->tol2 = tol2;
@@ -283,7 +284,7 @@ __device__ void sh_iter_end(DevScalars* ds, cudaGraphConditionalHandle handle) {
     ds->total_deferred += (long long)ds->g_sum[1];
     ds->max_diff2_bits = ds->g_max[0];
     ds->n_limited = (unsigned long long)limited;
-    ds->mode_exact = om_limiter_mode(ds->limiter_on != 0, limited, ds->n_free);
+    ds->mode_exact = om_limiter_mode(ds->limiter_on != 0, limited, ds->n_free, ds->lim_div_exact);
     double md;
     memcpy(&md, &ds->g_max[0], 8);
     if (ds->err || ds->g_max[1])
@@ -771,9 +772,10 @@ int om_shared_run(om_handle* h, double tol, int64_t max_num_steps, int64_t* step
   cudaSetDevice(h->device);
   int which = -1;
   OM_TRY(graph_for(h, sh, h->x, h->xnew, &which));
-  const int mode_exact = om_limiter_mode(h->limiter != 0, (long long)(h->limited_frac * 1.0e6), 1000000);
+  const int mode_exact = om_limiter_mode(h->limiter != 0, (long long)(h->limited_frac * 1.0e6), 1000000,
+                                         om_lim_div());
   OM_LAUNCH(h, k_sh_init, 1, 1, h->ds, (long long)max_num_steps, tol * tol, mode_exact,
-            (long long)h->N, h->limiter, 100);
+            (long long)h->N, h->limiter, 100, om_lim_div());
   CUDA_TRY(cudaGetLastError());
   double* A = h->x;
   double* B = h->xnew;
@@ -830,7 +832,7 @@ int om_shared_time_update(om_handle* h, int reps, double* ms_per_launch) {
   cudaEvent_t e0, e1;
   CUDA_TRY(cudaEventCreate(&e0));
   CUDA_TRY(cudaEventCreate(&e1));
-  OM_LAUNCH(h, k_sh_init, 1, 1, h->ds, 1ll, 0.0, 0, (long long)h->N, h->limiter, 100);
+  OM_LAUNCH(h, k_sh_init, 1, 1, h->ds, 1ll, 0.0, 0, (long long)h->N, h->limiter, 100, om_lim_div());
   OM_TRY(om_pl_launch_update_part(h, h->x, h->xnew, 1));  // warm-up
   CUDA_TRY(cudaEventRecord(e0, h->stream));
   for (int i = 0; i < reps; i++) OM_TRY(om_pl_launch_update_part(h, h->x, h->xnew, 1));

@@ -36,10 +36,10 @@
 #define OM_K1_BLOCK 128
 #endif
 #ifndef OM_K1_MINB
-#define OM_K1_MINB 7
+#define OM_K1_MINB 8
 #endif
 #ifndef OM_K1_UNROLL
-#define OM_K1_UNROLL 2
+#define OM_K1_UNROLL 1
 #endif
 #ifndef OM_K1_MINB_EXACT
 #define OM_K1_MINB_EXACT 6
@@ -186,7 +186,6 @@ struct StepParams {
   int force_walk;  // diagnostics (OM_NO_RINGS): every free vertex goes through k_post
   int prefetch_ahead;  // vertices between a block and the one that runs a wave later
   int gate;  // pipelined loop: return at once if the loop has halted / the other limiter mode is on
-  int mode;  // limiter variant (om_limiter_mode) when the host chose it (gate == 0)
   DevScalars* ds;
 };
 
@@ -280,23 +279,12 @@ __global__ void __launch_bounds__(OM_K1_BLOCK, (D == 2 ? (EXACT ? OM_K1_MINB_EXA
       if (EXACT) {
         limited = ch.limit(d, diff2);
       } else if (!ch.proves_unlimited(diff2)) {
-        // The division-free bound cannot rule the limiter out.  Many such vertices (mode 2):
-        // k_post takes them.  Few (a fraction of a percent once the mesh has settled): the
-        // smallest incident inradius is evaluated exactly here, from the ring still staged in
-        // shared memory, by the limiter-only chain -- the same cell code, hence the same bits,
-        // as the exact variant of this kernel.
-        if ((p.gate ? p.ds->mode_exact : p.mode) == 2) {
-          deferred = true;
-        } else {
-        Chain<D, OM_CHAIN_LIMITER_ONLY, true, false> lim;
-        lim.init(P0);
-        lim.start(ld_ring(0));
-        lim.first(ld_ring(1), false, true);
-#pragma unroll 1
-        for (int j = 2; j < k; j++) lim.next(ld_ring(j), false);
-        lim.close(ld_ring(0), false);
-        limited = lim.limit(d, diff2);
-        }
+        // The division-free bound cannot rule the limiter out (about 1.3 x the limited
+        // vertices): k_post compacts these vertices and evaluates the smallest incident
+        // inradius exactly from their ring rows, with full warps.  (Evaluating it here, by a
+        // second pass over the staged ring, was measured slower even when almost no lane
+        // needs it: 0.293 vs 0.273 ms, the extra code costs registers on the main path.)
+        deferred = true;
       }
     }
 #pragma unroll
@@ -872,7 +860,6 @@ StepParams make_params(om_handle* h, double* out) {
     p.prefetch_ahead = waves * OM_K1_BLOCK;
   }
   p.gate = 0;
-  p.mode = 0;
   p.ds = h->ds;
   return p;
 }
@@ -916,9 +903,10 @@ int om_launch_point_update(om_handle* h, double* out, bool check) {
   }
   // the lazy limiter pays off once few vertices are limited (the previous step tells; see
   // k_pl_iter_end in loop.cu for the break-even)
-  p.mode = om_limiter_mode(h->limiter != 0, (long long)(h->limited_frac * 1.0e6), 1000000);
+  const bool exact = om_limiter_mode(h->limiter != 0, (long long)(h->limited_frac * 1.0e6),
+                                     1000000, om_lim_div()) == 1;
   if (h->timing) cudaEventRecord(h->ev[0], h->stream);
-  OM_TRY(launch_step(h, p, check ? 1 : 0, p.mode == 1));
+  OM_TRY(launch_step(h, p, check ? 1 : 0, exact));
   if (h->timing) {
     cudaEventRecord(h->ev[1], h->stream);
     h->ev_pending = true;
