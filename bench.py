@@ -414,9 +414,10 @@ def run_single(args, torch, ob, local, stream):
     b_alg = alg_bytes(n, c, d)
     roofline = roofline_of(k1_ms, b_alg, n, method, {
         "kernel_share_of_step": k1_ms / (ms / args.steps),
-        "kernel_timing": f"CUDA events around each of {tim['step_kernel_launches']} launches "
-                         f"(both limiter variants are enqueued, one returns at once) in a second "
-                         f"run of {args.steps} steps, stream-launched variant of the same loop",
+        "kernel_timing": f"CUDA events around each of {tim['step_kernel_launches']} launches of "
+                         f"the ring kernel (the limiter variant the loop selects) in a second "
+                         f"run of {args.steps} steps that follows the timed one: the same loop, "
+                         f"its kernels launched from the stream instead of as one CUDA graph",
         "rest_of_step_ms": ms / args.steps - k1_ms,
         "note": "rest of the step = k_post + flag-driven Delaunay check + flip rounds + ring "
                 "rows + recomputation of touched vertices + statistics",
