@@ -409,6 +409,7 @@ def run_single(args, torch, ob, local, stream):
     dm.set_timing(True)
     dm.run(0.0, args.steps)
     tim = dm.timing()
+    phases = dm.phase_timing()
     dm.set_timing(False)
     k1_ms = tim["step_kernel_ms"] / max(tim["step_kernel_launches"], 1)
     b_alg = alg_bytes(n, c, d)
@@ -419,6 +420,7 @@ def run_single(args, torch, ob, local, stream):
                          f"run of {args.steps} steps that follows the timed one: the same loop, "
                          f"its kernels launched from the stream instead of as one CUDA graph",
         "rest_of_step_ms": ms / args.steps - k1_ms,
+        "phases_ms_stream_loop": phases,
         "note": "rest of the step = k_post + flag-driven Delaunay check + flip rounds + ring "
                 "rows + recomputation of touched vertices + statistics",
     })

@@ -300,6 +300,11 @@ int om_shared_time_update(om_handle* h, int reps, double* ms_per_launch);
 int om_set_timing(om_handle* h, int on);
 int om_get_timing(om_handle* h, double* step_kernel_ms, int64_t* step_kernel_launches,
                   double* flip_pass_ms, int64_t* flip_passes);
+/* While timing is on, om_run's loop (driven from the stream) also times its phases with CUDA
+ * events: phase_ms5 = {reset + ring kernel, vertices it left (k_post), flag-driven Delaunay
+ * check, flip rounds, ring rows + recomputation of touched vertices + statistics}, summed over
+ * `iterations` loop iterations. */
+int om_get_phase_timing(om_handle* h, double* phase_ms5, int64_t* iterations);
 
 /* Device memory of destroyed handles stays in the device's stream-ordered pool so that the
  * next om_create is cheap; this returns it to the driver. */

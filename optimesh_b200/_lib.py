@@ -109,6 +109,7 @@ SIGNATURES = {
     "om_shared_info": (C.c_int, [_H, _P(C.c_int64), _P(C.c_int64), _P(C.c_int64),
                                  _P(C.c_int64)]),
     "om_set_timing": (C.c_int, [_H, C.c_int]),
+    "om_get_phase_timing": (C.c_int, [_H, C.c_void_p, _P(C.c_int64)]),
     "om_get_timing": (C.c_int, [_H, _P(C.c_double), _P(C.c_int64), _P(C.c_double),
                                 _P(C.c_int64)]),
     "om_release_cached_memory": (C.c_int, [C.c_int]),

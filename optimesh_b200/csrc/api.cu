@@ -1109,6 +1109,8 @@ int om_set_timing(om_handle* h, int on) {
   h->timing = on != 0;
   h->t_step_ms = h->t_flip_ms = 0.0;
   h->n_step = h->n_flip = 0;
+  for (double& t : h->t_phase_ms) t = 0.0;
+  h->n_phase = 0;
   return OM_OK;
 }
 
@@ -1119,6 +1121,14 @@ int om_get_timing(om_handle* h, double* step_kernel_ms, int64_t* step_kernel_lau
   if (step_kernel_launches) *step_kernel_launches = h->n_step;
   if (flip_pass_ms) *flip_pass_ms = h->t_flip_ms;
   if (flip_passes) *flip_passes = h->n_flip;
+  return OM_OK;
+}
+
+int om_get_phase_timing(om_handle* h, double* phase_ms5, int64_t* iterations) {
+  OM_ENTER(h);
+  if (phase_ms5)
+    for (int i = 0; i < 5; i++) phase_ms5[i] = h->t_phase_ms[i];
+  if (iterations) *iterations = h->n_phase;
   return OM_OK;
 }
 

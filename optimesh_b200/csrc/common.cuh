@@ -217,6 +217,10 @@ struct om_handle {
   bool delaunay_clean = false;
   int64_t run_flips = 0, run_rounds = 0, run_limited = 0, run_deferred = 0;  // last om_run
   double t_step_ms = 0.0, t_flip_ms = 0.0;
+  // phases of the pipelined loop when it is timed (loop.cu, run_stream): reset+ring kernel,
+  // k_post, flag check, flip rounds, ring rows + recomputation + statistics
+  double t_phase_ms[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  int64_t n_phase = 0;
   int64_t n_step = 0, n_flip = 0;
 };
 

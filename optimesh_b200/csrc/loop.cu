@@ -255,35 +255,56 @@ void free_graph(PlGraph& g) {
   g.graph = nullptr;
 }
 
-// the same loop driven from the stream: one scalar readback per flip round and per step
+// the same loop driven from the stream: one scalar readback per flip round and per step.
+// Timed (om_set_timing): CUDA events between the phases of every iteration.
 int run_stream(om_handle* h, double* A, double* B, int mode) {
   const bool timed = h->timing;
-  for (int64_t it = 0;; it++) {
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  if (timed)
+    for (auto& e : ev) CUDA_TRY(cudaEventCreate(&e));
+  auto mark = [&](int i) {
+    if (timed) cudaEventRecord(ev[i], h->stream);
+  };
+  int rc = OM_OK;
+  for (int64_t it = 0; rc == OM_OK; it++) {
     const double* xin = (it & 1) ? B : A;
     double* xout = (it & 1) ? A : B;
-    OM_TRY(om_pl_launch_update_part(h, xin, xout, 0));
+    mark(0);
+    if ((rc = om_pl_launch_update_part(h, xin, xout, 0)) != OM_OK) break;
     if (timed) cudaEventRecord(h->ev[0], h->stream);
-    OM_TRY(om_pl_launch_update_part(h, xin, xout, mode == 1 ? 2 : 1));
+    if ((rc = om_pl_launch_update_part(h, xin, xout, mode == 1 ? 2 : 1)) != OM_OK) break;
     if (timed) cudaEventRecord(h->ev[1], h->stream);
-    OM_TRY(enqueue_head_rest(h, xin, xout, 0ull, 0));
-    while (true) {
-      OM_TRY(om_fetch_scalars(h));
-      if (!h->hs->pl_go) break;
-      OM_TRY(enqueue_round(h, xin, 0ull, 0));
+    mark(1);
+    if ((rc = om_pl_launch_update_part(h, xin, xout, 3)) != OM_OK) break;
+    mark(2);
+    if ((rc = om_pl_launch_flags_check(h, xin)) != OM_OK) break;
+    if ((rc = om_pl_launch_round_end(h, 0ull, 0)) != OM_OK) break;
+    mark(3);
+    while (rc == OM_OK) {
+      if ((rc = om_fetch_scalars(h)) != OM_OK || !h->hs->pl_go) break;
+      rc = enqueue_round(h, xin, 0ull, 0);
     }
+    if (rc != OM_OK) break;
+    mark(4);
+    if ((rc = enqueue_tail(h, xin, xout, 0ull, 0)) != OM_OK) break;
+    mark(5);
+    if ((rc = om_fetch_scalars(h)) != OM_OK) break;
     if (timed) {
       float ms = 0.f;
       if (cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]) == cudaSuccess) {
         h->t_step_ms += ms;
         h->n_step++;
       }
+      for (int i = 0; i < 5; i++)
+        if (cudaEventElapsedTime(&ms, ev[i], ev[i + 1]) == cudaSuccess) h->t_phase_ms[i] += ms;
+      h->n_phase++;
     }
-    OM_TRY(enqueue_tail(h, xin, xout, 0ull, 0));
-    OM_TRY(om_fetch_scalars(h));
     if (h->hs->halt) break;
     mode = h->hs->mode_exact;
   }
-  return OM_OK;
+  if (timed)
+    for (auto& e : ev) cudaEventDestroy(e);
+  return rc;
 }
 
 }  // namespace

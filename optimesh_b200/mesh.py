@@ -395,6 +395,16 @@ class DeviceMesh:
     def set_timing(self, on: bool = True):
         check(self._lib.om_set_timing(self._h, int(bool(on))))
 
+    def phase_timing(self) -> dict:
+        """ms per loop iteration of the phases of the timed (stream-driven) loop."""
+        ph = (C.c_double * 5)()
+        n = C.c_int64()
+        check(self._lib.om_get_phase_timing(self._h, ph, C.byref(n)))
+        k = max(n.value, 1)
+        names = ("reset_and_ring_kernel", "k_post", "flag_check", "flip_rounds",
+                 "rings_recompute_stats")
+        return {"iterations": n.value, **{m: ph[i] / k for i, m in enumerate(names)}}
+
     def timing(self) -> dict:
         a, b = C.c_double(), C.c_double()
         na, nb = C.c_int64(), C.c_int64()
