@@ -460,10 +460,6 @@ def run_single(args, torch, ob, local, stream):
         "gpu_launches": launches,
     }
     dm.close()  # its device memory returns to the pool before the end-to-end calls
-    if not args.no_config5:
-        ob._lib.load().om_release_cached_memory(local)
-        line["config5"] = config5_block(args, torch, None, ob, 1, 0, local, stream)
-        ob._lib.load().om_release_cached_memory(local)
     if not args.no_e2e:
         # end to end through the public API with HOST buffers: upload, setup, K steps,
         # download -- all inside the timed region.  Two warm-up calls, then five timed; the
@@ -489,6 +485,10 @@ def run_single(args, torch, ob, local, stream):
                     f"omega={omega}) on host numpy arrays (float64 points, int64 cells)",
             "seconds": dt, "seconds_all_calls": times, "steps": e2e_steps,
         }
+    if not args.no_config5:
+        ob._lib.load().om_release_cached_memory(local)
+        line["config5"] = config5_block(args, torch, None, ob, 1, 0, local, stream)
+        ob._lib.load().om_release_cached_memory(local)
     if not args.no_cpu_baseline:
         v, dt, ns, cs, nb, workers = cpu_step_rate(method, omega, 250000, 2, 0)
         line["cpu_baseline"] = {
