@@ -232,6 +232,15 @@ struct om_handle {
     }                                                                  \
   } while (0)
 
+// the same with dynamic shared memory
+#define OM_LAUNCH_SMEM(h, kernel, grid, block, smem, ...)                  \
+  do {                                                                    \
+    if ((grid) > 0) {                                                     \
+      kernel<<<(grid), (block), (smem), (h)->stream>>>(__VA_ARGS__);      \
+      (h)->launches++;                                                    \
+    }                                                                     \
+  } while (0)
+
 static inline int om_grid(int64_t n, int block) { return (int)((n + block - 1) / block); }
 
 // Device memory comes from the device's stream-ordered pool (kept across handles: the

@@ -467,7 +467,18 @@ __global__ void k_reset_flip_scalars(DevScalars* ds, int new_pass) {
 // Flagged cells go to the candidate list through a small per-warp list in shared memory: one
 // atomic on the global counter per warp and run.
 constexpr unsigned VF_SPOKES = 0xffu, VF_DEFER = 0x100u, VF_CHECKALL = 0x200u;
-constexpr int FLG_BLOCK = 256, FLG_PER = 8, FLG_RUN = 32 * FLG_PER, FLG_OUT = 192, FLG_HE = 256;
+// FLG_PER flag words per lane and trip (a multiple of 8: 16-byte loads).  The kernel is a chain
+// of dependent gathers with a handful of flagged vertices per 256 words.  Measured: 16 words per
+// lane (half as many trips, same number of resident warps) is SLOWER, 0.113 vs 0.081 ms per
+// step -- the slowest lane of a trip (a star walk) holds its warp, smaller trips balance better.
+#ifndef OM_FLG_PER
+#define OM_FLG_PER 8
+#endif
+constexpr int FLG_BLOCK = 256, FLG_PER = OM_FLG_PER, FLG_RUN = 32 * FLG_PER,
+              FLG_OUT = 24 * FLG_PER, FLG_HE = 32 * FLG_PER;
+static_assert(FLG_PER % 8 == 0, "flag words are read 8 at a time");
+constexpr size_t FLG_SMEM =
+    (FLG_BLOCK / 32) * (sizeof(int) * (FLG_RUN + FLG_HE + FLG_OUT) + sizeof(unsigned short) * FLG_RUN);
 constexpr int RING_IDMASK = (1 << 29) - 1;
 
 template <int D>
@@ -529,8 +540,11 @@ __device__ __forceinline__ void push_half_edge(int he, int* s_he, int* s_nhe,
   }
 }
 
+#ifndef OM_FLG_MINB
+#define OM_FLG_MINB 4
+#endif
 template <int D>
-__global__ void __launch_bounds__(FLG_BLOCK)
+__global__ void __launch_bounds__(FLG_BLOCK, OM_FLG_MINB)
     k_suspect_flags(const double* __restrict__ x, const int4* __restrict__ cells,
                     const int* __restrict__ adj, const int* __restrict__ v2c,
                     const int* __restrict__ ring, const int* __restrict__ ringc,
@@ -539,10 +553,12 @@ __global__ void __launch_bounds__(FLG_BLOCK)
                     int* __restrict__ cand_epoch, DevScalars* ds, int vlo, int vhi) {
   if (ds->halt & 1) return;
   constexpr int NW = FLG_BLOCK / 32;
-  __shared__ int s_v[NW][FLG_RUN];
-  __shared__ unsigned short s_f[NW][FLG_RUN];
-  __shared__ int s_he[NW][FLG_HE];
-  __shared__ int s_out[NW][FLG_OUT];
+  // dynamic shared memory (more than the 48 KB a static allocation may have): FLG_SMEM bytes
+  extern __shared__ __align__(16) unsigned char flg_smem[];
+  int(*s_v)[FLG_RUN] = reinterpret_cast<int(*)[FLG_RUN]>(flg_smem);
+  int(*s_he)[FLG_HE] = reinterpret_cast<int(*)[FLG_HE]>(s_v + NW);
+  int(*s_out)[FLG_OUT] = reinterpret_cast<int(*)[FLG_OUT]>(s_he + NW);
+  unsigned short(*s_f)[FLG_RUN] = reinterpret_cast<unsigned short(*)[FLG_RUN]>(s_out + NW);
   __shared__ int s_nout[NW], s_nhe[NW];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gwarp = blockIdx.x * NW + warp, nwarps = gridDim.x * NW;
@@ -556,16 +572,21 @@ __global__ void __launch_bounds__(FLG_BLOCK)
     int cnt = 0;
     if (vb < N) {
       // (the flag array is padded to a multiple of FLG_PER words beyond N)
-      const uint4 raw = *reinterpret_cast<const uint4*>(vflags + vb);
-      const unsigned r[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
-      for (int i = 0; i < FLG_PER; i++) {
-        w[i] = (unsigned short)((r[i >> 1] >> (16 * (i & 1))) & (VF_SPOKES | VF_CHECKALL));
-        if (vb + i >= N) w[i] = 0;
-        cnt += w[i] ? 1 : 0;
+      for (int g = 0; g < FLG_PER / 8; g++) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(vflags + vb + 8 * g);
+        const unsigned r[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          unsigned short f =
+              (unsigned short)((r[i >> 1] >> (16 * (i & 1))) & (VF_SPOKES | VF_CHECKALL));
+          if (vb + 8 * g + i >= N) f = 0;
+          w[8 * g + i] = f;
+          cnt += f ? 1 : 0;
+        }
+        if (raw.x | raw.y | raw.z | raw.w)  // every bit has been consumed by now
+          *reinterpret_cast<uint4*>(vflags + vb + 8 * g) = make_uint4(0u, 0u, 0u, 0u);
       }
-      if (raw.x | raw.y | raw.z | raw.w)  // every bit has been consumed by now
-        *reinterpret_cast<uint4*>(vflags + vb) = make_uint4(0u, 0u, 0u, 0u);
     } else {
 #pragma unroll
       for (int i = 0; i < FLG_PER; i++) w[i] = 0;
@@ -1040,14 +1061,23 @@ int om_pl_launch_flags_check(om_handle* h, const double* xin) {
   om_shared_vertex_range(h, &vlo, &vhi);
   const int blocks = om_grid(vhi - vlo, FLG_BLOCK * FLG_PER);
   const int G = std::min(blocks, 148 * 8);
+  static bool attr_set_dev[64] = {};  // (the attribute is per device)
+  bool& attr_set = attr_set_dev[h->device & 63];
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(k_suspect_flags<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)FLG_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(k_suspect_flags<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)FLG_SMEM));
+    attr_set = true;
+  }
   if (h->D == 2)
-    OM_LAUNCH(h, k_suspect_flags<2>, G, FLG_BLOCK, xin, h->cells, (const int*)h->adj, h->v2c,
-              (const int*)h->ring, (const int*)h->ringc, h->vflags, (int)h->N, 0.0, h->sarr,
-              h->cand, h->cand_epoch, h->ds, vlo, vhi);
+    OM_LAUNCH_SMEM(h, k_suspect_flags<2>, G, FLG_BLOCK, FLG_SMEM, xin, h->cells,
+                   (const int*)h->adj, h->v2c, (const int*)h->ring, (const int*)h->ringc,
+                   h->vflags, (int)h->N, 0.0, h->sarr, h->cand, h->cand_epoch, h->ds, vlo, vhi);
   else
-    OM_LAUNCH(h, k_suspect_flags<3>, G, FLG_BLOCK, xin, h->cells, (const int*)h->adj, h->v2c,
-              (const int*)h->ring, (const int*)h->ringc, h->vflags, (int)h->N, 0.0, h->sarr,
-              h->cand, h->cand_epoch, h->ds, vlo, vhi);
+    OM_LAUNCH_SMEM(h, k_suspect_flags<3>, G, FLG_BLOCK, FLG_SMEM, xin, h->cells,
+                   (const int*)h->adj, h->v2c, (const int*)h->ring, (const int*)h->ringc,
+                   h->vflags, (int)h->N, 0.0, h->sarr, h->cand, h->cand_epoch, h->ds, vlo, vhi);
   CUDA_TRY(cudaGetLastError());
   return OM_OK;
 }
