@@ -1,20 +1,21 @@
-"""Smoothing one mesh on several GPUs of a box (one process per GPU, torch.distributed).
+"""Smoothing one mesh on several GPUs of a box (one process per GPU, torch.distributed for
+the rendezvous).
 
-Round-1 decomposition ("replicated topology, sharded update"): every rank builds the SAME
-device mesh (identical inputs give identical internal numbering, so vertex ranges mean the
-same thing everywhere).  After the spatial renumbering a contiguous vertex range is a
-compact region, so rank r updates the range [r*chunk, (r+1)*chunk) with the fused step
-kernel -- the fp64-heavy half of a step -- and the updated coordinates are made visible
-everywhere by ONE in-place all-gather over NVLink straight on the device point array
-(`om_points_device`).  Convergence (max |diff|^2) and the limiter count are all-reduced.
-The first round of the flip-until-Delaunay pass -- the only one that scans every cell -- is
-split over the ranks by cell range; the flagged-edge records are all-gathered and applied by
-every rank, and the remaining work-list rounds (flagged cells only) run replicated: same
-data, same deterministic kernels -> same topology everywhere.  Results are bit-identical to
-the single-GPU run.
+Round 2 -- what `bench.py --gpus N` and `optimize_points_cells_shared` run: `SharedMesh`
+(bottom of this file; csrc/shared.cu).  ONE mesh in one address space: every array is cut into
+N chunks by vertex / cell id, chunk r is memory of GPU r, all chunks are mapped on every rank
+(CUDA virtual memory management over NVLink peer memory), so the single-GPU kernels run
+unchanged on each rank's vertex range and what crosses a chunk boundary is a peer load, store or
+atomic.  The topology is partitioned (memory per rank ~ 1/N), there is no collective and no host
+readback on the data path; the ranks meet on the device (k_sync) and the whole loop is one CUDA
+graph per rank.  Bit-identical to one GPU.  The host side here is small: the descriptor exchange
+(`exchange_fds`) and the calls.
 
-What this does NOT do yet: shard the topology storage, and shrink
-the coordinate exchange to the one-ring band.
+Round 1, kept behind its tests (`run_sharded`, `run_partitioned`): replicated topology, the
+point update split by vertex range, coordinates exchanged with NCCL (a band around each range),
+flip rounds exchanged as fixed-capacity record slots; every rank applies every flip.  Weak
+scaling 0.67 / 0.59 / 0.49 at 2 / 4 / 8 GPUs against 0.84 / 0.82 / 0.81 for the shared address
+space.
 """
 from __future__ import annotations
 
