@@ -879,6 +879,8 @@ int mg_build(om_handle* h, std::vector<MgLevel>& lv) {
       om_set_error("CUDA error %s in the multigrid setup: %s", cudaGetErrorName(e),
                    cudaGetErrorString(e));
       rc = OM_ERR_CUDA;
+      for (void* p : c.owned) om_free(h, p);  // the level under construction is not in lv yet
+      c.owned.clear();
     };
     cudaError_t e;
     if ((e = alloc(c, &c.diag, sizeof(double) * nc)) != cudaSuccess) { fail(e); break; }
