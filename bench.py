@@ -220,10 +220,10 @@ def run_reference(args):
         return
     method, omega, grid = workload(args)
     total = args.steps + args.warmup
-    # size the sample so the whole run stays within a few minutes:
-    # the numpy port costs ~25 us per vertex per step on one core
+    # size the sample so the whole run stays within a few minutes: the numpy port costs 6-12 us
+    # per vertex and step and core at these sizes (more on larger meshes: cache misses)
     budget_s = 120.0
-    n_target = int(min(4.0e5, max(2.0e4, budget_s / (total * 40e-6))))
+    n_target = int(min(4.0e5, max(2.0e4, budget_s / (total * 12e-6))))
     v, dt, n, c, nb, workers = cpu_step_rate(method, omega, n_target, args.steps, args.warmup)
     sample = (f"{workers} replicas (one per host core) of a random disk mesh disk({nb}) (Qhull): "
               f"{n} vertices / {c} cells each, {args.steps} steps of {method} (omega={omega}) "
