@@ -633,12 +633,21 @@ def run_b200(args):
 
 
 def main():
+    args = parse()
+    if args.impl != "reference" and args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # `python bench.py --gpus N` without a launcher: start the N ranks ourselves
+        import subprocess
+
+        port = 29500 + os.getpid() % 2000
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+               f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
     # the contract is ONE JSON line on stdout: keep a private copy of stdout for it and send
     # everything else (e.g. NCCL's version banner) to stderr
     real = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
     sys.stdout = real
-    args = parse()
     if args.impl == "reference":
         run_reference(args)
     else:
