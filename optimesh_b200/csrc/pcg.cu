@@ -519,7 +519,7 @@ int pcg(om_handle* h, double rtol, int max_iter, int32_t* iters, double* relres,
 //   * coarse operators are Galerkin products P^T A P with piecewise-constant P: the weight
 //     between two aggregates is the number of fine edges between them (integers: exact in
 //     fp64 whatever the summation order), built by one radix sort + reduce-by-key per level;
-//   * damped Jacobi smoothing (omega 0.8), coarse corrections over-weighted by 1.6 (the usual
+//   * damped Jacobi smoothing (omega 0.9), coarse corrections over-weighted by 1.6 (the usual
 //     remedy for the poor approximation of piecewise-constant interpolation), the coarsest
 //     level (<= 256 unknowns) solved by 64 Jacobi sweeps in one block.
 // Every piece is a fixed symmetric linear operator, so plain PCG applies; every sum has a
@@ -527,7 +527,7 @@ int pcg(om_handle* h, double rtol, int max_iter, int32_t* iters, double* relres,
 // (scipy prototype, square meshes): 63 / 99 iterations at 40 k / 250 k vertices with a V(1,1)
 // cycle, 73 at 1 M with this V(2,2) cycle, against 578 / 1,420 / ~2,800 for Jacobi.
 constexpr int MG_COARSEST = 256;
-constexpr double MG_OMEGA = 0.8, MG_SCALE = 1.6;
+constexpr double MG_OMEGA = 0.9, MG_SCALE = 1.6;
 constexpr int MG_COARSE_SWEEPS = 64;
 
 struct MgLevel {
