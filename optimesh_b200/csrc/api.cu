@@ -277,13 +277,17 @@ int staged_h2d(om_handle* h, const HOST_T* src_host, DEV_T* dst_dev, size_t n, b
       if (sizeof(DEV_T) == sizeof(HOST_T)) {
         memcpy((void*)(pin + lo), (const void*)(in + lo), (hi - lo) * sizeof(DEV_T));
       } else {
-        bool o = false;
+        // branch-free so that the host compiler vectorises it: a value outside [0, 2^31) has
+        // a bit at or above position 31 (negative values have them all)
+        unsigned long long acc = 0ull;
+        const HOST_T* __restrict__ src = in;
+        DEV_T* __restrict__ dst = pin;
         for (size_t i = lo; i < hi; i++) {
-          const HOST_T v = in[i];
-          o |= (v < 0) || ((long long)v > 0x7fffffffll);
-          pin[i] = (DEV_T)v;
+          const unsigned long long v = (unsigned long long)(long long)src[i];
+          acc |= v;
+          dst[i] = (DEV_T)v;
         }
-        if (o) overflow = true;
+        if (acc >> 31) overflow = true;
       }
     });
     cudaMemcpyAsync(dst_dev + b, pin, cnt * sizeof(DEV_T), cudaMemcpyHostToDevice, stream);
