@@ -224,10 +224,16 @@ struct om_handle {
   int64_t n_step = 0, n_flip = 0;
 };
 
+// (A rank of a shared mesh may own no vertex at all -- a mesh of fewer than world x 2^21
+// vertices: its range-sized grids are empty, but it must enqueue the same kernels as the others,
+// the loop is a captured graph and the ranks meet in it.  Every kernel returns at once on an
+// empty range.)
 #define OM_LAUNCH(h, kernel, grid, block, ...)                         \
   do {                                                                 \
-    if ((grid) > 0) {                                                  \
-      kernel<<<(grid), (block), 0, (h)->stream>>>(__VA_ARGS__);        \
+    int _g = (int)(grid);                                              \
+    if (_g < 1 && (h)->sh) _g = 1;                                     \
+    if (_g > 0) {                                                      \
+      kernel<<<_g, (block), 0, (h)->stream>>>(__VA_ARGS__);            \
       (h)->launches++;                                                 \
     }                                                                  \
   } while (0)
@@ -235,8 +241,10 @@ struct om_handle {
 // the same with dynamic shared memory
 #define OM_LAUNCH_SMEM(h, kernel, grid, block, smem, ...)                  \
   do {                                                                    \
-    if ((grid) > 0) {                                                     \
-      kernel<<<(grid), (block), (smem), (h)->stream>>>(__VA_ARGS__);      \
+    int _g = (int)(grid);                                                 \
+    if (_g < 1 && (h)->sh) _g = 1;                                        \
+    if (_g > 0) {                                                         \
+      kernel<<<_g, (block), (smem), (h)->stream>>>(__VA_ARGS__);          \
       (h)->launches++;                                                    \
     }                                                                     \
   } while (0)

@@ -599,8 +599,8 @@ __global__ void __launch_bounds__(256)
 
 template <int D, int METHOD, bool CHECK>
 int launch_ring(om_handle* h, const StepParams& p, bool exact, bool part) {
-  const int B = OM_K1_BLOCK, G = om_grid(p.hi - p.lo, B);
-  if (G == 0) return OM_OK;
+  const int B = OM_K1_BLOCK, G = om_grid(std::max(p.hi - p.lo, 0), B);
+  if (G == 0 && !h->sh) return OM_OK;  // (a rank of a shared mesh enqueues it anyway: OM_LAUNCH)
   if (exact) {
     if (part)
       OM_LAUNCH(h, (k_step_ring<D, METHOD, true, CHECK, true>), G, B, p);
