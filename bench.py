@@ -224,6 +224,7 @@ def run_reference(args):
     # per vertex and step and core at these sizes (more on larger meshes: cache misses)
     budget_s = 120.0
     n_target = int(min(4.0e5, max(2.0e4, budget_s / (total * 12e-6))))
+    n_target = int(os.environ.get("OM_BENCH_REF_VERTICES", n_target))  # (tests: a small sample)
     v, dt, n, c, nb, workers = cpu_step_rate(method, omega, n_target, args.steps, args.warmup)
     sample = (f"{workers} replicas (one per host core) of a random disk mesh disk({nb}) (Qhull): "
               f"{n} vertices / {c} cells each, {args.steps} steps of {method} (omega={omega}) "
