@@ -90,7 +90,11 @@ int stage_threads() {
   static const int n = [] {
     const char* e = getenv("OM_STAGE_THREADS");
     const int hw = (int)std::thread::hardware_concurrency();
-    const int v = e ? atoi(e) : std::min(std::max(hw, 4), 16);
+    int v = e ? atoi(e) : std::min(std::max(hw, 4), 16);
+    // several processes on one host (one per GPU, torchrun sets LOCAL_WORLD_SIZE): they share
+    // the cores, 16 staging threads each would only fight for them
+    const char* lws = getenv("LOCAL_WORLD_SIZE");
+    if (!e && lws && atoi(lws) > 1) v = std::max(2, std::max(hw, 4) / atoi(lws));
     return std::max(1, std::min(v, 64));
   }();
   return n;
